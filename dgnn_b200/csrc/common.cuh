@@ -1,0 +1,63 @@
+// Shared helpers for the dgnn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dgnn_b200.h"
+
+namespace dgnn {
+
+extern thread_local char g_err[512];
+
+inline int fail(const char* what, const char* detail) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, detail);
+    return 1;
+}
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));
+    return 0;
+}
+
+#define DGNN_REQUIRE(cond, what)                                   \
+    do {                                                           \
+        if (!(cond)) return ::dgnn::fail(__func__, what);          \
+    } while (0)
+
+int sm_count();
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// h = relu?(x*scale + shift) applied on load ("producer affine on load")
+__device__ __forceinline__ float act(float x, float sc, float sh, bool relu) {
+    float y = fmaf(x, sc, sh);
+    return relu ? fmaxf(y, 0.f) : y;
+}
+
+}  // namespace dgnn

@@ -1,0 +1,373 @@
+"""Forward / backward schedule of the Static edge-filter network over the C-ABI kernels.
+
+Mirrors, layer by layer, what autograd does for ``SurfaceNet.forward`` /
+``inference_layer`` in ``learning/surfaceNetStaticEdgeFilters.py:196-227,323-355``, but with
+one fused kernel per layer (``dgnn_layer_fwd``), the norm + ReLU of layer ``l`` applied on load by
+layer ``l+1``, and a hand-scheduled atomic-free backward.  Host code is PyTorch for memory,
+streams and autograd plumbing only; all arithmetic on activations happens in ``libdgnn_b200.so``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from ._lib import call, lib, ptr
+from .graph import EllGraph, pad4
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------- parameter packing
+
+
+@dataclass
+class NormSpec:
+    mode: int                    # 0 = BatchNorm1d, 1 = PyG graph LayerNorm
+    weight: torch.Tensor
+    bias: torch.Tensor
+    running_mean: Optional[torch.Tensor] = None
+    running_var: Optional[torch.Tensor] = None
+    num_batches_tracked: Optional[torch.Tensor] = None
+    eps: float = 1e-5
+    momentum: float = 0.1
+
+
+@dataclass
+class ConvSpec:
+    f_in: int                    # unpadded
+    f_out: int
+    w_i: torch.Tensor            # [f_out, f_in]
+    w_j: torch.Tensor
+    b_j: torch.Tensor
+    w_e: Optional[torch.Tensor]  # [f_in, fe] or None (edge_convs == 0)
+    b_e: Optional[torch.Tensor]
+    norm: Optional[NormSpec]
+
+
+@dataclass
+class NetSpec:
+    convs: List[ConvSpec]
+    decoder: int                                  # 0, 1, 2
+    dec0_w: Optional[torch.Tensor] = None
+    dec0_b: Optional[torch.Tensor] = None
+    dec_norm: Optional[NormSpec] = None
+    dec3_w: Optional[torch.Tensor] = None
+    dec3_b: Optional[torch.Tensor] = None
+    out_dim: int = 2
+
+
+def _pad2(w: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    if w.shape == (rows, cols):
+        return w
+    out = torch.zeros((rows, cols), dtype=w.dtype, device=w.device)
+    out[:w.shape[0], :w.shape[1]] = w
+    return out
+
+
+def _pad1(v: torch.Tensor, n: int) -> torch.Tensor:
+    if v.shape[0] == n:
+        return v
+    out = torch.zeros(n, dtype=v.dtype, device=v.device)
+    out[:v.shape[0]] = v
+    return out
+
+
+@dataclass
+class PackedConv:
+    f_in: int          # padded
+    f_out: int
+    fe: int            # padded (0 = none)
+    wt_cat: torch.Tensor   # [2 f_in, f_out]
+    w_cat: torch.Tensor    # [f_out, 2 f_in]
+    bias: torch.Tensor
+    w_e: Optional[torch.Tensor]
+    b_e: Optional[torch.Tensor]
+
+
+def pack_conv(c: ConvSpec, fe_p: int) -> PackedConv:
+    """Concatenate / transpose / zero-pad one layer's weights into the kernel layouts.
+    (Tiny per-step glue on the weights; activations never pass through torch ops.)"""
+    fi = pad4(c.f_in)
+    if c.f_out % 4:
+        raise NotImplementedError("hidden widths must be multiples of 4 (got %d)" % c.f_out)
+    wj = _pad2(c.w_j.detach(), c.f_out, fi)
+    wi = _pad2(c.w_i.detach(), c.f_out, fi)
+    w_cat = torch.cat([wj, wi], dim=1).contiguous()
+    wt_cat = w_cat.t().contiguous()
+    w_e = b_e = None
+    if c.w_e is not None:
+        w_e = _pad2(c.w_e.detach(), fi, fe_p).contiguous()
+        b_e = _pad1(c.b_e.detach(), fi).contiguous()
+    return PackedConv(fi, c.f_out, fe_p if c.w_e is not None else 0, wt_cat, w_cat, c.b_j.detach().contiguous(),
+                      w_e, b_e)
+
+
+# --------------------------------------------------------------------------- normalisation helpers
+
+
+@dataclass
+class Affine:
+    scale: torch.Tensor
+    shift: torch.Tensor
+    mean: Optional[torch.Tensor] = None
+    rstd: Optional[torch.Tensor] = None
+
+
+def eval_affine(n: NormSpec, c: int, dev) -> Affine:
+    if n.mode != 0:
+        raise NotImplementedError("graph LayerNorm has no running statistics; it is evaluated with batch statistics")
+    scale = torch.empty(c, dtype=torch.float32, device=dev)
+    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    call("dgnn_norm_eval_affine", ptr(n.weight), ptr(n.bias), ptr(n.running_mean), ptr(n.running_var),
+         float(n.eps), c, ptr(scale), ptr(shift), _stream())
+    return Affine(scale, shift)
+
+
+def batch_affine(n: NormSpec, stats: torch.Tensor, n_rows: int, c: int, dev, update_running: bool) -> Affine:
+    buf = torch.empty((4, c), dtype=torch.float32, device=dev)
+    rm = n.running_mean if (update_running and n.mode == 0) else None
+    rv = n.running_var if (update_running and n.mode == 0) else None
+    call("dgnn_norm_finalize", ptr(stats), stats.shape[0], n_rows, c, ptr(n.weight), ptr(n.bias), float(n.eps),
+         float(n.momentum), n.mode, ptr(rm), ptr(rv), ptr(buf[0]), ptr(buf[1]), ptr(buf[2]), ptr(buf[3]), _stream())
+    if rm is not None and n.num_batches_tracked is not None:
+        n.num_batches_tracked += 1
+    return Affine(buf[0], buf[1], buf[2], buf[3])
+
+
+# --------------------------------------------------------------------------- forward
+
+
+@dataclass
+class Saved:
+    x0: torch.Tensor = None
+    z: List[torch.Tensor] = field(default_factory=list)        # pre-norm outputs per conv layer
+    agg: List[torch.Tensor] = field(default_factory=list)
+    aff: List[Optional[Affine]] = field(default_factory=list)  # norm affine per conv layer
+    packed: List[PackedConv] = field(default_factory=list)
+    z_d: Optional[torch.Tensor] = None
+    aff_d: Optional[Affine] = None
+    graphs: List[EllGraph] = field(default_factory=list)
+
+
+def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGraph], pk_wt, pk_bias, w_e, b_e, fe,
+               out_aff: Optional[Affine], relu_out: bool, n_tgt, f_in, f_out, want_agg, want_stats):
+    dev = x_in.device
+    out = torch.empty((n_tgt, f_out), dtype=torch.float32, device=dev)
+    agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if want_agg else None
+    stats = None
+    if want_stats:
+        grid = lib().dgnn_layer_grid(f_in, f_out)
+        stats = torch.empty((grid, 2, f_out), dtype=torch.float64, device=dev)
+    call("dgnn_layer_fwd", ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+         int(relu_in), ptr(g.nbr) if g is not None else None, ptr(g.ea_in) if (g is not None and fe) else None, fe,
+         ptr(w_e), ptr(b_e), ptr(pk_wt), ptr(pk_bias),
+         ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None, int(relu_out),
+         n_tgt, f_in, f_out, ptr(out), ptr(agg), ptr(stats), _stream())
+    return out, agg, stats
+
+
+def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: bool, save: bool):
+    """Run all conv layers + decoder.  ``x0``: float32[n_src0, pad4(F0)] in the graphs' row order.
+    Returns ``(logits, Saved or None)``.  In training mode the norms use batch statistics
+    (and update the running buffers); in eval mode the running-statistic affine + ReLU is fused
+    into each layer's epilogue."""
+    dev = x0.device
+    sv = Saved() if save else None
+    fe_p = graphs[0].fe
+    h = x0
+    in_aff: Optional[Affine] = None
+    relu_in = False
+    if save:
+        sv.x0 = x0
+        sv.graphs = graphs
+    L = len(spec.convs)
+    batch_stats = training or any(c.norm is not None and c.norm.mode == 1 for c in spec.convs)
+    for l, c in enumerate(spec.convs):
+        g = graphs[l]
+        pk = pack_conv(c, fe_p)
+        if h.shape[1] != pk.f_in:
+            raise ValueError("layer %d expects %d input features, got %d" % (l, pk.f_in, h.shape[1]))
+        if c.norm is None:
+            raise NotImplementedError("normalization must be 'b' or 'l' (the reference crashes otherwise, Static:218)")
+        if batch_stats:
+            z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None, False,
+                                       g.n_tgt, pk.f_in, pk.f_out, save, True)
+            aff = batch_affine(c.norm, stats, g.n_tgt, pk.f_out, dev, update_running=training)
+            if save:
+                sv.z.append(z); sv.agg.append(agg); sv.aff.append(aff); sv.packed.append(pk)
+            h, in_aff, relu_in = z, aff, True
+        else:
+            aff = eval_affine(c.norm, pk.f_out, dev)
+            h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
+                                 g.n_tgt, pk.f_in, pk.f_out, False, False)
+            in_aff, relu_in = None, False
+    n_out = graphs[-1].n_tgt
+    f_last = spec.convs[-1].f_out
+    if spec.decoder == 0:
+        out = torch.empty((n_out, f_last), dtype=torch.float32, device=dev)
+        call("dgnn_affine_relu", ptr(h), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+             int(relu_in), n_out, f_last, ptr(out), _stream())
+        return out, sv
+    if spec.decoder == 1:
+        w, b = spec.dec0_w.detach().contiguous(), spec.dec0_b.detach().contiguous()
+        out = torch.empty((n_out, spec.out_dim), dtype=torch.float32, device=dev)
+        call("dgnn_rowdot_fwd", ptr(h), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+             int(relu_in), ptr(w), ptr(b), n_out, f_last, spec.out_dim, ptr(out), _stream())
+        return out, sv
+    # decoder == 2: Linear -> norm -> ReLU -> Linear
+    f_d = spec.dec0_w.shape[0]
+    if f_d % 4:
+        raise NotImplementedError("decoder hidden width must be a multiple of 4")
+    wt = spec.dec0_w.detach().t().contiguous()
+    b0 = spec.dec0_b.detach().contiguous()
+    dn = spec.dec_norm
+    if batch_stats:
+        z_d, _, stats = _layer_fwd(h, in_aff, relu_in, None, wt, b0, None, None, 0, None, False, n_out, f_last, f_d,
+                                   False, True)
+        aff_d = batch_affine(dn, stats, n_out, f_d, dev, update_running=training)
+        hd, hd_aff, hd_relu = z_d, aff_d, True
+        if save:
+            sv.z_d, sv.aff_d = z_d, aff_d
+    else:
+        aff_d = eval_affine(dn, f_d, dev)
+        hd, _, _ = _layer_fwd(h, in_aff, relu_in, None, wt, b0, None, None, 0, aff_d, True, n_out, f_last, f_d,
+                              False, False)
+        hd_aff, hd_relu = None, False
+    w3, b3 = spec.dec3_w.detach().contiguous(), spec.dec3_b.detach().contiguous()
+    out = torch.empty((n_out, spec.out_dim), dtype=torch.float32, device=dev)
+    call("dgnn_rowdot_fwd", ptr(hd), ptr(hd_aff.scale) if hd_aff else None, ptr(hd_aff.shift) if hd_aff else None,
+         int(hd_relu), ptr(w3), ptr(b3), n_out, f_d, spec.out_dim, ptr(out), _stream())
+    return out, sv
+
+
+# --------------------------------------------------------------------------- backward
+
+
+def _reduce(partials: torch.Tensor) -> torch.Tensor:
+    """Sum double partials [P, len] -> float32[len]."""
+    out = torch.empty(partials.shape[1], dtype=torch.float32, device=partials.device)
+    call("dgnn_reduce_partials", ptr(partials), partials.shape[0], partials.shape[1], ptr(out), _stream())
+    return out
+
+
+def _norm_coeffs(n: NormSpec, aff: Affine, s1, s2, n_rows, c):
+    buf = torch.empty((3, c), dtype=torch.float32, device=s1.device)
+    call("dgnn_norm_bwd_coeffs", ptr(s1), ptr(s2), n_rows, c, ptr(n.weight), ptr(aff.rstd), n.mode,
+         ptr(buf[0]), ptr(buf[1]), ptr(buf[2]), _stream())
+    return buf[0], buf[1], buf[2]
+
+
+def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, in_aff, relu_in, n_tgt, f_in, f_out):
+    """dz . W (-> d_agg, d_self, db) and dz^T . [agg | h] (-> dW_cat)."""
+    dev = dy.device
+    k_total = 2 * f_in if g is not None else f_in
+    gq, aq, bq = coeffs
+    d_self = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev)
+    d_agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if g is not None else None
+    grid = lib().dgnn_layer_grid(f_in, f_out)
+    db_p = torch.empty((grid, f_out), dtype=torch.float64, device=dev)
+    call("dgnn_dense_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(w_cat),
+         ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, k_total, ptr(d_agg), ptr(d_self), ptr(db_p),
+         _stream())
+    db = _reduce(db_p)
+    splits = lib().dgnn_dw_splits(f_out, k_total)
+    dw_p = torch.empty((splits, f_out, k_total), dtype=torch.float32, device=dev)
+    call("dgnn_dw_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(agg), ptr(x_in),
+         ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None, int(relu_in), n_tgt, f_in,
+         f_out, k_total, ptr(dw_p), _stream())
+    dw = torch.empty((f_out, k_total), dtype=torch.float32, device=dev)
+    call("dgnn_reduce_partials_f32", ptr(dw_p), splits, f_out * k_total, ptr(dw), _stream())
+    return d_agg, d_self, db, dw
+
+
+def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
+    """Gradients of every parameter given ``dout`` = dL/d(output of ``forward``).
+    Returns a dict name -> grad keyed like ``NetSpec`` fields (``convs.{l}.w_i`` ...)."""
+    dev = dout.device
+    st = _stream()
+    grads = {}
+    L = len(spec.convs)
+    n_out = sv.graphs[-1].n_tgt
+    f_last = spec.convs[-1].f_out
+    zL, affL = sv.z[-1], sv.aff[-1]
+    small = lib().dgnn_small_grid()
+    dout = dout.contiguous()
+    # ---- decoder
+    if spec.decoder == 0:
+        dy = torch.empty((n_out, f_last), dtype=torch.float32, device=dev)
+        part = torch.empty((small, 2 * f_last), dtype=torch.float64, device=dev)
+        call("dgnn_act_bwd", ptr(dout), ptr(zL), ptr(affL.scale), ptr(affL.shift), ptr(affL.mean), ptr(affL.rstd), 1,
+             n_out, f_last, ptr(dy), ptr(part), st)
+        r = _reduce(part)
+        s1, s2 = r[:f_last], r[f_last:]
+    elif spec.decoder == 1:
+        od = spec.out_dim
+        dy = torch.empty((n_out, f_last), dtype=torch.float32, device=dev)
+        part = torch.empty((small, od * f_last + od + 2 * f_last), dtype=torch.float64, device=dev)
+        call("dgnn_rowdot_bwd", ptr(dout), ptr(zL), ptr(affL.scale), ptr(affL.shift), ptr(affL.mean), ptr(affL.rstd), 1,
+             ptr(spec.dec0_w.detach().contiguous()), n_out, f_last, od, ptr(dy), ptr(part), st)
+        r = _reduce(part)
+        grads["dec0_w"] = r[:od * f_last].view(od, f_last)
+        grads["dec0_b"] = r[od * f_last:od * f_last + od]
+        s1, s2 = r[od * f_last + od:od * f_last + od + f_last], r[od * f_last + od + f_last:]
+    else:
+        od = spec.out_dim
+        f_d = spec.dec0_w.shape[0]
+        dy_d = torch.empty((n_out, f_d), dtype=torch.float32, device=dev)
+        part = torch.empty((small, od * f_d + od + 2 * f_d), dtype=torch.float64, device=dev)
+        affd = sv.aff_d
+        call("dgnn_rowdot_bwd", ptr(dout), ptr(sv.z_d), ptr(affd.scale), ptr(affd.shift), ptr(affd.mean), ptr(affd.rstd),
+             1, ptr(spec.dec3_w.detach().contiguous()), n_out, f_d, od, ptr(dy_d), ptr(part), st)
+        r = _reduce(part)
+        grads["dec3_w"] = r[:od * f_d].view(od, f_d)
+        grads["dec3_b"] = r[od * f_d:od * f_d + od]
+        s1d, s2d = r[od * f_d + od:od * f_d + od + f_d], r[od * f_d + od + f_d:]
+        grads["dec_norm_w"], grads["dec_norm_b"] = s2d, s1d
+        coeffs = _norm_coeffs(spec.dec_norm, affd, s1d, s2d, n_out, f_d)
+        _, dh, db0, dw0 = _dense_and_dw(dy_d, sv.z_d, coeffs, affd, spec.dec0_w.detach().contiguous(), None, None, zL,
+                                        affL, True, n_out, f_last, f_d)
+        grads["dec0_w"], grads["dec0_b"] = dw0, db0
+        dy = dh  # in place: dy = relu'(y_L) * dh
+        part = torch.empty((small, 2 * f_last), dtype=torch.float64, device=dev)
+        call("dgnn_act_bwd", ptr(dh), ptr(zL), ptr(affL.scale), ptr(affL.shift), ptr(affL.mean), ptr(affL.rstd), 1,
+             n_out, f_last, ptr(dy), ptr(part), st)
+        r = _reduce(part)
+        s1, s2 = r[:f_last], r[f_last:]
+    # ---- conv layers, last to first
+    for l in range(L - 1, -1, -1):
+        c, pk, g, aff = spec.convs[l], sv.packed[l], sv.graphs[l], sv.aff[l]
+        grads["convs.%d.norm_w" % l], grads["convs.%d.norm_b" % l] = s2, s1
+        coeffs = _norm_coeffs(c.norm, aff, s1, s2, g.n_tgt, pk.f_out)
+        x_in = sv.z[l - 1] if l > 0 else sv.x0
+        in_aff = sv.aff[l - 1] if l > 0 else None
+        relu_in = l > 0
+        d_agg, d_self, db, dw = _dense_and_dw(dy, sv.z[l], coeffs, aff, pk.w_cat, g, sv.agg[l], x_in, in_aff, relu_in,
+                                              g.n_tgt, pk.f_in, pk.f_out)
+        grads["convs.%d.b_j" % l] = db
+        grads["convs.%d.w_j" % l] = dw[:, :c.f_in]
+        grads["convs.%d.w_i" % l] = dw[:, pk.f_in:pk.f_in + c.f_in]
+        need_prev = l > 0
+        if need_prev or pk.fe:
+            grid = lib().dgnn_gather_bwd_grid(pk.f_in)
+            plen = pk.f_in * (pk.fe + 1) + 2 * pk.f_in
+            part = torch.empty((grid, plen), dtype=torch.float64, device=dev)
+            dy_prev = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev) if need_prev else None
+            call("dgnn_gather_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.ea_own) if pk.fe else None, pk.fe,
+                 ptr(pk.w_e), ptr(pk.b_e), ptr(x_in), ptr(in_aff.scale) if in_aff else None,
+                 ptr(in_aff.shift) if in_aff else None, ptr(in_aff.mean) if in_aff else None,
+                 ptr(in_aff.rstd) if in_aff else None, int(relu_in), g.n_src, g.n_tgt, pk.f_in, ptr(dy_prev),
+                 ptr(part), st)
+            r = _reduce(part)
+            if pk.fe:
+                fe_u = c.w_e.shape[1]
+                grads["convs.%d.w_e" % l] = r[:pk.f_in * pk.fe].view(pk.f_in, pk.fe)[:c.f_in, :fe_u]
+                grads["convs.%d.b_e" % l] = r[pk.f_in * pk.fe:pk.f_in * (pk.fe + 1)][:c.f_in]
+            if need_prev:
+                s1 = r[pk.f_in * (pk.fe + 1):pk.f_in * (pk.fe + 1) + pk.f_in]
+                s2 = r[pk.f_in * (pk.fe + 1) + pk.f_in:]
+                dy = dy_prev
+    return grads

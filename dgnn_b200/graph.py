@@ -1,0 +1,202 @@
+"""Graph loader re-layout: the reference's ``edge_index`` / ``edge_attr``
+(``processing/data.py:434-439,512-519``; ``run.py:211-213``) to the device-resident ELL-4 layout
+the fused kernels consume.
+
+``EllGraph`` holds, for one (bipartite) message-passing step with ``n_src`` source rows and
+``n_tgt <= n_src`` target rows (targets are the first ``n_tgt`` sources, PyG convention,
+``surfaceNetStaticEdgeFilters.py:217``):
+
+* ``nbr   int32[n_tgt,4]``     source row of the k-th in-edge (-1 = none)
+* ``ea_in float32[n_tgt,4,Fe]`` that edge's attributes (incoming order, forward)
+* ``onbr  int32[n_src,4]``     target row of the k-th out-edge (-1 = none)
+* ``ea_own float32[n_src,4,Fe]`` that edge's attributes (own-slot order, backward)
+
+For a whole Delaunay graph in the reference file layout (row ``4i+k`` = facet ``k`` of cell ``i``)
+the table is the adjacency itself, ``onbr == nbr`` by symmetry, and the incoming edge row is found
+through the reverse-facet slot; cells are renumbered by a locality order (Morton code of the cell
+centroid when positions are known, reverse Cuthill-McKee of the adjacency otherwise).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def pad_cols(t: torch.Tensor, width: int) -> torch.Tensor:
+    """Zero-pad the last dim of a 2-D float tensor to ``width`` columns (contiguous)."""
+    if t.shape[1] == width:
+        return t.contiguous()
+    out = torch.zeros((t.shape[0], width), dtype=t.dtype, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out
+
+
+@dataclass
+class EllGraph:
+    n_src: int
+    n_tgt: int
+    fe: int                                  # padded edge feature width (0 = no edge features)
+    nbr: torch.Tensor
+    ea_in: Optional[torch.Tensor]
+    onbr: Optional[torch.Tensor] = None
+    ea_own: Optional[torch.Tensor] = None
+    perm: Optional[torch.Tensor] = None      # int32[n]: new -> old  (None = caller order)
+    inv: Optional[torch.Tensor] = None       # int32[n]: old -> new
+
+    def permute_rows(self, x: torch.Tensor) -> torch.Tensor:
+        """Rows of ``x`` (caller order, width multiple of 4) in internal order."""
+        if self.perm is None:
+            return x.contiguous()
+        out = torch.empty_like(x)
+        call("dgnn_gather_rows", ptr(x), ptr(self.perm), x.shape[0], x.shape[1], ptr(out), _stream())
+        return out
+
+    def unpermute_rows(self, y: torch.Tensor) -> torch.Tensor:
+        """Rows of ``y`` (internal order) back in caller order."""
+        if self.perm is None:
+            return y
+        if y.shape[1] % 4 == 0:
+            out = torch.empty_like(y)
+            call("dgnn_gather_rows", ptr(y), ptr(self.inv), y.shape[0], y.shape[1], ptr(out), _stream())
+            return out
+        return y.index_select(0, self.inv.long())
+
+
+def is_reference_layout(edge_index: torch.Tensor, n: int) -> bool:
+    """True if ``edge_index`` is the reference file layout: E == 4n and row 4i+k is owned by i."""
+    if edge_index.shape[1] != 4 * n or n == 0:
+        return False
+    own = edge_index[0].view(n, 4)
+    return bool((own == torch.arange(n, device=own.device, dtype=own.dtype)[:, None]).all())
+
+
+def locality_order(edge_index_cpu: Optional[torch.Tensor], n: int, pos: Optional[torch.Tensor], device,
+                   bits: int = 10) -> Optional[torch.Tensor]:
+    """``perm[new] = old`` as int32 on ``device``: Morton order of ``pos`` if given, else reverse
+    Cuthill-McKee of the adjacency (host, scipy), else None."""
+    if pos is not None:
+        p = pos.to(device=device, dtype=torch.float32).contiguous()
+        lo = p.min(dim=0).values.cpu().numpy().astype(np.float32)
+        hi = p.max(dim=0).values.cpu().numpy().astype(np.float32)
+        codes = torch.empty(n, dtype=torch.int64, device=device)
+        call("dgnn_morton_codes", ptr(p), n, lo.ctypes.data, hi.ctypes.data, bits, ptr(codes), _stream())
+        # stable sort of the codes (graph preparation, not the hot path)
+        return torch.sort(codes, stable=True).indices.to(torch.int32)
+    if edge_index_cpu is not None:
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+        ei = edge_index_cpu.numpy()
+        a = sp.csr_matrix((np.ones(ei.shape[1], dtype=np.int8), (ei[1], ei[0])), shape=(n, n))
+        perm = reverse_cuthill_mckee(a, symmetric_mode=True)
+        return torch.from_numpy(np.ascontiguousarray(perm.astype(np.int32))).to(device)
+    return None
+
+
+def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], n: int, device,
+                     pos: Optional[torch.Tensor] = None, order: str = "auto",
+                     need_backward: bool = True) -> EllGraph:
+    """Whole-graph layout (inference, or training on whole graphs).
+
+    ``order``: "auto" (Morton if ``pos`` else RCM), "morton", "rcm", "none".
+    """
+    dev = torch.device(device)
+    _lib.check_device(dev.index or 0)
+    fe = 0 if edge_attr is None else pad4(edge_attr.shape[1])
+    if not is_reference_layout(edge_index, n):
+        g = build_from_edges(edge_index.to(dev), None, edge_attr, n, n, dev, need_backward)
+        return g
+    st = _stream()
+    adj = edge_index.t().to(torch.int32).contiguous().to(dev)  # [4n,2] == adjacencies.npz layout
+    nbr0 = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    rslot = torch.empty((n, 4), dtype=torch.uint8, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("dgnn_ell_from_adjacency", ptr(adj), n, ptr(nbr0), ptr(rslot), ptr(err), st)
+    code = int(err.item())
+    if code == 2:  # not symmetric: the generic edge-list builder handles it
+        return build_from_edges(edge_index.to(dev), None, edge_attr, n, n, dev, need_backward)
+    if code != 0:
+        raise _lib.DgnnError("dgnn_ell_from_adjacency: malformed adjacency (code %d)" % code)
+    perm = None
+    if order != "none":
+        use_pos = pos if order in ("auto", "morton") else None
+        if order == "morton" and pos is None:
+            raise ValueError("order='morton' needs positions")
+        ei_cpu = edge_index.cpu() if (use_pos is None and order in ("auto", "rcm")) else None
+        perm = locality_order(ei_cpu, n, use_pos, dev)
+    if perm is not None:
+        inv = torch.empty_like(perm)
+        inv[perm.long()] = torch.arange(n, dtype=torch.int32, device=dev)
+        nbr = torch.empty_like(nbr0)
+        call("dgnn_perm_apply_ell", ptr(nbr0), ptr(perm), ptr(inv), n, ptr(nbr), st)
+    else:
+        inv = None
+        nbr = nbr0
+    ea_in = ea_own = None
+    if edge_attr is not None:
+        ea = pad_cols(edge_attr.to(dev, dtype=torch.float32), fe)
+        ea_in = torch.empty((n, 4, fe), dtype=torch.float32, device=dev)
+        if need_backward:
+            ea_own = torch.empty((n, 4, fe), dtype=torch.float32, device=dev) if perm is not None else ea.view(n, 4, fe)
+        call("dgnn_edge_relayout", ptr(ea), ptr(nbr0), ptr(rslot), ptr(perm), n, fe, ptr(ea_in),
+             ptr(ea_own) if (need_backward and perm is not None) else None, st)
+    return EllGraph(n_src=n, n_tgt=n, fe=fe, nbr=nbr, ea_in=ea_in, onbr=nbr if need_backward else None,
+                    ea_own=ea_own, perm=perm, inv=inv)
+
+
+def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edge_attr: Optional[torch.Tensor],
+                     n_src: int, n_tgt: int, device, need_backward: bool = True) -> EllGraph:
+    """Generic (bipartite / sampled) layout from an edge list in local ids
+    (``data.batch_adjs[i] = (edge_index, e_id, size)``, ``surfaceNetStaticEdgeFilters.py:215-217``).
+    ``edge_attr`` rows are selected by ``e_id`` (all edges in order when ``e_id`` is None)."""
+    dev = torch.device(device)
+    _lib.check_device(dev.index or 0)
+    st = _stream()
+    ei = edge_index.to(dev, dtype=torch.int64).contiguous()
+    E = ei.shape[1]
+    fe = 0 if edge_attr is None else pad4(edge_attr.shape[1])
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def one_side(src, tgt, rows):
+        nb = torch.empty((rows, 4), dtype=torch.int32, device=dev)
+        eid = torch.empty((rows, 4), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(rows, dtype=torch.int32, device=dev)
+        call("dgnn_ell_build", ptr(src), ptr(tgt), E, rows, ptr(nb), ptr(eid), ptr(cnt), ptr(err), st)
+        return nb, eid
+
+    nbr, eid_in = one_side(ei[0], ei[1], n_tgt)
+    onbr = eid_out = None
+    if need_backward:
+        onbr, eid_out = one_side(ei[1], ei[0], n_src)
+    code = int(err.item())
+    if code == 3:
+        raise _lib.DgnnError("a cell has more than 4 facet neighbours: not a Delaunay cell graph "
+                             "(self-loops / cliques are not supported by the ELL-4 layout)")
+    if code != 0:
+        raise _lib.DgnnError("dgnn_ell_build: edge endpoint out of range (code %d)" % code)
+    ea_in = ea_own = None
+    if edge_attr is not None:
+        if e_id is not None:
+            rows = edge_attr[e_id.to(edge_attr.device)]
+        else:
+            rows = edge_attr
+        ea = pad_cols(rows.to(dev, dtype=torch.float32), fe)
+        ea_in = torch.empty((n_tgt, 4, fe), dtype=torch.float32, device=dev)
+        call("dgnn_gather_rows", ptr(ea), ptr(eid_in), n_tgt * 4, fe, ptr(ea_in), st)
+        if need_backward:
+            ea_own = torch.empty((n_src, 4, fe), dtype=torch.float32, device=dev)
+            call("dgnn_gather_rows", ptr(ea), ptr(eid_out), n_src * 4, fe, ptr(ea_own), st)
+    return EllGraph(n_src=n_src, n_tgt=n_tgt, fe=fe, nbr=nbr, ea_in=ea_in, onbr=onbr, ea_own=ea_own)

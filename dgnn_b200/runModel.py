@@ -1,0 +1,137 @@
+"""Loss, regulariser, labels and optimiser step of ``learning/runModel.py`` on the B200 kernels.
+
+``cell_loss`` is ``Trainer.calcLossAndOA``'s cell branch (``runModel.py:163-211``): per-cell
+``F.kl_div(log_softmax(z), y).sum(1)`` weighted by the raw cell volume (or sqrt / log1p of it),
+normalised by the weight sum.  It is an autograd node, so a reference ``Trainer`` may also keep
+its own torch loss on the logits this package returns.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import call, lib, ptr
+
+_WEIGHT_MODE = {None: 0, "none": 0, "sqrt": 1, "log": 2}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _strided(t: torch.Tensor, col0: int):
+    """(tensor kept alive, element stride) for a float32 2-D/1-D device tensor column view."""
+    if t.dim() == 1:
+        return t, 1
+    return t, t.stride(0)
+
+
+class _KLCellLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, gt, weight, mode):
+        n = logits.shape[0]
+        dev = logits.device
+        logits = logits.contiguous()
+        grid = lib().dgnn_small_grid()
+        part = torch.empty((grid, 2), dtype=torch.float64, device=dev)
+        w_ptr = ptr(weight) if weight is not None else None
+        ws = weight.stride(0) if weight is not None else 0
+        call("dgnn_kl_loss_fwd", ptr(logits), ptr(gt), gt.stride(0), w_ptr, ws, mode, n, ptr(part), _stream())
+        sums = torch.empty(3, dtype=torch.float32, device=dev)
+        call("dgnn_kl_loss_finalize", ptr(part), grid, ptr(sums), _stream())
+        ctx.save_for_backward(logits, gt, sums)
+        ctx.weight, ctx.mode = weight, mode
+        ctx.mark_non_differentiable(sums)
+        return sums[0].clone(), sums
+
+    @staticmethod
+    def backward(ctx, gout, _gs):
+        logits, gt, sums = ctx.saved_tensors
+        weight = ctx.weight
+        d = torch.empty_like(logits)
+        gout = gout.contiguous().to(torch.float32)
+        call("dgnn_kl_loss_bwd", ptr(logits), ptr(gt), gt.stride(0), ptr(weight) if weight is not None else None,
+             weight.stride(0) if weight is not None else 0, ctx.mode, logits.shape[0], ptr(sums), ptr(gout), ptr(d),
+             _stream())
+        return d, None, None, None
+
+
+def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False):
+    """``Trainer.calcLossAndOA`` (kl): ``batch_gt[:, :2]`` targets, ``batch_x[:, 0]`` raw volume.
+    ``batch_gt`` / ``batch_x`` may live on the host; they are moved to ``logits.device``."""
+    if clf.training.loss != "kl":
+        raise NotImplementedError("only the 'kl' loss of the shipped configs has a CUDA kernel (got %r)"
+                                  % clf.training.loss)
+    dev = logits.device
+    gt = batch_gt.to(dev, dtype=torch.float32)
+    if gt.stride(1) != 1:
+        gt = gt.contiguous()
+    if clf.regularization.cell_type:
+        w = batch_x.to(dev, dtype=torch.float32)
+        w = w[:, 0] if w.dim() == 2 else w
+        mode = _WEIGHT_MODE[clf.regularization.cell_norm]
+    else:
+        w, mode = None, 3
+    loss, sums = _KLCellLoss.apply(logits, gt, w, mode)
+    return (loss, sums) if return_sums else loss
+
+
+def edge_regularization(logits, edge_index, edge_weight):
+    """``Trainer.calcRegularization`` forward value (``runModel.py:109-160``); disabled in every
+    shipped config (``edge_epoch: null``), so only the value (no gradient) is provided."""
+    dev = logits.device
+    ei = edge_index.to(dev, dtype=torch.int64).contiguous()
+    grid = lib().dgnn_small_grid()
+    part = torch.empty((grid, 2), dtype=torch.float64, device=dev)
+    call("dgnn_edge_reg_fwd", ptr(logits.contiguous()), ptr(ei[0]), ptr(ei[1]), ei.shape[1], ptr(part), _stream())
+    return (part[:, 0].sum() * (edge_weight / ei.shape[1])).to(torch.float32)
+
+
+def labels(logits):
+    """``processing/generate_mesh.py:75``: argmax(log_softmax), ties -> 0; uint8 on the device."""
+    out = torch.empty(logits.shape[0], dtype=torch.uint8, device=logits.device)
+    call("dgnn_argmax_labels", ptr(logits.contiguous()), logits.shape[0], logits.shape[1], ptr(out), _stream())
+    return out
+
+
+def interface_facets(labels_finite, nfacets):
+    """``processing/generate_mesh.py:94-105``: mask of facets whose two cells' labels differ
+    (the infinite cell, -1, forced outside)."""
+    nf = nfacets.to(labels_finite.device, dtype=torch.int32).contiguous()
+    flag = torch.empty(nf.shape[0], dtype=torch.uint8, device=labels_finite.device)
+    call("dgnn_interface_facets", ptr(labels_finite), labels_finite.shape[0], ptr(nf), nf.shape[0], ptr(flag), _stream())
+    return flag
+
+
+class Adam(torch.optim.Optimizer):
+    """``torch.optim.Adam(params, lr)`` with the reference's defaults (``runModel.py:290``), all
+    parameter tensors updated by ONE kernel launch (``dgnn_adam_multi``)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._step = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self._step += 1
+        for group in self.param_groups:
+            rows, max_n = [], 0
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                st["_g"] = g  # keep alive until the launch is enqueued
+                rows.append([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                             p.numel()])
+                max_n = max(max_n, p.numel())
+            if not rows:
+                continue
+            dev = group["params"][0].device
+            table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+            b1, b2 = group["betas"]
+            call("dgnn_adam_multi", ptr(table), len(rows), max_n, float(group["lr"]), float(b1), float(b2),
+                 float(group["eps"]), self._step, _stream())
+            group["_table"] = table

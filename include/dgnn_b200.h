@@ -1,0 +1,207 @@
+/*
+ * dgnn_b200 — C ABI of the B200-native DGNN cell-classification hot path.
+ *
+ * Drop-in boundary: these are the entry points a host binding (ctypes here; see
+ * INTEGRATION.md) calls in place of the library kernels the reference reaches through
+ * PyTorch / PyG / torch_scatter.  Every function
+ *   - returns 0 on success, non-zero on failure (message: dgnn_last_error()),
+ *   - takes raw DEVICE pointers unless a parameter says "host",
+ *   - allocates nothing: the caller passes outputs and workspaces,
+ *   - enqueues on the given cudaStream_t (passed as void*) and does not synchronise.
+ * All feature matrices are row-major float32 with row length a multiple of 4 floats and a
+ * 16-byte aligned base.  Indices are int32 on the device (int64 only where the reference's
+ * own tensors are handed in unchanged).
+ *
+ * Reference interfaces replaced (file:line under /root/reference):
+ *   learning/surfaceNetStaticEdgeFilters.py:66-96   SAGEConv.forward/message (+ PyG propagate,
+ *                                                   torch_scatter mean)        -> dgnn_layer_fwd / _bwd_*
+ *   learning/surfaceNetStaticEdgeFilters.py:116-123 BatchNorm / LayerNorm      -> dgnn_norm_finalize (+ affine-on-load)
+ *   learning/surfaceNetStaticEdgeFilters.py:180-187 decoder                    -> dgnn_layer_fwd(no gather) + dgnn_rowdot_*
+ *   learning/surfaceNetUpdatedEdgeFilters.py:147-176 SAGEConv (updated filters) -> dgnn_layer_fwd with chained edge state
+ *   learning/runModel.py:163-211                    calcLossAndOA (kl)         -> dgnn_kl_loss_fwd / _bwd
+ *   learning/runModel.py:109-160                    calcRegularization         -> dgnn_edge_reg_fwd
+ *   learning/runModel.py:290,282                    Adam step                  -> dgnn_adam_step
+ *   processing/data.py:434-439                      adjacency -> edge_index    -> dgnn_ell_from_adjacency / dgnn_ell_build
+ *   processing/generate_mesh.py:75,94-105           labels, interface facets   -> dgnn_argmax_labels / dgnn_interface_facets
+ */
+#ifndef DGNN_B200_H
+#define DGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGNN_B200_VERSION 100
+
+/* ---- library ------------------------------------------------------------------------- */
+int dgnn_version(void);
+const char* dgnn_last_error(void);
+/* 0 if `device` is a compute-capability 10.x GPU; error otherwise (no fallback exists). */
+int dgnn_device_check(int device);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int dgnn_sm_count(void);
+
+/* ---- graph layout (processing/data.py:434-439 re-laid to ELL-4) ------------------------ */
+/* adjacencies int32[4n,2] (row 4i+k = (i, k-th facet neighbour)) -> nbr int32[n,4] and the
+ * reverse-facet slot rslot uint8[n,4] (nbr[nbr[i,k], rslot[i,k]] == i).  *err_flag (device
+ * int32, caller-zeroed) is set to 1 if a row's owner column is not i, 2 if not symmetric. */
+int dgnn_ell_from_adjacency(const int32_t* adj, int64_t n, int32_t* nbr, uint8_t* rslot,
+                            int32_t* err_flag, void* stream);
+/* generic: edge list (src[e] -> tgt[e], int64 as in edge_index) -> per-target rows of <=4
+ * in-edges in ascending edge id.  nbr int32[n_rows,4] (source ids, -1 pad), eid
+ * int32[n_rows,4] (edge id e, -1 pad), cnt int32[n_rows] (caller-zeroed).  *err_flag=3 if
+ * a row has more than 4 in-edges. */
+int dgnn_ell_build(const int64_t* src, const int64_t* tgt, int64_t n_edges, int64_t n_rows,
+                   int32_t* nbr, int32_t* eid, int32_t* cnt, int32_t* err_flag, void* stream);
+/* 3*bits-bit Morton code of pos float32[n,3] quantised over [lo,hi] (host float[3]) */
+int dgnn_morton_codes(const float* pos, int64_t n, const float* lo_host, const float* hi_host,
+                      int bits, uint64_t* codes, void* stream);
+/* out[new,k] = inv[nbr[perm[new],k]] (negative ids kept) */
+int dgnn_perm_apply_ell(const int32_t* nbr, const int32_t* perm, const int32_t* inv, int64_t n,
+                        int32_t* out, void* stream);
+/* dst[r,:] = src[idx[r],:]  (row_floats multiple of 4; idx<0 -> zeros) */
+int dgnn_gather_rows(const float* src, const int32_t* idx, int64_t n_rows, int row_floats,
+                     float* dst, void* stream);
+/* dst[idx[r],:] = src[r,:] */
+int dgnn_scatter_rows(const float* src, const int32_t* idx, int64_t n_rows, int row_floats,
+                      float* dst, void* stream);
+/* edge attributes ea float32[4n,fe] (reference row order 4i+k) -> incoming order
+ * ea_in[new,k] = ea[4*nbr[i,k]+rslot[i,k]] and own-slot order ea_own[new,k] = ea[4i+k],
+ * i = perm[new] (perm may be NULL = identity); nbr/rslot in ORIGINAL numbering. Either
+ * output may be NULL. */
+int dgnn_edge_relayout(const float* ea, const int32_t* nbr, const uint8_t* rslot,
+                       const int32_t* perm, int64_t n, int fe, float* ea_in, float* ea_own,
+                       void* stream);
+
+/* ---- one message-passing layer, forward (Static:66-96 + norm/ReLU of the producer) ------
+ * For target row t < n_tgt (targets are the first n_tgt source rows):
+ *   h(s)   = in_scale ? relu?(x_in[s]*in_scale + in_shift) : relu?(x_in[s])   (relu iff relu_in)
+ *   phi_k  = w_e ? (w_e . ea[t,k] + b_e) : 1
+ *   agg[t] = (1/max(cnt,1)) * sum_{k: nbr[t,k]>=0} h(nbr[t,k]) (*) phi_k
+ *   z[t]   = [agg[t] | h(t)] . wt_cat + bias          (wt_cat float32[k_total, f_out],
+ *            k_total = 2*f_in, rows 0..f_in-1 = lin_j^T, rows f_in.. = lin_i^T)
+ *   out[t] = out_scale ? relu?(z*out_scale + out_shift) : z            (relu iff relu_out)
+ * With nbr == NULL the gather is skipped (dense layer: z = h(t) . wt_cat + bias, k_total = f_in).
+ * agg_save (nullable) receives agg (training).  stats (nullable) = double[grid, 2, f_out]
+ * per-CTA partial (sum z, sum z^2) over valid rows; grid = dgnn_layer_grid().
+ * ea_stride = floats per edge row in `ea` (>= fe).  */
+int dgnn_layer_grid(int f_in, int f_out);
+int dgnn_layer_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                   const int32_t* nbr, const float* ea, int fe,
+                   const float* w_e, const float* b_e,
+                   const float* wt_cat, const float* bias,
+                   const float* out_scale, const float* out_shift, int relu_out,
+                   int64_t n_tgt, int f_in, int f_out,
+                   float* out, float* agg_save, double* stats, void* stream);
+
+/* Reduce per-CTA (sum, sum^2) partials and produce the normalisation's per-channel affine.
+ * mode 0 = BatchNorm1d training statistics (biased var for normalisation; running_mean /
+ *          running_var (unbiased) updated with `momentum` when non-NULL),
+ * mode 1 = PyG graph LayerNorm (scalar mean / population std over all rows x channels;
+ *          eps added to the std).
+ * Outputs (float[c] each): scale, shift (y = z*scale + shift), mean, rstd. */
+int dgnn_norm_finalize(const double* stats, int n_partials, int64_t n_rows, int c,
+                       const float* weight, const float* bias, float eps, float momentum,
+                       int mode, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* mean, float* rstd, void* stream);
+/* eval-mode BatchNorm affine from running statistics */
+int dgnn_norm_eval_affine(const float* weight, const float* bias, const float* running_mean,
+                          const float* running_var, float eps, int c, float* scale, float* shift,
+                          void* stream);
+
+/* out[r,o] = sum_f h(r,f) * w[o,f] + b[o], o < od <= 4, h as in dgnn_layer_fwd */
+int dgnn_rowdot_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                    const float* w, const float* b, int64_t n, int f, int od, float* out,
+                    void* stream);
+/* out = h(x_in) materialised (decoder == 0) */
+int dgnn_affine_relu(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                     int64_t n, int f, float* out, void* stream);
+
+/* ---- loss (runModel.py:163-211, kl branch) ---------------------------------------------
+ * weight_mode: 0 = w, 1 = sqrt(w), 2 = log(1+w), 3 = 1.  partials = double[grid,2]
+ * (sum w*l, sum w), grid = dgnn_small_grid().  dgnn_kl_loss_finalize writes
+ * out[0]=loss, out[1]=sum w*l, out[2]=sum w (float). */
+int dgnn_small_grid(void);
+int dgnn_kl_loss_fwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
+                     int weight_mode, int64_t n, double* partials, void* stream);
+int dgnn_kl_loss_finalize(const double* partials, int n_partials, float* out, void* stream);
+/* dlogits[r,k] = grad_out * w_r * (softmax_k * sum_k y - y_k) / sum_w ; sums = out of finalize */
+int dgnn_kl_loss_bwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
+                     int weight_mode, int64_t n, const float* sums, const float* grad_out,
+                     float* dlogits, void* stream);
+/* runModel.py:109-160: partial sums of |p0[src]-p0[tgt]| over an edge list (int64) */
+int dgnn_edge_reg_fwd(const float* logits, const int64_t* src, const int64_t* tgt, int64_t n_edges,
+                      double* partials, void* stream);
+
+/* ---- backward ---------------------------------------------------------------------------
+ * Normalisation backward is carried by per-channel coefficient vectors
+ *   dz = g*dy - (a + xhat*b),  xhat = (z - mean)*rstd
+ * produced by dgnn_norm_bwd_coeffs from the reduced (S1 = sum dy, S2 = sum dy*xhat). */
+/* d(final linear): dy[r,f] = relu'(.) * sum_o dlogits[r,o]*w[o,f]; partials double[grid, od*f + od + 2*f]
+ * = (dW[od,f], db[od], S1[f], S2[f]) */
+int dgnn_rowdot_bwd(const float* dlogits, const float* z_in, const float* in_scale, const float* in_shift,
+                    const float* mean, const float* rstd, int relu_in,
+                    const float* w, int64_t n, int f, int od, float* dy, double* partials, void* stream);
+/* elementwise: dy = relu'(z*scale+shift) * dh (relu_in) and the producer norm's (S1,S2);
+ * partials double[dgnn_small_grid(), 2*f]; dy may alias dh. */
+int dgnn_act_bwd(const float* dh, const float* z, const float* in_scale, const float* in_shift,
+                 const float* mean, const float* rstd, int relu_in, int64_t n, int f, float* dy,
+                 double* partials, void* stream);
+int dgnn_reduce_partials(const double* partials, int n_partials, int len, float* out, void* stream);
+int dgnn_norm_bwd_coeffs(const float* s1, const float* s2, int64_t n_rows, int c, const float* weight,
+                         const float* rstd, int mode, float* g, float* a, float* b, void* stream);
+/* dense part: dz = g*dy - (a + xhat*b) (g == NULL: dz = dy);  dA = dz . w_cat (w_cat
+ * float32[f_out, k_total]);  d_agg[t] = dA[t,:f_in]/max(cnt,1) (nbr != NULL), d_self = rest.
+ * db partial sums double[grid, f_out]. */
+int dgnn_dense_bwd(const float* dy, const float* z, const float* g, const float* a, const float* b,
+                   const float* mean, const float* rstd,
+                   const float* w_cat, const int32_t* nbr, int64_t n_tgt, int f_in, int f_out, int k_total,
+                   float* d_agg, float* d_self, double* db_partials, void* stream);
+/* dW[f_out, k_total] = sum_t dz[t]^T [agg[t] | h(t)];  partials float[splits, f_out, k_total],
+ * splits = dgnn_dw_splits(f_out, k_total). agg may be NULL (dense layer, k_total = f_in). */
+int dgnn_dw_splits(int f_out, int k_total);
+int dgnn_dw_bwd(const float* dy, const float* z, const float* g, const float* a, const float* b,
+                const float* mean, const float* rstd,
+                const float* agg, const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                int64_t n_tgt, int f_in, int f_out, int k_total, float* partials, void* stream);
+int dgnn_reduce_partials_f32(const float* partials, int n_partials, int64_t len, float* out, void* stream);
+/* gather part, atomic-free through the out-edge ELL table (onbr[s,k] = target of the k-th
+ * out-edge of s, ea_own its attributes):
+ *   dh[s]   = d_self[s] (s < n_tgt) + sum_k phi(ea_own[s,k]) (*) d_agg[onbr[s,k]]
+ *   dphi_k  = h(s) (*) d_agg[onbr[s,k]] ;  dW_e += dphi_k (x) ea_own[s,k] ; db_e += dphi_k
+ *   dy_prev[s] = relu'(.) * dh[s]   (written when dy_prev != NULL), S1/S2 of the producer norm.
+ * partials double[grid, f_in*(fe+1) + 2*f_in] = (dW_e[f_in,fe], db_e[f_in], S1[f_in], S2[f_in]). */
+int dgnn_gather_bwd_grid(int f_in);
+int dgnn_gather_bwd(const float* d_agg, const float* d_self, const int32_t* onbr, const float* ea_own, int fe,
+                    const float* w_e, const float* b_e,
+                    const float* x_in, const float* in_scale, const float* in_shift,
+                    const float* in_mean, const float* in_rstd, int relu_in,
+                    int64_t n_src, int64_t n_tgt, int f_in,
+                    float* dy_prev, double* partials, void* stream);
+
+/* ---- optimiser (torch.optim.Adam defaults, runModel.py:290) ------------------------------ */
+int dgnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+/* all tensors in one launch: table = device int64[n_tensors,5] rows (param, grad, exp_avg,
+ * exp_avg_sq, numel); max_n = largest numel */
+int dgnn_adam_multi(const int64_t* table, int n_tensors, int64_t max_n, float lr, float beta1,
+                    float beta2, float eps, int step, void* stream);
+
+/* ---- labels / facets (generate_mesh.py:75, 94-105) --------------------------------------- */
+int dgnn_argmax_labels(const float* logits, int64_t n, int od, uint8_t* labels, void* stream);
+/* nfacets int32[f,2] in finite-cell numbering (-1 = infinite -> outside); flag[f] = 1 if the two
+ * cells' labels differ */
+int dgnn_interface_facets(const uint8_t* labels_finite, int64_t n_finite, const int32_t* nfacets,
+                          int64_t n_facets, uint8_t* flag, void* stream);
+
+/* ---- halo exchange staging (multi-GPU) ---------------------------------------- */
+/* buf[r,:] = x[idx[r],:] / x[base + r,:] = buf[r,:] are dgnn_gather_rows / plain copies; the
+ * NCCL send/recv itself stays with the host (torch.distributed) on the same stream. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGNN_B200_H */

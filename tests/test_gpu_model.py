@@ -1,0 +1,200 @@
+"""GPU parity of the Static edge-filter network: CUDA path (through the C ABI) vs the CPU oracle
+and the golden vectors.  Tolerance (north_star): fp32 logits within 1e-4 relative to the logit
+scale; labels identical off exact ties."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import trainer as otr
+from oracle.static_model import NeighborSampler, SurfaceNet as OracleNet, make_clf, to_attr
+from tests.helpers import data_all, full_batch, grad_close, labels_equal_off_ties, logits_close, make_graph
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def cuda_net(clf_kwargs, state):
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    net = SurfaceNet(make_clf(device=DEV, **clf_kwargs))
+    net.load_state_dict(state, strict=True)
+    return net.to(DEV)
+
+
+def golden_data(golden):
+    return to_attr(dict(x=torch.from_numpy(golden["x"]), edge_attr=torch.from_numpy(golden["ea"]),
+                        y=torch.from_numpy(golden["y"]),
+                        edge_index=torch.from_numpy(golden["adj"].T.astype(np.int64)).contiguous()))
+
+
+def test_kf96_inference_matches_reference_golden(golden, kf96_state):
+    net = cuda_net({}, kf96_state).eval()
+    d = golden_data(golden)
+    z = net.inference_layer(d)
+    assert z.device.type == "cuda" and z.shape == (d.x.shape[0], 2)
+    err, ok = logits_close(z.cpu().numpy(), golden["kf96_inference_layer"])
+    assert ok, err
+    flips, ties = labels_equal_off_ties(z.cpu().numpy(), golden["kf96_inference_layer"])
+    assert flips == 0
+    # the two batched schedules of the reference return the same logits
+    for name in ("inference_layer_batch", "inference_batch_layer"):
+        zb = getattr(net, name)(d, None)
+        err, ok = logits_close(zb.cpu().numpy(), golden["kf96_" + name])
+        assert ok, (name, err)
+
+
+@pytest.mark.parametrize("order", ["pos", "rcm"])
+def test_inference_medium_graph_vs_oracle(kf96_state, order):
+    g = make_graph(6000, seed=11)
+    d = data_all(g, with_pos=(order == "pos"))
+    ref = OracleNet(make_clf()); ref.load_state_dict(kf96_state); ref.eval()
+    with torch.no_grad():
+        zr = ref.inference_layer(d).numpy()
+    net = cuda_net({}, kf96_state).eval()
+    z = net.inference_layer(d).cpu().numpy()
+    err, ok = logits_close(z, zr)
+    assert ok, err
+    flips, ties = labels_equal_off_ties(z, zr)
+    assert flips == 0
+
+
+def _train_compare(clf_kwargs, data, d, n_sup_rows, seed=0, loss_kwargs=None):
+    from dgnn_b200 import runModel as rm
+    torch.manual_seed(seed)
+    ref = OracleNet(make_clf(**clf_kwargs))
+    # make the norm affine non-trivial so its gradients are exercised
+    with torch.no_grad():
+        for k, p in ref.named_parameters():
+            if "norm" in k or k.startswith("decoder.1"):
+                p.add_(0.3 * torch.randn_like(p))
+    net = cuda_net(clf_kwargs, ref.state_dict())
+    ref.train(); net.train()
+    clf = make_clf(device=DEV, **clf_kwargs)
+    if loss_kwargs:
+        clf.regularization.update(loss_kwargs)
+    zr = ref(data)
+    gt = d.y[data.batch_n_id[:n_sup_rows]]
+    bx = d.x[data.batch_n_id[:n_sup_rows]]
+    lr, _, _ = otr.cell_loss(zr, gt, bx[:, 0], "kl", clf.regularization.cell_norm, clf.regularization.cell_type)
+    lr.backward()
+    z = net(data)
+    assert z.requires_grad and z.shape == zr.shape
+    loss = rm.cell_loss(z, gt, bx, clf)
+    loss.backward()
+    err, ok = logits_close(z.detach().cpu().numpy(), zr.detach().numpy())
+    assert ok, err
+    assert abs(loss.item() - lr.item()) <= 2e-5 * max(1.0, abs(lr.item())), (loss.item(), lr.item())
+    refp = dict(ref.named_parameters())
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        e, tol = grad_close(p.grad, refp[k].grad)
+        assert e <= tol, (k, e, tol)
+    # running statistics were updated like BatchNorm1d does
+    for k, b in net.named_buffers():
+        rb = dict(ref.named_buffers())[k]
+        np.testing.assert_allclose(b.cpu().numpy(), rb.numpy(), rtol=2e-4, atol=1e-6, err_msg=k)
+    return net, ref
+
+
+def test_train_full_graph_kf96_widths():
+    g = make_graph(1200, seed=21)
+    d = data_all(g)
+    data = full_batch(d)
+    _train_compare({}, data, d, d.x.shape[0])
+
+
+@pytest.mark.parametrize("cell_norm", ["sqrt", "log"])
+def test_train_loss_weight_variants(cell_norm):
+    g = make_graph(300, seed=22)
+    d = data_all(g)
+    _train_compare(dict(convs=(16, 32, 32, 32)), full_batch(d), d, d.x.shape[0], loss_kwargs=dict(cell_norm=cell_norm))
+
+
+@pytest.mark.parametrize("kw", [dict(convs=(16, 32, 32, 32)),
+                                dict(convs=(16, 32, 32, 32), edge_convs=0, decoder=1, n_edge_feat=None),
+                                dict(convs=(32, 64), decoder=0),
+                                dict(convs=(16, 32, 32), normalization="l")])
+def test_train_sampled_closure_matches_oracle(golden, kw):
+    """Seed-batched training semantics of the reference (run.py:72-74): per-layer bipartite
+    sub-graphs with n_src != n_tgt."""
+    d = golden_data(golden)
+    L = len(kw["convs"])
+    smp = NeighborSampler(d.edge_index, [-1] * (L + 1), 96, node_idx=torch.arange(40, 136), num_nodes=d.x.shape[0])
+    bs, n_id, adjs = next(iter(smp))
+    data = to_attr(dict(all=d, batch_n_id=n_id, batch_adjs=adjs))
+    n_sup = adjs[L - 1][2][1]
+    if kw.get("decoder", 2) == 0:
+        pytest.skip("decoder=0 emits hidden features, no kl loss")
+    _train_compare(kw, data, d, n_sup)
+
+
+def test_golden_train_step_a(golden):
+    """The reference's own train step (golden case 'a'): logits, loss and every gradient."""
+    from dgnn_b200 import runModel as rm
+    d = golden_data(golden)
+    state = {k[len("train_a_init."):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith("train_a_init.")}
+    kw = dict(convs=(16, 32, 32, 32))
+    net = cuda_net(kw, state).train()
+    n_id = torch.from_numpy(golden["train_a_n_id"])
+    adjs = [(torch.from_numpy(golden["train_a_adj%d_ei" % i]), torch.from_numpy(golden["train_a_adj%d_eid" % i]),
+             tuple(int(v) for v in golden["train_a_adj%d_size" % i])) for i in range(5)]
+    data = to_attr(dict(all=d, batch_n_id=n_id, batch_adjs=adjs))
+    z = net(data)
+    n_sup = adjs[3][2][1]
+    clf = make_clf(device=DEV, **kw)
+    loss = rm.cell_loss(z, d.y[n_id[:n_sup]], d.x[n_id[:n_sup]], clf)
+    loss.backward()
+    err, ok = logits_close(z.detach().cpu().numpy(), golden["train_a_logits"])
+    assert ok, err
+    assert abs(loss.item() - float(golden["train_a_loss"])) <= 2e-5
+    for k, p in net.named_parameters():
+        e, tol = grad_close(p.grad, torch.from_numpy(golden["train_a_grad." + k]))
+        assert e <= tol, (k, e, tol)
+
+
+def test_adam_matches_torch():
+    from dgnn_b200.runModel import Adam
+    torch.manual_seed(0)
+    ps = [torch.randn(7, 5), torch.randn(33), torch.randn(128, 64)]
+    a = [p.clone().cuda().requires_grad_() for p in ps]
+    b = [p.clone().requires_grad_() for p in ps]
+    oa, ob = Adam(a, lr=0.005), torch.optim.Adam(b, lr=0.005)
+    for step in range(5):
+        for x, y in zip(a, b):
+            gr = torch.randn_like(y)
+            y.grad = gr.clone(); x.grad = gr.cuda()
+        oa.step(); ob.step()
+    for x, y in zip(a, b):
+        np.testing.assert_allclose(x.detach().cpu().numpy(), y.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_training_reduces_loss_and_matches_oracle_trajectory():
+    """Five Adam steps on a small graph: the loss trajectory follows the oracle's."""
+    from dgnn_b200 import runModel as rm
+    g = make_graph(300, seed=31)
+    d = data_all(g)
+    data = full_batch(d)
+    kw = dict(convs=(16, 32, 32, 32))
+    torch.manual_seed(0)
+    ref = OracleNet(make_clf(**kw))
+    net = cuda_net(kw, ref.state_dict())
+    clf = make_clf(device=DEV, **kw)
+    oa, ob = rm.Adam(net.parameters(), lr=0.005), torch.optim.Adam(ref.parameters(), lr=0.005)
+    la, lb = [], []
+    for _ in range(5):
+        net.train(); ref.train()
+        loss = rm.cell_loss(net(data), d.y, d.x, clf)
+        oa.zero_grad(); loss.backward(); oa.step()
+        lr, _, _ = otr.cell_loss(ref(data), d.y, d.x[:, 0])
+        ob.zero_grad(); lr.backward(); ob.step()
+        la.append(loss.item()); lb.append(lr.item())
+    assert la[-1] < la[0]
+    np.testing.assert_allclose(la, lb, rtol=2e-3)
+
+
+def test_unsupported_options_fail_loudly():
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    g = make_graph(60, seed=1)
+    net = SurfaceNet(make_clf(device=DEV, edge_convs=2)).to(DEV).eval()
+    with pytest.raises(NotImplementedError):
+        net.inference_layer(data_all(g))

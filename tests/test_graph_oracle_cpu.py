@@ -1,0 +1,93 @@
+"""NumPy graph oracle: structural properties of the synthetic Delaunay graphs, the ELL-4 table,
+the reverse-facet slot, permutations and halo maps (CPU only)."""
+import numpy as np
+import pytest
+
+from oracle import graph as og
+
+
+@pytest.mark.parametrize("n_points,seed", [(40, 0), (300, 1), (2000, 2)])
+def test_delaunay_graph_is_4_regular_and_symmetric(n_points, seed):
+    adj, infinite, cen, tets = og.delaunay_graph(og.random_points(n_points, seed))
+    n = infinite.shape[0]
+    assert adj.shape == (4 * n, 2) and tets.shape[0] == n - infinite.sum()
+    nbr, rslot = og.ell_from_adjacency(adj)
+    assert (nbr >= 0).all() and (nbr < n).all()
+    assert (nbr != np.arange(n)[:, None]).all()                      # no self loops
+    assert all(len(set(r)) == 4 for r in nbr[:: max(1, n // 200)])   # 4 distinct neighbours
+    back = nbr[nbr, rslot.astype(np.int64)]
+    assert (back == np.arange(n)[:, None]).all()                     # reverse slot closes the loop
+    inf = infinite.astype(bool)
+    assert (inf[nbr[inf]].sum(axis=1) == 3).all()                    # infinite cell: 3 infinite + 1 finite
+    assert (~inf[nbr[inf, 0]]).all()
+
+
+def test_golden_adjacency_matches_generator(golden):
+    adj, infinite, cen, _ = og.delaunay_graph(og.scan_like_points(220, seed=3))
+    assert np.array_equal(adj, golden["adj"]) and np.array_equal(infinite, golden["infinite"])
+
+
+def test_ell_from_edges_equals_adjacency_view(golden):
+    adj = golden["adj"]
+    n = adj.shape[0] // 4
+    nbr, rslot = og.ell_from_adjacency(adj)
+    nb2, eid, cnt = og.ell_from_edges(adj[:, 0].astype(np.int64), adj[:, 1].astype(np.int64), n)
+    assert (cnt == 4).all()
+    # same multiset of sources per target, and eid addresses the incoming edge row
+    assert np.array_equal(np.sort(nb2, axis=1), np.sort(nbr, axis=1))
+    assert np.array_equal(adj[eid, 1], np.repeat(np.arange(n), 4).reshape(n, 4))
+    rows_in = 4 * nbr.astype(np.int64) + rslot
+    assert np.array_equal(np.sort(rows_in, axis=1), np.sort(eid, axis=1))
+
+
+def test_morton_perm_improves_locality_and_is_a_permutation(golden):
+    nbr, _ = og.ell_from_adjacency(golden["adj"])
+    perm = og.morton_perm(golden["cen"])
+    n = perm.shape[0]
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    nb2 = og.apply_perm_ell(nbr, perm)
+    # qhull's own cell order is already spatially coherent; compare against a random numbering
+    # (the reference's file order is not coherent: median |i-nbr| 753 vs 12 on Ignatius)
+    rnd = og.apply_perm_ell(nbr, np.random.default_rng(0).permutation(n).astype(np.int32))
+    before = np.median(np.abs(rnd - np.arange(n)[:, None]))
+    after = np.median(np.abs(nb2 - np.arange(n)[:, None]))
+    assert after * 10 < before
+    inv = og.invert_perm(perm)
+    assert np.array_equal(perm[nb2][inv], nbr)                        # renumbering round-trips
+
+
+def test_halo_maps_cover_all_remote_neighbours(golden):
+    nbr, _ = og.ell_from_adjacency(golden["adj"])
+    perm = og.morton_perm(golden["cen"])
+    nb = og.apply_perm_ell(nbr, perm)
+    n = nb.shape[0]
+    P = 4
+    bounds = og.partition_ranges(n, P)
+    maps = [og.halo_maps(nb, bounds, p) for p in range(P)]
+    for p, m in enumerate(maps):
+        lo, hi = bounds[p], bounds[p + 1]
+        glob = np.concatenate([np.arange(lo, hi), m["halo_gid"]])
+        assert np.array_equal(glob[m["local_nbr"]], nb[lo:hi])         # local table resolves to the global one
+        assert m["recv_counts"].sum() == m["halo_gid"].shape[0] and m["recv_counts"][p] == 0
+        off = 0
+        for q in range(P):                                             # what q sends is what p expects, in order
+            cnt = int(m["recv_counts"][q])
+            expect = m["halo_gid"][off:off + cnt]
+            sent = maps[q]["send_idx"][p] + bounds[q]
+            assert np.array_equal(sent, expect)
+            off += cnt
+
+
+def test_lattice_graph_is_4_regular():
+    adj, infinite, cen = og.lattice_graph(4, 3, 5)
+    nbr, rslot = og.ell_from_adjacency(adj)
+    assert (rslot == np.arange(4)[None, :]).all()
+    assert all(len(set(r)) == 4 for r in nbr)
+
+
+def test_labels_and_interface_facets():
+    z = np.array([[0.1, 0.2], [0.3, 0.3], [0.5, -1.0]], dtype=np.float32)
+    lab = og.labels_from_logits(z)
+    assert lab.tolist() == [1, 0, 0]
+    nf = np.array([[0, 1], [1, 2], [2, -1], [0, -1]], dtype=np.int32)
+    assert og.interface_facets(lab, nf).tolist() == [0, 2]
