@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the DGNN cell-classification hot path on B200 (one JSON line on stdout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): ModelNet10-shaped
+training — a batch is the disjoint union of B synthetic object graphs (scipy Delaunay of 3 000
+scan-like points each, ~19.7 k cells per object incl. infinite cells, random features of the
+``feat`` tool's shape), kf96 widths 28->64->128->128->128, decoder 128->64->2, BatchNorm in
+training mode, volume-weighted KL loss, Adam lr 0.005.  One step = forward + loss + backward +
+Adam over the whole batch.  Metric: Delaunay cells/s (whole job, all GPUs).
+
+N > 1 (launched by torchrun, one rank per GPU): data-parallel over objects — every rank trains on
+its own batch of B objects (weak scaling) and the gradients are averaged with one NCCL all-reduce
+per step before the optimiser step.
+
+``--impl reference`` times the CPU restatement of the reference (oracle/, plain PyTorch with all
+host threads; the reference's own modules need torch_geometric, which cannot be installed here) on
+a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+POINTS_PER_OBJECT = 3000
+FE, F0 = 20, 28
+WIDTHS = (64, 128, 128, 128)
+
+
+# --------------------------------------------------------------------------- workload
+
+
+def make_objects(n_objects: int, seed0: int):
+    """Disjoint union of ``n_objects`` synthetic object graphs in the reference's collated layout
+    (run.py:59-61): x[N,1+28], edge_attr[4N,20], y[N,2], edge_index int64[2,4N], centroids."""
+    from dgnn_b200 import synthetic as og
+    xs, eas, ys, eis, cens = [], [], [], [], []
+    off = 0
+    for i in range(n_objects):
+        pts = og.scan_like_points(POINTS_PER_OBJECT, seed=seed0 + i)
+        adj, infinite, cen, _ = og.delaunay_graph(pts)
+        n = infinite.shape[0]
+        x, ea, y = og.synthetic_features(n, infinite, seed=10_000 + seed0 + i)
+        xs.append(x); eas.append(ea); ys.append(y); cens.append(cen.astype(np.float32) + 2.0 * i)
+        eis.append(adj.T.astype(np.int64) + off)
+        off += n
+    return dict(x=torch.from_numpy(np.concatenate(xs)), edge_attr=torch.from_numpy(np.concatenate(eas)),
+                y=torch.from_numpy(np.concatenate(ys)), edge_index=torch.from_numpy(np.concatenate(eis, axis=1)),
+                pos=torch.from_numpy(np.concatenate(cens)), n=off)
+
+
+def batch_of(d, to_attr):
+    n = d["n"]
+    all_ = to_attr({k: v for k, v in d.items() if k != "n"})
+    ei = all_.edge_index
+    return to_attr(dict(all=all_, batch_n_id=torch.arange(n, device=ei.device),
+                        batch_adjs=[(ei, torch.arange(ei.shape[1], device=ei.device), (n, n))] * 5))
+
+
+# --------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- roofline bookkeeping
+
+
+def algorithmic_bytes(name, a):
+    """Compulsory HBM bytes of one launch (DESIGN.md section 'kernels'; SURVEY.md 8d per-layer
+    figures split per kernel).  ``a`` = the ctypes argument list of the call."""
+    if name == "dgnn_layer_fwd":
+        n, f_in, f_out, fe = a[14], a[15], a[16], (a[6] if a[7] else 0)
+        gather = a[4] is not None
+        b = 4 * f_in + 4 * f_out
+        if gather:
+            b += 16 + 16 * fe
+        if a[18] is not None:
+            b += 4 * f_in
+        return n * b, "f%d->%d" % (f_in, f_out)
+    if name == "dgnn_dense_bwd":
+        n, f_in, f_out = a[9], a[10], a[11]
+        gather = a[8] is not None
+        return n * (8 * f_out + (8 * f_in + 16 if gather else 4 * f_in)), "f%d->%d" % (f_in, f_out)
+    if name == "dgnn_dw_bwd":
+        n, f_in, f_out = a[12], a[13], a[14]
+        return n * (8 * f_out + (8 * f_in if a[7] is not None else 4 * f_in)), "f%d->%d" % (f_in, f_out)
+    if name == "dgnn_gather_bwd":
+        n, f_in, fe = a[13], a[15], (a[4] if a[5] else 0)
+        return n * (16 + 16 * fe + 12 * f_in + (4 * f_in if a[16] is not None else 0)), "f%d" % f_in
+    return None, ""
+
+
+class KernelProfile:
+    """Per-launch device time of every C-ABI call, measured with CUDA events on the launching
+    stream (used after the timed region to find the dominant kernel and its achieved GB/s)."""
+
+    def __init__(self):
+        self.rows = []
+
+    def install(self):
+        from dgnn_b200 import _lib
+        self._orig = _lib.call
+        prof = self
+
+        def timed_call(name, *args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            prof._orig(name, *args)
+            e1.record()
+            prof.rows.append((name, args, e0, e1))
+
+        for modname in ("dgnn_b200._lib", "dgnn_b200.engine", "dgnn_b200.graph", "dgnn_b200.runModel"):
+            mod = sys.modules.get(modname)
+            if mod is not None and hasattr(mod, "call"):
+                setattr(mod, "call", timed_call)
+
+    def uninstall(self):
+        for modname in ("dgnn_b200._lib", "dgnn_b200.engine", "dgnn_b200.graph", "dgnn_b200.runModel"):
+            mod = sys.modules.get(modname)
+            if mod is not None and hasattr(mod, "call"):
+                setattr(mod, "call", self._orig)
+
+    def summary(self, n_steps, peak_gbs, peak_src):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, args, e0, e1 in self.rows:
+            ms = e0.elapsed_time(e1)
+            nbytes, tag = algorithmic_bytes(name, args)
+            k = (name, tag)
+            r = agg.setdefault(k, dict(ms=0.0, launches=0, bytes=0, known=nbytes is not None))
+            r["ms"] += ms; r["launches"] += 1; r["bytes"] += nbytes or 0
+        total = sum(r["ms"] for r in agg.values())
+        top = max((k for k in agg if agg[k]["known"]), key=lambda k: agg[k]["ms"])
+        r = agg[top]
+        ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        table = sorted(((k[0] + ":" + k[1], round(v["ms"] / n_steps, 4), v["launches"] // n_steps) for k, v in agg.items()),
+                       key=lambda t: -t[1])
+        roof = {"bound": "hbm", "kernel": top[0] + ":" + top[1], "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
+                "frac": round(ach / peak_gbs, 4), "peak_source": peak_src, "traffic": None,
+                "kernel_ms_per_launch": round(r["ms"] / r["launches"], 4),
+                "kernel_share_of_step": round(r["ms"] / total, 4),
+                "algorithmic_bytes_per_launch": r["bytes"] // r["launches"]}
+        return roof, table[:12], total / n_steps
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+
+
+def cpu_reference(n_objects, steps, warmup, seed0=0):
+    """fwd + loss + bwd + Adam of the oracle (plain PyTorch on the host cores) on ``n_objects``."""
+    from oracle import trainer as otr
+    from oracle.static_model import SurfaceNet as OracleNet
+    from dgnn_b200.synthetic import make_clf, to_attr
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = make_objects(n_objects, seed0)
+    data = batch_of(d, to_attr)
+    clf = make_clf(convs=WIDTHS)
+    torch.manual_seed(0)
+    net = OracleNet(clf)
+    opt = torch.optim.Adam(net.parameters(), lr=0.005)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        otr.train_step(net, opt, data, clf)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.sum(times))
+    return d["n"] * steps / dt, cores, d["n"], dt / steps
+
+
+# --------------------------------------------------------------------------- main
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--objects", type=int, default=64, help="object graphs per GPU per step")
+    ap.add_argument("--cpu-objects", type=int, default=4, help="objects in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "configs[1] ModelNet10-shaped training: %d object graphs/GPU/step x ~19.7k cells "
+                          "(3000 scan-like points each), fwd+loss+bwd+Adam, BN train mode, kl loss" % args.objects,
+              "widths": [F0] + list(WIDTHS), "decoder": "128->64->2", "edge_features": FE,
+              "objects_per_gpu": args.objects, "parallelism": "dp%d (gradient all-reduce)" % world if world > 1 else "single GPU",
+              "l2_policy": "inputs + saved activations per step (>1 GB) exceed the 126 MB L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        warm = max(1, min(args.warmup, 1))
+        v, cores, n_cells, s_per = cpu_reference(args.cpu_objects, steps, warm)
+        sample = "%d objects (%d cells) per step, %d steps after %d warm-up" % (args.cpu_objects, n_cells, steps, warm)
+        print(json.dumps({"impl": "reference", "metric": "Delaunay cells/sec (GNN fwd+bwd)", "value": v, "unit": "cells/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": s_per * 1e3,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from dgnn_b200 import _lib, runModel as rm
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    from dgnn_b200.synthetic import make_clf, to_attr  # clf / attr-dict stand-ins for Munch
+
+    # count kernel launches issued through the C ABI
+    launches = {"n": 0}
+    orig_call = _lib.call
+    two = {"dgnn_ell_build": 2}
+
+    def counting_call(name, *a):
+        launches["n"] += two.get(name, 1)
+        return orig_call(name, *a)
+
+    for modname in ("dgnn_b200._lib", "dgnn_b200.engine", "dgnn_b200.graph", "dgnn_b200.runModel"):
+        setattr(sys.modules[modname], "call", counting_call)
+
+    host = make_objects(args.objects, seed0=1000 * rank)
+    n_cells = host["n"]
+    clf = make_clf(convs=WIDTHS, device=str(dev))
+    torch.manual_seed(0)
+    net = SurfaceNet(clf).to(dev).train()
+    opt = rm.Adam(net.parameters(), lr=0.005)
+    params = [p for p in net.parameters()]
+
+    # device-resident batch (value) ---------------------------------------------------------
+    dres = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    data = batch_of(dres, to_attr)
+
+    def step(batch, d_all):
+        logits = net(batch)
+        loss = rm.cell_loss(logits, d_all.y, d_all.x, clf)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        opt.step()
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches["n"] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches["n"]
+
+    with ClockSampler(local_rank) as clocks:
+        ms, n_launch = timed(lambda: step(data, data.all), args.steps, args.warmup)
+    value = world * n_cells * args.steps / (ms * 1e-3)
+
+    # end to end through the public API with HOST buffers (e2e) ------------------------------
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    net.cache_graphs = False
+    h2d = sum(pinned[k].numel() * pinned[k].element_size() for k in ("x", "edge_attr", "y", "edge_index", "pos"))
+
+    def e2e_step():
+        hb = batch_of(pinned, to_attr)          # host batch, as the reference trainer holds it
+        loss = step(hb, hb.all)
+        return loss.item()                      # device -> host read of the step's result
+
+    e2e_steps = max(3, args.steps // 4)
+    ms_e2e, _ = timed(e2e_step, e2e_steps, 2)
+    e2e_value = world * n_cells * e2e_steps / (ms_e2e * 1e-3)
+    net.cache_graphs = True
+
+    # per-kernel device time of one step -> roofline of the dominant kernel --------------------
+    peak, peak_src = peak_hbm()
+    prof = KernelProfile()
+    for modname in ("dgnn_b200._lib", "dgnn_b200.engine", "dgnn_b200.graph", "dgnn_b200.runModel"):
+        setattr(sys.modules[modname], "call", orig_call)
+    prof.install()
+    n_prof = 3
+    for _ in range(n_prof):
+        step(data, data.all)
+    prof.uninstall()
+    roofline, table, kernel_ms = prof.summary(n_prof, peak, peak_src)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, nc, s_per = cpu_reference(args.cpu_objects, 2, 1)
+        cpu = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
+               "sample": "%d objects (%d cells) per step, 2 steps after 1 warm-up, oracle (plain PyTorch CPU)" % (args.cpu_objects, nc)}
+
+    # whole-step algorithmic bytes (kf96 training fwd+bwd ~ 19.9 KB/cell)
+    step_bytes_per_cell = 19_900
+    out = {"metric": "Delaunay cells/sec (GNN fwd+bwd)", "value": value, "unit": "cells/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+           "cells_per_gpu_per_step": n_cells,
+           "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_e2e / e2e_steps},
+           "gpu_launches": int(n_launch),
+           "clocks": clocks.summary(),
+           "roofline": roofline,
+           "step_hbm_frac": round(n_cells * step_bytes_per_cell / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
+           "kernel_ms_per_step": round(kernel_ms, 3),
+           "kernels": table,
+           "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

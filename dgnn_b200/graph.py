@@ -189,10 +189,12 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
         raise _lib.DgnnError("dgnn_ell_build: edge endpoint out of range (code %d)" % code)
     ea_in = ea_own = None
     if edge_attr is not None:
-        if e_id is not None:
-            rows = edge_attr[e_id.to(edge_attr.device)]
-        else:
+        if e_id is None:
             rows = edge_attr
+        elif e_id.numel() * 2 >= edge_attr.shape[0]:
+            rows = edge_attr.to(dev, non_blocking=True)[e_id.to(dev)]
+        else:
+            rows = edge_attr[e_id.to(edge_attr.device)]
         ea = pad_cols(rows.to(dev, dtype=torch.float32), fe)
         ea_in = torch.empty((n_tgt, 4, fe), dtype=torch.float32, device=dev)
         call("dgnn_gather_rows", ptr(ea), ptr(eid_in), n_tgt * 4, fe, ptr(ea_in), st)

@@ -235,7 +235,7 @@ class SurfaceNet(nn.Module):
             def build():
                 if full:
                     ei, e_id, size = adjs[0]
-                    ea = ea_all[e_id.to(ea_all.device)] if ea_all is not None else None
+                    ea = ea_all.to(dev, non_blocking=True)[e_id.to(dev)] if ea_all is not None else None
                     pos = getattr(data.all, "pos", None)
                     pos = pos[n_id.to(pos.device)] if pos is not None else None
                     g = build_full_graph(ei, ea, size[0], dev, pos=pos, order="auto")
@@ -245,7 +245,10 @@ class SurfaceNet(nn.Module):
             graphs = self._cached(data, key, build)
             xa = data.all.x
             cols = slice(1, None) if self.clf.regularization.cell_type else slice(None)
-            x = xa[n_id.to(xa.device)][:, cols].to(dev, dtype=torch.float32, non_blocking=True)
+            if n_id.numel() * 2 >= xa.shape[0]:   # most rows used: upload once, select on the device
+                x = xa.to(dev, non_blocking=True)[n_id.to(dev)][:, cols].to(torch.float32)
+            else:
+                x = xa[n_id.to(xa.device)][:, cols].to(dev, dtype=torch.float32, non_blocking=True)
             x0 = graphs[0].permute_rows(pad_cols(x, pad4(x.shape[1])))
             out = self._run(graphs, x0)
             return graphs[-1].unpermute_rows(out) if full else out

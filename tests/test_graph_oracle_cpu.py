@@ -91,3 +91,18 @@ def test_labels_and_interface_facets():
     assert lab.tolist() == [1, 0, 0]
     nf = np.array([[0, 1], [1, 2], [2, -1], [0, -1]], dtype=np.int32)
     assert og.interface_facets(lab, nf).tolist() == [0, 2]
+
+
+def test_product_generator_matches_oracle_generator():
+    """dgnn_b200.synthetic (used by bench / smoke) against the oracle's own copy, bit-exact."""
+    from dgnn_b200 import synthetic as syn
+    for pts_fn, n, seed in (("random_points", 500, 3), ("scan_like_points", 700, 4)):
+        a = getattr(syn, pts_fn)(n, seed); b = getattr(og, pts_fn)(n, seed)
+        assert np.array_equal(a, b)
+        ga, gb = syn.delaunay_graph(a), og.delaunay_graph(b)
+        for u, v in zip(ga, gb):
+            assert np.array_equal(u, v)
+        fa = syn.synthetic_features(ga[1].shape[0], ga[1], seed=9)
+        fb = og.synthetic_features(gb[1].shape[0], gb[1], seed=9)
+        for u, v in zip(fa, fb):
+            assert np.array_equal(u, v)
