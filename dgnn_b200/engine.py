@@ -247,6 +247,15 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
 # --------------------------------------------------------------------------- backward
 
 
+#: set to a dict to record backward intermediates (development / tests only)
+DEBUG = None
+
+
+def _dbg(name, t):
+    if DEBUG is not None:
+        DEBUG[name] = t.detach().clone() if t is not None else None
+
+
 def _reduce(partials: torch.Tensor) -> torch.Tensor:
     """Sum double partials [P, len] -> float32[len]."""
     out = torch.empty(partials.shape[1], dtype=torch.float32, device=partials.device)
@@ -327,10 +336,12 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
         grads["dec3_b"] = r[od * f_d:od * f_d + od]
         s1d, s2d = r[od * f_d + od:od * f_d + od + f_d], r[od * f_d + od + f_d:]
         grads["dec_norm_w"], grads["dec_norm_b"] = s2d, s1d
+        _dbg("dy_d", dy_d)
         coeffs = _norm_coeffs(spec.dec_norm, affd, s1d, s2d, n_out, f_d)
         _, dh, db0, dw0 = _dense_and_dw(dy_d, sv.z_d, coeffs, affd, spec.dec0_w.detach().contiguous(), None, None, zL,
                                         affL, True, n_out, f_last, f_d)
         grads["dec0_w"], grads["dec0_b"] = dw0, db0
+        _dbg("dh_L", dh)
         dy = dh  # in place: dy = relu'(y_L) * dh
         part = torch.empty((small, 2 * f_last), dtype=torch.float64, device=dev)
         call("dgnn_act_bwd", ptr(dh), ptr(zL), ptr(affL.scale), ptr(affL.shift), ptr(affL.mean), ptr(affL.rstd), 1,
@@ -341,6 +352,7 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
     for l in range(L - 1, -1, -1):
         c, pk, g, aff = spec.convs[l], sv.packed[l], sv.graphs[l], sv.aff[l]
         grads["convs.%d.norm_w" % l], grads["convs.%d.norm_b" % l] = s2, s1
+        _dbg("dy_%d" % l, dy)
         coeffs = _norm_coeffs(c.norm, aff, s1, s2, g.n_tgt, pk.f_out)
         x_in = sv.z[l - 1] if l > 0 else sv.x0
         in_aff = sv.aff[l - 1] if l > 0 else None
@@ -348,6 +360,7 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
         d_agg, d_self, db, dw = _dense_and_dw(dy, sv.z[l], coeffs, aff, pk.w_cat, g, sv.agg[l], x_in, in_aff, relu_in,
                                               g.n_tgt, pk.f_in, pk.f_out)
         grads["convs.%d.b_j" % l] = db
+        _dbg("d_agg_%d" % l, d_agg); _dbg("d_self_%d" % l, d_self)
         grads["convs.%d.w_j" % l] = dw[:, :c.f_in]
         grads["convs.%d.w_i" % l] = dw[:, pk.f_in:pk.f_in + c.f_in]
         need_prev = l > 0
