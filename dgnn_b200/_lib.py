@@ -33,6 +33,12 @@ SIGNATURES = {
     "dgnn_edge_relayout": [P, P, P, P, L, I, P, P, P],
     "dgnn_layer_grid": [I, I],
     "dgnn_layer_fwd": [P, P, P, I, P, P, I, P, P, P, P, P, P, I, L, I, I, P, P, P, P],
+    "dgnn_tc_supported": [I, I, I],
+    "dgnn_tc_grid": [],
+    "dgnn_tc_packed_floats": [I, I, I],
+    "dgnn_pack_b_tf32": [P, I, I, I, I, P, P],
+    "dgnn_layer_fwd_tc": [P, P, P, I, P, P, I, P, P, P, P, P, P, I, L, I, I, P, P, P, P],
+    "dgnn_dense_bwd_tc": [P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P],
     "dgnn_norm_finalize": [P, I, L, I, P, P, F, F, I, P, P, P, P, P, P, P],
     "dgnn_norm_eval_affine": [P, P, P, P, F, I, P, P, P],
     "dgnn_rowdot_fwd": [P, P, P, I, P, P, L, I, I, P, P],

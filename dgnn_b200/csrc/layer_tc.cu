@@ -1,0 +1,580 @@
+// Tensor-core (tcgen05 + TMEM) version of the fused layer kernels for widths that fit one
+// UMMA tile: f_out (forward) / k_total (backward) <= 256.
+//
+//   forward :  z = [agg | h] . [W_j | W_i]^T      (dgnn_layer_fwd_tc, gather or dense mode)
+//   backward:  [d_agg | d_self] = dz . [W_j | W_i] (dgnn_dense_bwd_tc)
+//
+// One persistent CTA (512 threads, 1 per SM) owns tiles of 128 cells (UMMA M = 128).  The A
+// operand never exists in global memory: per K-atom (32 features) all 16 warps produce the
+// [128 x 32] slice — gathering neighbour rows and applying the edge filter (forward), or
+// applying the normalisation backward to dy (backward) — split it into TF32 hi/lo parts and
+// store it straight into the 128B-swizzled UMMA layout of a ring stage, next to that atom's
+// pre-packed weight slice.  One thread then issues the 12 tcgen05.mma of the stage
+// (3xTF32: hi*hi + lo*hi + hi*lo, 4 k-steps) which accumulate in TMEM while the CTA already
+// produces the next atom; tcgen05.commit frees the stage.  Accumulators are double-buffered in
+// TMEM (2 x N columns), so the epilogue of tile i (tcgen05.ld -> bias / affine / ReLU / BN
+// partials -> global) runs after tile i+1 has been issued.
+#include "umma.cuh"
+#include "common.cuh"
+
+namespace dgnn {
+
+using namespace umma;
+
+constexpr int TC_M = 128;
+constexpr int TC_THREADS = 512;
+constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int A_ATOM_BYTES = TC_M * ATOM_ROW_BYTES;  // 16 KB
+
+enum { MODE_FWD_DENSE = 0, MODE_FWD_GATHER = 1, MODE_BWD = 2 };
+
+struct TcArgs {
+    // forward producer
+    const float* x_in;
+    const float* in_scale;
+    const float* in_shift;
+    int relu_in;
+    const int32_t* nbr;
+    const float* ea;
+    const float* w_e;
+    const float* b_e;
+    // backward producer: dz = g*dy - (a + xhat*b)
+    const float* dy;
+    const float* z;
+    const float* ng;
+    const float* na;
+    const float* nb;
+    const float* nmean;
+    const float* nrstd;
+    // operand B
+    const float* b_packed;  // [KA][2][NP][32] swizzled atoms (hi, lo)
+    int ka;                 // K-atoms
+    int ka_agg;             // atoms of the agg segment (gather mode), 0 otherwise
+    int np;                 // padded N (multiple of 32, <= 256)
+    int stages;
+    // sizes
+    int64_t n_tgt;
+    int f_in;   // forward: input width; backward: width of d_agg / d_self
+    int f_out;  // forward: output width (N); backward: K (width of dy)
+    // forward epilogue
+    const float* bias;
+    const float* out_scale;
+    const float* out_shift;
+    int relu_out;
+    float* out;
+    float* agg_save;
+    double* stats;
+    // backward epilogue
+    float* d_agg;
+    float* d_self;
+    double* db_partials;
+};
+
+__device__ __forceinline__ void store_split2(uint8_t* a_hi, uint8_t* a_lo, int r, int k, float v0, float v1) {
+    float h0, l0, h1, l1;
+    split_tf32(v0, h0, l0);
+    split_tf32(v1, h1, l1);
+    uint32_t off = atom_off(r, k);
+    *reinterpret_cast<float2*>(a_hi + off) = make_float2(h0, h1);
+    *reinterpret_cast<float2*>(a_lo + off) = make_float2(l0, l1);
+}
+__device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, int r, int k, float4 v) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+    uint32_t off = atom_off(r, k);
+    *reinterpret_cast<float4*>(a_hi + off) = h;
+    *reinterpret_cast<float4*>(a_lo + off) = l;
+}
+
+// A-atom = h(x_in[tile rows, f0 .. f0+32))  (self part of a gather layer, or a dense layer)
+__device__ __forceinline__ void produce_rows(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0) {
+    const bool relu = p.relu_in != 0;
+#pragma unroll
+    for (int it = 0; it < (TC_M * 8) / TC_THREADS; ++it) {
+        int idx = threadIdx.x + it * TC_THREADS;
+        int r = idx >> 3, c = (idx & 7) * 4;
+        int f = f0 + c;
+        int64_t t = tile0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < p.n_tgt && f < p.f_in) {
+            v = ldg4(p.x_in + (size_t)t * p.f_in + f);
+            if (p.in_scale != nullptr) {
+                float4 sc = ldg4(p.in_scale + f), sh = ldg4(p.in_shift + f);
+                v.x = act(v.x, sc.x, sh.x, relu); v.y = act(v.y, sc.y, sh.y, relu);
+                v.z = act(v.z, sc.z, sh.z, relu); v.w = act(v.w, sc.w, sh.w, relu);
+            } else if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+        }
+        store_split4(a_hi, a_lo, r, c, v);
+    }
+}
+
+// A-atom = dz[tile rows, f0 .. f0+32); column sums of dz go to red_s (shared floats, zeroed per tile)
+__device__ __forceinline__ void produce_dz(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0,
+                                           float* red_s) {
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = (threadIdx.x & 7) * 4;
+    const int f = f0 + c;
+#pragma unroll
+    for (int it = 0; it < (TC_M * 8) / TC_THREADS; ++it) {
+        int idx = threadIdx.x + it * TC_THREADS;
+        int r = idx >> 3;
+        int64_t t = tile0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < p.n_tgt && f < p.f_out) {
+            float4 d = ldg4(p.dy + (size_t)t * p.f_out + f);
+            if (p.ng != nullptr) {
+                float4 zv = ldg4(p.z + (size_t)t * p.f_out + f);
+                float4 g = ldg4(p.ng + f), a = ldg4(p.na + f), b = ldg4(p.nb + f), m = ldg4(p.nmean + f),
+                       rs = ldg4(p.nrstd + f);
+                v.x = g.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
+                v.y = g.y * d.y - (a.y + (zv.y - m.y) * rs.y * b.y);
+                v.z = g.z * d.z - (a.z + (zv.z - m.z) * rs.z * b.z);
+                v.w = g.w * d.w - (a.w + (zv.w - m.w) * rs.w * b.w);
+            } else {
+                v = d;
+            }
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+        }
+        store_split4(a_hi, a_lo, r, c, v);
+    }
+    if (p.db_partials != nullptr) {
+        // lanes l, l+8, l+16, l+24 share the column group
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+        if ((threadIdx.x & 31) < 8 && f < p.f_out) {
+            atomicAdd(&red_s[f], cs.x); atomicAdd(&red_s[f + 1], cs.y);
+            atomicAdd(&red_s[f + 2], cs.z); atomicAdd(&red_s[f + 3], cs.w);
+        }
+    }
+}
+
+// A-atom = agg[tile rows, f0 .. f0+32): 16 lanes per cell, 2 features per lane
+template <int FE>
+__device__ __forceinline__ void produce_agg(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane >> 4, li = lane & 15;
+    const int F = p.f_in;
+    const int f = f0 + li * 2;
+    const bool fv = f < F;
+    const bool relu = p.relu_in != 0;
+    float we0[FE > 0 ? FE : 1], we1[FE > 0 ? FE : 1];
+    float be0 = 1.f, be1 = 1.f;
+    if (FE > 0) {
+#pragma unroll
+        for (int j = 0; j < FE; ++j) {
+            we0[j] = fv ? __ldg(p.w_e + (size_t)f * FE + j) : 0.f;
+            we1[j] = fv ? __ldg(p.w_e + (size_t)(f + 1) * FE + j) : 0.f;
+        }
+        be0 = fv ? __ldg(p.b_e + f) : 0.f;
+        be1 = fv ? __ldg(p.b_e + f + 1) : 0.f;
+    }
+    float sc0 = 1.f, sc1 = 1.f, sh0 = 0.f, sh1 = 0.f;
+    if (p.in_scale != nullptr && fv) {
+        sc0 = __ldg(p.in_scale + f); sc1 = __ldg(p.in_scale + f + 1);
+        sh0 = __ldg(p.in_shift + f); sh1 = __ldg(p.in_shift + f + 1);
+    }
+#pragma unroll 1
+    for (int cell = warp * 2 + sub; cell < TC_M; cell += TC_WARPS * 2) {
+        const int64_t t = tile0 + cell;
+        const bool tv = t < p.n_tgt;
+        int4 nb = make_int4(-1, -1, -1, -1);
+        if (tv) nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+        const int nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        float2 xs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            xs[k] = make_float2(0.f, 0.f);
+            if (nbv[k] >= 0 && fv) xs[k] = ldg2(p.x_in + (size_t)nbv[k] * F + f);
+        }
+        float a0 = 0.f, a1 = 0.f;
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (nbv[k] < 0) continue;
+            ++cnt;
+            float ph0 = be0, ph1 = be1;
+            if (FE > 0) {
+                const float* er = p.ea + ((size_t)t * 4 + k) * FE;
+#pragma unroll
+                for (int j = 0; j < FE; j += 4) {
+                    float4 e = ldg4(er + j);
+                    ph0 = fmaf(we0[j], e.x, ph0); ph1 = fmaf(we1[j], e.x, ph1);
+                    ph0 = fmaf(we0[j + 1], e.y, ph0); ph1 = fmaf(we1[j + 1], e.y, ph1);
+                    ph0 = fmaf(we0[j + 2], e.z, ph0); ph1 = fmaf(we1[j + 2], e.z, ph1);
+                    ph0 = fmaf(we0[j + 3], e.w, ph0); ph1 = fmaf(we1[j + 3], e.w, ph1);
+                }
+            }
+            float h0 = act(xs[k].x, sc0, sh0, relu), h1 = act(xs[k].y, sc1, sh1, relu);
+            a0 = fmaf(h0, ph0, a0);
+            a1 = fmaf(h1, ph1, a1);
+        }
+        float d = (float)(cnt > 0 ? cnt : 1);
+        a0 = fv ? a0 / d : 0.f;
+        a1 = fv ? a1 / d : 0.f;
+        store_split2(a_hi, a_lo, cell, li * 2, a0, a1);
+        if (p.agg_save != nullptr && tv && fv)
+            *reinterpret_cast<float2*>(p.agg_save + (size_t)t * F + f) = make_float2(a0, a1);
+    }
+}
+
+// butterfly transpose-reduce: on return lane l holds sum over the warp's 32 rows of column l
+__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            float mine = up ? v[i + off] : v[i];
+            float theirs = up ? v[i] : v[i + off];
+            v[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, off);
+        }
+    }
+    return v[0];
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int64_t tile0, float* red_s,
+                                         double* my_stats) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, grp = warp >> 2;
+    const int r = q * 32 + lane;
+    const int64_t t = tile0 + r;
+    const bool tv = t < p.n_tgt;
+    const int n_real = MODE == MODE_BWD ? (p.nbr ? 2 * p.f_in : p.f_in) : p.f_out;
+    float icnt = 1.f;
+    if (MODE == MODE_BWD && p.nbr != nullptr && tv) {
+        int4 nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+        int cnt = (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
+        icnt = 1.f / (float)(cnt > 0 ? cnt : 1);
+    }
+    const bool want_stats = MODE != MODE_BWD && my_stats != nullptr;
+    if (want_stats) {
+        for (int c = threadIdx.x; c < 2 * p.np; c += TC_THREADS) red_s[c] = 0.f;
+        __syncthreads();
+    }
+    for (int chunk = grp; chunk * 32 < p.np; chunk += TC_WARPS / 4) {
+        const int c0 = chunk * 32;
+        float v[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (MODE != MODE_BWD) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const int n = c0 + i;
+                if (n >= n_real) continue;
+                if (p.bias != nullptr) {
+                    float4 bi = ldg4(p.bias + n);
+                    v[i] += bi.x; v[i + 1] += bi.y; v[i + 2] += bi.z; v[i + 3] += bi.w;
+                }
+            }
+            if (tv) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int n = c0 + i;
+                    if (n >= n_real) continue;
+                    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    if (p.out_scale != nullptr) {
+                        float4 os = ldg4(p.out_scale + n), oh = ldg4(p.out_shift + n);
+                        o.x = fmaf(o.x, os.x, oh.x); o.y = fmaf(o.y, os.y, oh.y);
+                        o.z = fmaf(o.z, os.z, oh.z); o.w = fmaf(o.w, os.w, oh.w);
+                    }
+                    if (p.relu_out) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f_out + n) = o;
+                }
+            }
+            if (want_stats) {
+                float sq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (!tv) v[i] = 0.f;
+                    sq[i] = v[i] * v[i];
+                }
+                float s = warp_colsum32(v);
+                float s2 = warp_colsum32(sq);
+                if (c0 + lane < n_real) {
+                    atomicAdd(&red_s[c0 + lane], s);
+                    atomicAdd(&red_s[p.np + c0 + lane], s2);
+                }
+            }
+        } else if (tv) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const int n = c0 + i;
+                if (n >= n_real) continue;
+                const bool is_agg = p.nbr != nullptr && n < p.f_in;
+                float s = is_agg ? icnt : 1.f;
+                float* dst = is_agg ? p.d_agg : p.d_self;
+                int col = is_agg ? n : (p.nbr ? n - p.f_in : n);
+                *reinterpret_cast<float4*>(dst + (size_t)t * p.f_in + col) =
+                    make_float4(v[i] * s, v[i + 1] * s, v[i + 2] * s, v[i + 3] * s);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    if (want_stats) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < n_real; c += TC_THREADS) {
+            my_stats[c] += (double)red_s[c];
+            my_stats[p.f_out + c] += (double)red_s[p.np + c];
+        }
+    }
+}
+
+template <int MODE, int FE>
+__global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_empty[4];
+    __shared__ uint64_t bar_acc[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_s[512];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int b_atom_bytes = p.np * ATOM_ROW_BYTES;
+    const int stage_bytes = 2 * A_ATOM_BYTES + 2 * b_atom_bytes;
+
+    if (tid == 0) {
+        for (int s = 0; s < 4; ++s) mbar_init(&bar_empty[s], 1);
+        mbar_init(&bar_acc[0], 1);
+        mbar_init(&bar_acc[1], 1);
+        fence_barrier_init();
+    }
+    if (tid < 32) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t idesc = make_idesc_tf32(TC_M, p.np);
+
+    double* my_stats = nullptr;
+    if (MODE != MODE_BWD && p.stats != nullptr) {
+        my_stats = p.stats + (size_t)blockIdx.x * 2 * p.f_out;
+        for (int c = tid; c < 2 * p.f_out; c += TC_THREADS) my_stats[c] = 0.0;
+    }
+    double* my_db = nullptr;
+    if (MODE == MODE_BWD && p.db_partials != nullptr) {
+        my_db = p.db_partials + (size_t)blockIdx.x * p.f_out;
+        for (int c = tid; c < p.f_out; c += TC_THREADS) my_db[c] = 0.0;
+    }
+
+    const int64_t n_tiles = (p.n_tgt + TC_M - 1) / TC_M;
+    uint32_t it = 0;          // global stage-iteration counter
+    uint32_t tile_cnt = 0;    // tiles processed by this CTA
+    int64_t prev_tile0 = -1;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t tile0 = tile * TC_M;
+        const uint32_t acc = tile_cnt & 1;
+        const uint32_t tmem_acc = tmem_base + acc * (uint32_t)p.np;
+        if (MODE == MODE_BWD && my_db != nullptr) {
+            __syncthreads();
+            for (int c = tid; c < p.f_out; c += TC_THREADS) red_s[c] = 0.f;
+            __syncthreads();
+        }
+        for (int a = 0; a < p.ka; ++a, ++it) {
+            const uint32_t s = it % (uint32_t)p.stages;
+            const uint32_t use = it / (uint32_t)p.stages;
+            uint8_t* st = smem + (size_t)s * stage_bytes;
+            uint8_t* a_hi = st;
+            uint8_t* a_lo = st + A_ATOM_BYTES;
+            uint8_t* b_hi = st + 2 * A_ATOM_BYTES;
+            uint8_t* b_lo = b_hi + b_atom_bytes;
+            // the MMAs that last read this stage must have completed
+            mbar_wait(&bar_empty[s], (use & 1) ^ 1);
+            // B atom (hi | lo): straight copy of the pre-packed image
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.b_packed) + (size_t)a * (2 * b_atom_bytes / 16);
+                float4* dst = reinterpret_cast<float4*>(b_hi);
+                for (int i = tid; i < 2 * b_atom_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
+            }
+            if (MODE == MODE_FWD_DENSE) {
+                produce_rows(p, a_hi, a_lo, tile0, a * ATOM_K);
+            } else if (MODE == MODE_FWD_GATHER) {
+                if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K);
+                else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K);
+            } else {
+                produce_dz(p, a_hi, a_lo, tile0, a * ATOM_K, red_s);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after_sync();
+                const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+                for (int kk = 0; kk < ATOM_K / 8; ++kk) {
+                    const uint32_t ko = kk * 32;
+                    mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bh + ko), idesc, (a > 0 || kk > 0) ? 1u : 0u);
+                    mma_tf32(tmem_acc, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
+                    mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
+                }
+                mma_commit(&bar_empty[s]);
+                if (a == p.ka - 1) mma_commit(&bar_acc[acc]);
+            }
+        }
+        if (MODE == MODE_BWD && my_db != nullptr) {
+            __syncthreads();
+            for (int c = tid; c < p.f_out; c += TC_THREADS) my_db[c] += (double)red_s[c];
+        }
+        // deferred epilogue of the previous tile (its MMAs finished long ago)
+        if (prev_tile0 >= 0) {
+            const uint32_t pacc = acc ^ 1;
+            mbar_wait(&bar_acc[pacc], ((tile_cnt - 1) >> 1) & 1);
+            tc_fence_after_sync();
+            epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, red_s + (MODE == MODE_BWD ? 256 : 0), my_stats);
+        }
+        prev_tile0 = tile0;
+        ++tile_cnt;
+    }
+    if (prev_tile0 >= 0) {
+        const uint32_t pacc = (tile_cnt - 1) & 1;
+        mbar_wait(&bar_acc[pacc], ((tile_cnt - 1) >> 1) & 1);
+        tc_fence_after_sync();
+        epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, red_s + (MODE == MODE_BWD ? 256 : 0), my_stats);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- weight packing: w[n, k] (row stride ld) -> per K-atom swizzled hi / lo images ---------------
+__global__ void pack_b_kernel(const float* __restrict__ w, int n_rows, int ld, int seg_len, int n_segs, int seg_pad,
+                              int np, float* __restrict__ packed) {
+    const int ka = n_segs * seg_pad / ATOM_K;
+    const long long total = (long long)ka * np * ATOM_K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(i % ATOM_K);
+        int n = (int)((i / ATOM_K) % np);
+        int a = (int)(i / ((long long)ATOM_K * np));
+        int kp = a * ATOM_K + k;            // padded k
+        int seg = kp / seg_pad, kk = kp % seg_pad;
+        float v = 0.f;
+        if (n < n_rows && kk < seg_len) v = w[(size_t)n * ld + seg * seg_len + kk];
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        size_t base = (size_t)a * 2 * np * ATOM_K;
+        uint32_t off = atom_off(n, k) / 4;
+        packed[base + off] = hi;
+        packed[base + (size_t)np * ATOM_K + off] = lo;
+    }
+}
+
+}  // namespace dgnn
+
+using namespace dgnn;
+
+static inline int ceil32(int x) { return (x + 31) / 32 * 32; }
+
+extern "C" int dgnn_tc_packed_floats(int n_rows, int seg_len, int n_segs) {
+    return (n_segs * ceil32(seg_len) / ATOM_K) * 2 * ceil32(n_rows) * ATOM_K;
+}
+
+extern "C" int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len, int n_segs, float* packed,
+                                void* stream) {
+    DGNN_REQUIRE(w && packed, "null pointer");
+    int np = ceil32(n_rows), seg_pad = ceil32(seg_len);
+    long long total = (long long)(n_segs * seg_pad) * np;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 1024) grid = 1024;
+    pack_b_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, n_rows, ld, seg_len, n_segs, seg_pad, np, packed);
+    return check_launch("dgnn_pack_b_tf32");
+}
+
+static int tc_stage_config(int np, int* stages, size_t* smem) {
+    int stage_bytes = 2 * A_ATOM_BYTES + 2 * np * ATOM_ROW_BYTES;
+    int s = (200 * 1024) / stage_bytes;
+    if (s > 4) s = 4;
+    if (s < 2) return 1;
+    *stages = s;
+    *smem = (size_t)s * stage_bytes + 1024;
+    return 0;
+}
+
+template <int MODE, int FE>
+static int launch_tc(const TcArgs& p, size_t smem, cudaStream_t st, const char* what) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(layer_tc_kernel<MODE, FE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             210 * 1024);
+        if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));
+        configured = true;
+    }
+    layer_tc_kernel<MODE, FE><<<sm_count(), TC_THREADS, smem, st>>>(p);
+    return check_launch(what);
+}
+
+extern "C" int dgnn_tc_grid(void) { return sm_count(); }
+
+// 1 if the tensor-core path supports these widths
+extern "C" int dgnn_tc_supported(int f_in, int f_out, int gather) {
+    (void)gather;
+    return (f_in % 4 == 0 && f_out % 4 == 0 && ceil32(f_out) <= 256 && ceil32(2 * f_in) <= 256) ? 1 : 0;
+}
+
+extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                                 const int32_t* nbr, const float* ea, int fe, const float* w_e, const float* b_e,
+                                 const float* b_packed, const float* bias, const float* out_scale,
+                                 const float* out_shift, int relu_out, int64_t n_tgt, int f_in, int f_out, float* out,
+                                 float* agg_save, double* stats, void* stream) {
+    DGNN_REQUIRE(f_in % 4 == 0 && f_out % 4 == 0, "widths must be multiples of 4");
+    DGNN_REQUIRE(ceil32(f_out) <= 256, "f_out too wide for one UMMA tile");
+    DGNN_REQUIRE(x_in && b_packed && out, "null pointer");
+    if (w_e == nullptr) fe = 0;
+    DGNN_REQUIRE(fe == 0 || fe == 20 || fe % 4 == 0, "edge feature width must be a multiple of 4");
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;
+    p.nbr = nbr; p.ea = ea; p.w_e = w_e; p.b_e = b_e; p.b_packed = b_packed;
+    const int seg = ceil32(f_in) / ATOM_K;
+    p.ka_agg = nbr ? seg : 0;
+    p.ka = nbr ? 2 * seg : seg;
+    p.np = ceil32(f_out);
+    p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
+    p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
+    p.out = out; p.agg_save = agg_save; p.stats = stats;
+    size_t smem;
+    DGNN_REQUIRE(tc_stage_config(p.np, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    cudaStream_t st = as_stream(stream);
+    if (nbr == nullptr) return launch_tc<MODE_FWD_DENSE, 0>(p, smem, st, "dgnn_layer_fwd_tc");
+    switch (fe) {
+        case 0: return launch_tc<MODE_FWD_GATHER, 0>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 4: return launch_tc<MODE_FWD_GATHER, 4>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 8: return launch_tc<MODE_FWD_GATHER, 8>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 12: return launch_tc<MODE_FWD_GATHER, 12>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 16: return launch_tc<MODE_FWD_GATHER, 16>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 20: return launch_tc<MODE_FWD_GATHER, 20>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 24: return launch_tc<MODE_FWD_GATHER, 24>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 28: return launch_tc<MODE_FWD_GATHER, 28>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 32: return launch_tc<MODE_FWD_GATHER, 32>(p, smem, st, "dgnn_layer_fwd_tc");
+    }
+    return fail("dgnn_layer_fwd_tc", "unsupported edge feature width");
+}
+
+extern "C" int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
+                                 const float* mean, const float* rstd, const float* b_packed, const int32_t* nbr,
+                                 int64_t n_tgt, int f_in, int f_out, float* d_agg, float* d_self, double* db_partials,
+                                 void* stream) {
+    DGNN_REQUIRE(f_in % 4 == 0 && f_out % 4 == 0, "widths must be multiples of 4");
+    const int n_real = nbr ? 2 * f_in : f_in;
+    DGNN_REQUIRE(ceil32(n_real) <= 256, "2*f_in too wide for one UMMA tile");
+    DGNN_REQUIRE(f_out <= 256, "f_out too wide for the shared column sums");
+    DGNN_REQUIRE(dy && b_packed && d_self && (!nbr || d_agg), "null pointer");
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    p.dy = dy; p.z = z; p.ng = g; p.na = a; p.nb = b; p.nmean = mean; p.nrstd = rstd;
+    p.b_packed = b_packed; p.nbr = nbr;
+    p.ka = ceil32(f_out) / ATOM_K; p.ka_agg = 0;
+    p.np = ceil32(n_real);
+    p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
+    p.d_agg = d_agg; p.d_self = d_self; p.db_partials = db_partials;
+    size_t smem;
+    DGNN_REQUIRE(tc_stage_config(p.np, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    return launch_tc<MODE_BWD, 0>(p, smem, as_stream(stream), "dgnn_dense_bwd_tc");
+}

@@ -8,6 +8,7 @@ streams and autograd plumbing only; all arithmetic on activations happens in ``l
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -19,6 +20,19 @@ from .graph import EllGraph, pad4
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def use_tensor_cores() -> bool:
+    """tcgen05 path for the dense transforms unless DGNN_FMA_ONLY=1 (generic FP32 path)."""
+    return os.environ.get("DGNN_FMA_ONLY", "0") != "1"
+
+
+def pack_b(w: torch.Tensor, n_rows: int, seg_len: int, n_segs: int) -> torch.Tensor:
+    """``w`` float32[n_rows, n_segs*seg_len] (row-major) -> 128B-swizzled TF32 hi/lo K-atoms."""
+    w = w.contiguous()
+    out = torch.empty(lib().dgnn_tc_packed_floats(n_rows, seg_len, n_segs), dtype=torch.float32, device=w.device)
+    call("dgnn_pack_b_tf32", ptr(w), n_rows, w.shape[1], seg_len, n_segs, ptr(out), _stream())
+    return out
 
 
 # --------------------------------------------------------------------------- parameter packing
@@ -86,6 +100,8 @@ class PackedConv:
     bias: torch.Tensor
     w_e: Optional[torch.Tensor]
     b_e: Optional[torch.Tensor]
+    b_fwd: Optional[torch.Tensor] = None   # tcgen05 operand of the forward  ([W_j | W_i], K-major atoms)
+    b_bwd: Optional[torch.Tensor] = None   # tcgen05 operand of the backward ([W_j | W_i]^T)
 
 
 def pack_conv(c: ConvSpec, fe_p: int) -> PackedConv:
@@ -102,8 +118,11 @@ def pack_conv(c: ConvSpec, fe_p: int) -> PackedConv:
     if c.w_e is not None:
         w_e = _pad2(c.w_e.detach(), fi, fe_p).contiguous()
         b_e = _pad1(c.b_e.detach(), fi).contiguous()
-    return PackedConv(fi, c.f_out, fe_p if c.w_e is not None else 0, wt_cat, w_cat, c.b_j.detach().contiguous(),
-                      w_e, b_e)
+    pk = PackedConv(fi, c.f_out, fe_p if c.w_e is not None else 0, wt_cat, w_cat, c.b_j.detach().contiguous(),
+                    w_e, b_e)
+    if use_tensor_cores() and lib().dgnn_tc_supported(fi, c.f_out, 1):
+        pk.b_fwd = pack_b(w_cat, c.f_out, fi, 2)
+    return pk
 
 
 # --------------------------------------------------------------------------- normalisation helpers
@@ -154,17 +173,17 @@ class Saved:
 
 
 def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGraph], pk_wt, pk_bias, w_e, b_e, fe,
-               out_aff: Optional[Affine], relu_out: bool, n_tgt, f_in, f_out, want_agg, want_stats):
+               out_aff: Optional[Affine], relu_out: bool, n_tgt, f_in, f_out, want_agg, want_stats, b_packed=None):
     dev = x_in.device
     out = torch.empty((n_tgt, f_out), dtype=torch.float32, device=dev)
     agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if want_agg else None
     stats = None
     if want_stats:
-        grid = lib().dgnn_layer_grid(f_in, f_out)
+        grid = lib().dgnn_tc_grid() if b_packed is not None else lib().dgnn_layer_grid(f_in, f_out)
         stats = torch.empty((grid, 2, f_out), dtype=torch.float64, device=dev)
-    call("dgnn_layer_fwd", ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+    call("dgnn_layer_fwd_tc" if b_packed is not None else "dgnn_layer_fwd", ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
          int(relu_in), ptr(g.nbr) if g is not None else None, ptr(g.ea_in) if (g is not None and fe) else None, fe,
-         ptr(w_e), ptr(b_e), ptr(pk_wt), ptr(pk_bias),
+         ptr(w_e), ptr(b_e), ptr(b_packed) if b_packed is not None else ptr(pk_wt), ptr(pk_bias),
          ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None, int(relu_out),
          n_tgt, f_in, f_out, ptr(out), ptr(agg), ptr(stats), _stream())
     return out, agg, stats
@@ -195,7 +214,7 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             raise NotImplementedError("normalization must be 'b' or 'l' (the reference crashes otherwise, Static:218)")
         if batch_stats:
             z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None, False,
-                                       g.n_tgt, pk.f_in, pk.f_out, save, True)
+                                       g.n_tgt, pk.f_in, pk.f_out, save, True, b_packed=pk.b_fwd)
             aff = batch_affine(c.norm, stats, g.n_tgt, pk.f_out, dev, update_running=training)
             if save:
                 sv.z.append(z); sv.agg.append(agg); sv.aff.append(aff); sv.packed.append(pk)
@@ -203,7 +222,7 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
         else:
             aff = eval_affine(c.norm, pk.f_out, dev)
             h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
-                                 g.n_tgt, pk.f_in, pk.f_out, False, False)
+                                 g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd)
             in_aff, relu_in = None, False
     n_out = graphs[-1].n_tgt
     f_last = spec.convs[-1].f_out
@@ -225,9 +244,12 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
     wt = spec.dec0_w.detach().t().contiguous()
     b0 = spec.dec0_b.detach().contiguous()
     dn = spec.dec_norm
+    bd = None
+    if use_tensor_cores() and lib().dgnn_tc_supported(f_last, f_d, 0):
+        bd = pack_b(spec.dec0_w.detach(), f_d, f_last, 1)
     if batch_stats:
         z_d, _, stats = _layer_fwd(h, in_aff, relu_in, None, wt, b0, None, None, 0, None, False, n_out, f_last, f_d,
-                                   False, True)
+                                   False, True, b_packed=bd)
         aff_d = batch_affine(dn, stats, n_out, f_d, dev, update_running=training)
         hd, hd_aff, hd_relu = z_d, aff_d, True
         if save:
@@ -235,7 +257,7 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
     else:
         aff_d = eval_affine(dn, f_d, dev)
         hd, _, _ = _layer_fwd(h, in_aff, relu_in, None, wt, b0, None, None, 0, aff_d, True, n_out, f_last, f_d,
-                              False, False)
+                              False, False, b_packed=bd)
         hd_aff, hd_relu = None, False
     w3, b3 = spec.dec3_w.detach().contiguous(), spec.dec3_b.detach().contiguous()
     out = torch.empty((n_out, spec.out_dim), dtype=torch.float32, device=dev)
@@ -277,11 +299,18 @@ def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, i
     gq, aq, bq = coeffs
     d_self = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev)
     d_agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if g is not None else None
-    grid = lib().dgnn_layer_grid(f_in, f_out)
-    db_p = torch.empty((grid, f_out), dtype=torch.float64, device=dev)
-    call("dgnn_dense_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(w_cat),
-         ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, k_total, ptr(d_agg), ptr(d_self), ptr(db_p),
-         _stream())
+    if use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 1 if g is not None else 0) and f_out <= 256:
+        # operand B of the backward: [W_j | W_i]^T, i.e. rows = columns of d[agg|self], K = f_out
+        b_bwd = pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
+        db_p = torch.empty((lib().dgnn_tc_grid(), f_out), dtype=torch.float64, device=dev)
+        call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(b_bwd),
+             ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, ptr(d_agg), ptr(d_self), ptr(db_p), _stream())
+    else:
+        grid = lib().dgnn_layer_grid(f_in, f_out)
+        db_p = torch.empty((grid, f_out), dtype=torch.float64, device=dev)
+        call("dgnn_dense_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(w_cat),
+             ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, k_total, ptr(d_agg), ptr(d_self), ptr(db_p),
+             _stream())
     db = _reduce(db_p)
     splits = lib().dgnn_dw_splits(f_out, k_total)
     dw_p = torch.empty((splits, f_out, k_total), dtype=torch.float32, device=dev)

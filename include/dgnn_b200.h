@@ -96,6 +96,32 @@ int dgnn_layer_fwd(const float* x_in, const float* in_scale, const float* in_shi
                    int64_t n_tgt, int f_in, int f_out,
                    float* out, float* agg_save, double* stats, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM, 3xTF32) variants for widths that fit one UMMA tile --------
+ * Same semantics as dgnn_layer_fwd / dgnn_dense_bwd; the dense operand is pre-packed by
+ * dgnn_pack_b_tf32 into 128B-swizzled K-atoms split into TF32 hi / lo parts:
+ *   forward : w = [W_j | W_i] (float32[f_out, 2 f_in] or [f_out, f_in] for a dense layer),
+ *             n_rows = f_out, ld = row stride, seg_len = f_in, n_segs = 2 (1 for dense)
+ *   backward: w = [W_j | W_i]^T (float32[k_total, f_out]), n_rows = k_total, ld = f_out,
+ *             seg_len = f_out, n_segs = 1
+ * packed holds dgnn_tc_packed_floats(n_rows, seg_len, n_segs) floats.  Partial-sum workspaces
+ * (stats, db_partials) have dgnn_tc_grid() rows. */
+int dgnn_tc_supported(int f_in, int f_out, int gather);
+int dgnn_tc_grid(void);
+int dgnn_tc_packed_floats(int n_rows, int seg_len, int n_segs);
+int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len, int n_segs, float* packed,
+                     void* stream);
+int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                      const int32_t* nbr, const float* ea, int fe,
+                      const float* w_e, const float* b_e,
+                      const float* b_packed, const float* bias,
+                      const float* out_scale, const float* out_shift, int relu_out,
+                      int64_t n_tgt, int f_in, int f_out,
+                      float* out, float* agg_save, double* stats, void* stream);
+int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
+                      const float* mean, const float* rstd,
+                      const float* b_packed, const int32_t* nbr, int64_t n_tgt, int f_in, int f_out,
+                      float* d_agg, float* d_self, double* db_partials, void* stream);
+
 /* Reduce per-CTA (sum, sum^2) partials and produce the normalisation's per-channel affine.
  * mode 0 = BatchNorm1d training statistics (biased var for normalisation; running_mean /
  *          running_var (unbiased) updated with `momentum` when non-NULL),

@@ -1,0 +1,108 @@
+"""GPU: the tcgen05 (3xTF32) kernels against float64 references and against the generic FP32
+kernels, called through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import make_graph
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a = a.double().cpu(); b = b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.mark.parametrize("n,f_in,f_out", [(1000, 28, 64), (129, 64, 128), (4096, 128, 128), (777, 128, 64), (50, 32, 32)])
+def test_dense_forward_tc_matches_fp64(n, f_in, f_out):
+    from dgnn_b200 import engine
+    torch.manual_seed(0)
+    x = torch.randn(n, f_in, device=DEV)
+    w = torch.randn(f_out, f_in, device=DEV) * 0.2
+    b = torch.randn(f_out, device=DEV)
+    sc = torch.rand(f_in, device=DEV) + 0.5
+    sh = torch.randn(f_in, device=DEV) * 0.3
+    aff = engine.Affine(sc, sh)
+    bp = engine.pack_b(w, f_out, f_in, 1)
+    out, _, stats = engine._layer_fwd(x, aff, True, None, None, b, None, None, 0, None, False, n, f_in, f_out,
+                                      False, True, b_packed=bp)
+    h = torch.relu(x.double() * sc.double() + sh.double())
+    ref = h @ w.double().t() + b.double()
+    assert _rel(out, ref) < 2e-6
+    # per-channel (sum, sum^2) partials
+    st = stats.sum(0)
+    np.testing.assert_allclose(st[0].cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(st[1].cpu().numpy(), (ref * ref).sum(0).cpu().numpy(), rtol=1e-5)
+    # eval epilogue: affine + relu fused
+    osc = torch.rand(f_out, device=DEV) + 0.5
+    osh = torch.randn(f_out, device=DEV)
+    out2, _, _ = engine._layer_fwd(x, aff, True, None, None, b, None, None, 0, engine.Affine(osc, osh), True, n, f_in,
+                                   f_out, False, False, b_packed=bp)
+    ref2 = torch.relu(ref * osc.double() + osh.double())
+    assert _rel(out2, ref2) < 2e-6
+
+
+@pytest.mark.parametrize("f_in,f_out,fe", [(28, 64, 20), (64, 128, 20), (128, 128, 20), (32, 32, 0)])
+def test_gather_forward_tc_matches_generic_kernel(f_in, f_out, fe):
+    from dgnn_b200 import engine
+    from dgnn_b200.graph import build_full_graph
+    g = make_graph(900, seed=3)
+    n = g["n"]
+    ei = torch.from_numpy(g["adj"].T.astype(np.int64)).contiguous()
+    torch.manual_seed(1)
+    ea = torch.randn(4 * n, fe) if fe else None
+    eg = build_full_graph(ei, ea, n, DEV, order="rcm")
+    x = torch.randn(n, f_in, device=DEV)
+    w_cat = torch.randn(f_out, 2 * f_in, device=DEV) * 0.2
+    bias = torch.randn(f_out, device=DEV)
+    w_e = torch.randn(f_in, fe, device=DEV) * 0.3 if fe else None
+    b_e = torch.randn(f_in, device=DEV) if fe else None
+    sc = torch.rand(f_in, device=DEV) + 0.5
+    sh = torch.randn(f_in, device=DEV) * 0.3
+    aff = engine.Affine(sc, sh)
+    wt = w_cat.t().contiguous()
+    o1, a1, s1 = engine._layer_fwd(x, aff, True, eg, wt, bias, w_e, b_e, fe, None, False, n, f_in, f_out, True, True)
+    bp = engine.pack_b(w_cat, f_out, f_in, 2)
+    o2, a2, s2 = engine._layer_fwd(x, aff, True, eg, wt, bias, w_e, b_e, fe, None, False, n, f_in, f_out, True, True,
+                                   b_packed=bp)
+    assert _rel(a2, a1) < 1e-6
+    assert _rel(o2, o1) < 5e-6
+    np.testing.assert_allclose(s2.sum(0).cpu().numpy(), s1.sum(0).cpu().numpy(), rtol=2e-5, atol=1e-2)
+
+
+@pytest.mark.parametrize("n,f_in,f_out,gather", [(1000, 28, 64, True), (3000, 128, 128, True), (515, 128, 64, False),
+                                                  (640, 64, 128, True)])
+def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather):
+    from dgnn_b200 import engine
+    from dgnn_b200._lib import call, lib, ptr
+    torch.manual_seed(2)
+    dy = torch.randn(n, f_out, device=DEV)
+    z = torch.randn(n, f_out, device=DEV)
+    gq, aq, bq = (torch.randn(f_out, device=DEV) for _ in range(3))
+    mean = torch.randn(f_out, device=DEV) * 0.1
+    rstd = torch.rand(f_out, device=DEV) + 0.5
+    k_total = 2 * f_in if gather else f_in
+    w_cat = torch.randn(f_out, k_total, device=DEV) * 0.2
+    nbr = None
+    if gather:
+        nbr = torch.randint(0, n, (n, 4), device=DEV, dtype=torch.int32)
+        nbr[::5, 3] = -1
+        nbr[::7, 1] = -1
+    bp = engine.pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
+    d_self = torch.empty(n, f_in, device=DEV)
+    d_agg = torch.empty(n, f_in, device=DEV) if gather else None
+    db_p = torch.empty(lib().dgnn_tc_grid(), f_out, dtype=torch.float64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(mean), ptr(rstd), ptr(bp), ptr(nbr), n,
+         f_in, f_out, ptr(d_agg), ptr(d_self), ptr(db_p), st)
+    dz = gq.double() * dy.double() - (aq.double() + (z.double() - mean.double()) * rstd.double() * bq.double())
+    dA = dz @ w_cat.double()
+    if gather:
+        cnt = (nbr >= 0).sum(1).clamp(min=1).double()
+        assert _rel(d_agg, dA[:, :f_in] / cnt[:, None]) < 3e-6
+        assert _rel(d_self, dA[:, f_in:]) < 3e-6
+    else:
+        assert _rel(d_self, dA) < 3e-6
+    np.testing.assert_allclose(db_p.sum(0).cpu().numpy(), dz.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
