@@ -1,19 +1,23 @@
 // Tensor-core (tcgen05 + TMEM) version of the fused layer kernels for widths that fit one
 // UMMA tile: f_out (forward) / k_total (backward) <= 256.
 //
-//   forward :  z = [agg | h] . [W_j | W_i]^T      (dgnn_layer_fwd_tc, gather or dense mode)
-//   backward:  [d_agg | d_self] = dz . [W_j | W_i] (dgnn_dense_bwd_tc)
+//   forward :  z = [agg | h] . [W_j | W_i]^T       (dgnn_layer_fwd_tc, gather or dense mode)
+//   backward:  [d_agg | d_self] = dz . [W_j | W_i]  (dgnn_dense_bwd_tc)
 //
-// One persistent CTA (512 threads, 1 per SM) owns tiles of 128 cells (UMMA M = 128).  The A
-// operand never exists in global memory: per K-atom (32 features) all 16 warps produce the
-// [128 x 32] slice — gathering neighbour rows and applying the edge filter (forward), or
-// applying the normalisation backward to dy (backward) — split it into TF32 hi/lo parts and
-// store it straight into the 128B-swizzled UMMA layout of a ring stage, next to that atom's
-// pre-packed weight slice.  One thread then issues the 12 tcgen05.mma of the stage
-// (3xTF32: hi*hi + lo*hi + hi*lo, 4 k-steps) which accumulate in TMEM while the CTA already
-// produces the next atom; tcgen05.commit frees the stage.  Accumulators are double-buffered in
-// TMEM (2 x N columns), so the epilogue of tile i (tcgen05.ld -> bias / affine / ReLU / BN
-// partials -> global) runs after tile i+1 has been issued.
+// One persistent CTA per SM, warp-specialised, no CTA-wide barrier in the main loop:
+//   * 16 producer warps own tiles of 128 cells (UMMA M = 128).  The A operand never exists in
+//     global memory: per K-atom (32 features) each warp produces its 8 rows of the [128 x 32]
+//     slice — gathering neighbour rows and applying the edge filter (forward), or applying the
+//     normalisation backward to dy (backward) — splits it into TF32 hi/lo parts and stores it
+//     straight into the 128B-swizzled UMMA layout of a ring stage, then arrives on the stage's
+//     `full` mbarrier.  Fast warps run ahead by the ring depth.
+//   * 1 MMA warp: for every stage it bulk-copies (TMA, cp.async.bulk) that atom's pre-packed
+//     weight slice next to the A slice, waits for `full`, issues the 12 tcgen05.mma of the stage
+//     (3xTF32: hi*hi + lo*hi + hi*lo, 4 k-steps) accumulating in TMEM, and tcgen05.commit's the
+//     stage's `empty` mbarrier.
+//   * accumulators are double-buffered in TMEM (2 x N columns): the producer warps run the
+//     epilogue of tile i (tcgen05.ld -> bias / affine / ReLU / BN partials -> global) after they
+//     have produced tile i+1, and hand the buffer back through `acc_free`.
 #include "umma.cuh"
 #include "common.cuh"
 
@@ -22,9 +26,10 @@ namespace dgnn {
 using namespace umma;
 
 constexpr int TC_M = 128;
-constexpr int TC_THREADS = 512;
-constexpr int TC_WARPS = TC_THREADS / 32;
+constexpr int NPW = 16;                        // producer warps
+constexpr int TC_THREADS = (NPW + 1) * 32;     // + 1 MMA / TMA warp
 constexpr int A_ATOM_BYTES = TC_M * ATOM_ROW_BYTES;  // 16 KB
+constexpr int MAX_STAGES = 4;
 
 enum { MODE_FWD_DENSE = 0, MODE_FWD_GATHER = 1, MODE_BWD = 2 };
 
@@ -89,20 +94,22 @@ __device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, int r
     *reinterpret_cast<float4*>(a_lo + off) = l;
 }
 
-// A-atom = h(x_in[tile rows, f0 .. f0+32))  (self part of a gather layer, or a dense layer)
-__device__ __forceinline__ void produce_rows(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0) {
+// warp `w` fills its 8 rows of the atom with h(x_in[row, f0 .. f0+32))
+__device__ __forceinline__ void produce_rows(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0,
+                                             int warp, int lane) {
     const bool relu = p.relu_in != 0;
+    const int c = (lane & 7) * 4;
+    const int f = f0 + c;
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.in_scale != nullptr && f < p.f_in) { sc = ldg4(p.in_scale + f); sh = ldg4(p.in_shift + f); }
 #pragma unroll
-    for (int it = 0; it < (TC_M * 8) / TC_THREADS; ++it) {
-        int idx = threadIdx.x + it * TC_THREADS;
-        int r = idx >> 3, c = (idx & 7) * 4;
-        int f = f0 + c;
-        int64_t t = tile0 + r;
+    for (int it = 0; it < 2; ++it) {
+        const int r = warp * 8 + (lane >> 3) + it * 4;
+        const int64_t t = tile0 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < p.n_tgt && f < p.f_in) {
             v = ldg4(p.x_in + (size_t)t * p.f_in + f);
             if (p.in_scale != nullptr) {
-                float4 sc = ldg4(p.in_scale + f), sh = ldg4(p.in_shift + f);
                 v.x = act(v.x, sc.x, sh.x, relu); v.y = act(v.y, sc.y, sh.y, relu);
                 v.z = act(v.z, sc.z, sh.z, relu); v.w = act(v.w, sc.w, sh.w, relu);
             } else if (relu) {
@@ -113,24 +120,24 @@ __device__ __forceinline__ void produce_rows(const TcArgs& p, uint8_t* a_hi, uin
     }
 }
 
-// A-atom = dz[tile rows, f0 .. f0+32); column sums of dz go to red_s (shared floats, zeroed per tile)
+// warp `w` fills its 8 rows of the atom with dz[row, f0 .. f0+32); column sums go to red_db (shared)
 __device__ __forceinline__ void produce_dz(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0,
-                                           float* red_s) {
+                                           int warp, int lane, float* red_db) {
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int c = (threadIdx.x & 7) * 4;
+    const int c = (lane & 7) * 4;
     const int f = f0 + c;
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, m = a, rs = g;
+    const bool norm = p.ng != nullptr && f < p.f_out;
+    if (norm) { g = ldg4(p.ng + f); a = ldg4(p.na + f); b = ldg4(p.nb + f); m = ldg4(p.nmean + f); rs = ldg4(p.nrstd + f); }
 #pragma unroll
-    for (int it = 0; it < (TC_M * 8) / TC_THREADS; ++it) {
-        int idx = threadIdx.x + it * TC_THREADS;
-        int r = idx >> 3;
-        int64_t t = tile0 + r;
+    for (int it = 0; it < 2; ++it) {
+        const int r = warp * 8 + (lane >> 3) + it * 4;
+        const int64_t t = tile0 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < p.n_tgt && f < p.f_out) {
             float4 d = ldg4(p.dy + (size_t)t * p.f_out + f);
-            if (p.ng != nullptr) {
+            if (norm) {
                 float4 zv = ldg4(p.z + (size_t)t * p.f_out + f);
-                float4 g = ldg4(p.ng + f), a = ldg4(p.na + f), b = ldg4(p.nb + f), m = ldg4(p.nmean + f),
-                       rs = ldg4(p.nrstd + f);
                 v.x = g.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
                 v.y = g.y * d.y - (a.y + (zv.y - m.y) * rs.y * b.y);
                 v.z = g.z * d.z - (a.z + (zv.z - m.z) * rs.z * b.z);
@@ -142,23 +149,24 @@ __device__ __forceinline__ void produce_dz(const TcArgs& p, uint8_t* a_hi, uint8
         }
         store_split4(a_hi, a_lo, r, c, v);
     }
-    if (p.db_partials != nullptr) {
+    if (red_db != nullptr) {
         // lanes l, l+8, l+16, l+24 share the column group
         cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
         cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
         cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
         cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-        if ((threadIdx.x & 31) < 8 && f < p.f_out) {
-            atomicAdd(&red_s[f], cs.x); atomicAdd(&red_s[f + 1], cs.y);
-            atomicAdd(&red_s[f + 2], cs.z); atomicAdd(&red_s[f + 3], cs.w);
+        if (lane < 8 && f < p.f_out) {
+            atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
+            atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
         }
     }
 }
 
-// A-atom = agg[tile rows, f0 .. f0+32): 16 lanes per cell, 2 features per lane
+// warp `w` fills its 8 rows of the atom with agg[row, f0 .. f0+32): 16 lanes per cell, 2 features per
+// lane; the 4 passes are software-pipelined (indices for all passes up front, neighbour rows one pass ahead)
 template <int FE>
-__device__ __forceinline__ void produce_agg(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void produce_agg(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0,
+                                            int warp, int lane) {
     const int sub = lane >> 4, li = lane & 15;
     const int F = p.f_in;
     const int f = f0 + li * 2;
@@ -180,18 +188,35 @@ __device__ __forceinline__ void produce_agg(const TcArgs& p, uint8_t* a_hi, uint
         sc0 = __ldg(p.in_scale + f); sc1 = __ldg(p.in_scale + f + 1);
         sh0 = __ldg(p.in_shift + f); sh1 = __ldg(p.in_shift + f + 1);
     }
-#pragma unroll 1
-    for (int cell = warp * 2 + sub; cell < TC_M; cell += TC_WARPS * 2) {
-        const int64_t t = tile0 + cell;
-        const bool tv = t < p.n_tgt;
-        int4 nb = make_int4(-1, -1, -1, -1);
-        if (tv) nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
-        const int nbv[4] = {nb.x, nb.y, nb.z, nb.w};
-        float2 xs[4];
+    // rows of this warp: 8w .. 8w+7; pass i handles rows 8w + 2i + sub
+    int4 nbs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t t = tile0 + warp * 8 + i * 2 + sub;
+        nbs[i] = make_int4(-1, -1, -1, -1);
+        if (t < p.n_tgt) nbs[i] = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+    }
+    float2 xs[4], xn[4];
+    {
+        const int nbv[4] = {nbs[0].x, nbs[0].y, nbs[0].z, nbs[0].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             xs[k] = make_float2(0.f, 0.f);
             if (nbv[k] >= 0 && fv) xs[k] = ldg2(p.x_in + (size_t)nbv[k] * F + f);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int cell = warp * 8 + i * 2 + sub;
+        const int64_t t = tile0 + cell;
+        const int nbv[4] = {nbs[i].x, nbs[i].y, nbs[i].z, nbs[i].w};
+        if (i < 3) {
+            const int nn[4] = {nbs[i + 1].x, nbs[i + 1].y, nbs[i + 1].z, nbs[i + 1].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xn[k] = make_float2(0.f, 0.f);
+                if (nn[k] >= 0 && fv) xn[k] = ldg2(p.x_in + (size_t)nn[k] * F + f);
+            }
         }
         float a0 = 0.f, a1 = 0.f;
         int cnt = 0;
@@ -219,12 +244,16 @@ __device__ __forceinline__ void produce_agg(const TcArgs& p, uint8_t* a_hi, uint
         a0 = fv ? a0 / d : 0.f;
         a1 = fv ? a1 / d : 0.f;
         store_split2(a_hi, a_lo, cell, li * 2, a0, a1);
-        if (p.agg_save != nullptr && tv && fv)
+        if (p.agg_save != nullptr && t < p.n_tgt && fv)
             *reinterpret_cast<float2*>(p.agg_save + (size_t)t * F + f) = make_float2(a0, a1);
+        if (i < 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xs[k] = xn[k];
+        }
     }
 }
 
-// butterfly transpose-reduce: on return lane l holds sum over the warp's 32 rows of column l
+// butterfly transpose-reduce: on return lane l holds the sum over the warp's 32 rows of column l
 __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -240,10 +269,11 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
     return v[0];
 }
 
+// one producer warp's share of a tile epilogue: TMEM lanes 32q..32q+31 (rows), column chunks grp, grp+4, ..
+// st_sum / st_sq: per-lane running column sums (chunk slot j = (chunk - grp)/4), kept across tiles
 template <int MODE>
-__device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int64_t tile0, float* red_s,
-                                         double* my_stats) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int64_t tile0, int warp, int lane,
+                                         double (&st_sum)[2], double (&st_sq)[2]) {
     const int q = warp & 3, grp = warp >> 2;
     const int r = q * 32 + lane;
     const int64_t t = tile0 + r;
@@ -255,24 +285,21 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
         int cnt = (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
         icnt = 1.f / (float)(cnt > 0 ? cnt : 1);
     }
-    const bool want_stats = MODE != MODE_BWD && my_stats != nullptr;
-    if (want_stats) {
-        for (int c = threadIdx.x; c < 2 * p.np; c += TC_THREADS) red_s[c] = 0.f;
-        __syncthreads();
-    }
-    for (int chunk = grp; chunk * 32 < p.np; chunk += TC_WARPS / 4) {
+    const bool want_stats = MODE != MODE_BWD && p.stats != nullptr;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int chunk = grp + 4 * j;
         const int c0 = chunk * 32;
+        if (c0 >= p.np) break;
         float v[32];
         tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         if (MODE != MODE_BWD) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
                 const int n = c0 + i;
-                if (n >= n_real) continue;
-                if (p.bias != nullptr) {
-                    float4 bi = ldg4(p.bias + n);
-                    v[i] += bi.x; v[i + 1] += bi.y; v[i + 2] += bi.z; v[i + 3] += bi.w;
-                }
+                if (n >= n_real || p.bias == nullptr) continue;
+                float4 bi = ldg4(p.bias + n);
+                v[i] += bi.x; v[i + 1] += bi.y; v[i + 2] += bi.z; v[i + 3] += bi.w;
             }
             if (tv) {
 #pragma unroll
@@ -298,12 +325,8 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                     if (!tv) v[i] = 0.f;
                     sq[i] = v[i] * v[i];
                 }
-                float s = warp_colsum32(v);
-                float s2 = warp_colsum32(sq);
-                if (c0 + lane < n_real) {
-                    atomicAdd(&red_s[c0 + lane], s);
-                    atomicAdd(&red_s[p.np + c0 + lane], s2);
-                }
+                st_sum[j] += (double)warp_colsum32(v);
+                st_sq[j] += (double)warp_colsum32(sq);
             }
         } else if (tv) {
 #pragma unroll
@@ -319,129 +342,145 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
             }
         }
     }
-    tc_fence_before_sync();
-    if (want_stats) {
-        __syncthreads();
-        for (int c = threadIdx.x; c < n_real; c += TC_THREADS) {
-            my_stats[c] += (double)red_s[c];
-            my_stats[p.f_out + c] += (double)red_s[p.np + c];
-        }
-    }
 }
 
 template <int MODE, int FE>
 __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_empty[4];
-    __shared__ uint64_t bar_acc[2];
+    __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
+    __shared__ uint64_t bar_acc_full[2], bar_acc_free[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float red_s[512];
+    __shared__ float red_db[256];
+    __shared__ double red_st[2 * 256];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int b_atom_bytes = p.np * ATOM_ROW_BYTES;
     const int stage_bytes = 2 * A_ATOM_BYTES + 2 * b_atom_bytes;
 
     if (tid == 0) {
-        for (int s = 0; s < 4; ++s) mbar_init(&bar_empty[s], 1);
-        mbar_init(&bar_acc[0], 1);
-        mbar_init(&bar_acc[1], 1);
+        for (int s = 0; s < MAX_STAGES; ++s) {
+            mbar_init(&bar_full[s], NPW + 1);   // 16 producer warps + the TMA arrive.expect_tx
+            mbar_init(&bar_empty[s], 1);        // tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bar_acc_full[b], 1);     // tcgen05.commit
+            mbar_init(&bar_acc_free[b], NPW);   // every producer warp after its epilogue share
+        }
         fence_barrier_init();
     }
-    if (tid < 32) tmem_alloc(&tmem_slot, 512);
+    for (int c = tid; c < 256; c += TC_THREADS) red_db[c] = 0.f;
+    for (int c = tid; c < 512; c += TC_THREADS) red_st[c] = 0.0;
+    if (warp == NPW) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
-    const uint32_t idesc = make_idesc_tf32(TC_M, p.np);
-
-    double* my_stats = nullptr;
-    if (MODE != MODE_BWD && p.stats != nullptr) {
-        my_stats = p.stats + (size_t)blockIdx.x * 2 * p.f_out;
-        for (int c = tid; c < 2 * p.f_out; c += TC_THREADS) my_stats[c] = 0.0;
-    }
-    double* my_db = nullptr;
-    if (MODE == MODE_BWD && p.db_partials != nullptr) {
-        my_db = p.db_partials + (size_t)blockIdx.x * p.f_out;
-        for (int c = tid; c < p.f_out; c += TC_THREADS) my_db[c] = 0.0;
-    }
-
     const int64_t n_tiles = (p.n_tgt + TC_M - 1) / TC_M;
-    uint32_t it = 0;          // global stage-iteration counter
-    uint32_t tile_cnt = 0;    // tiles processed by this CTA
-    int64_t prev_tile0 = -1;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t tile0 = tile * TC_M;
-        const uint32_t acc = tile_cnt & 1;
-        const uint32_t tmem_acc = tmem_base + acc * (uint32_t)p.np;
-        if (MODE == MODE_BWD && my_db != nullptr) {
-            __syncthreads();
-            for (int c = tid; c < p.f_out; c += TC_THREADS) red_s[c] = 0.f;
-            __syncthreads();
-        }
-        for (int a = 0; a < p.ka; ++a, ++it) {
-            const uint32_t s = it % (uint32_t)p.stages;
-            const uint32_t use = it / (uint32_t)p.stages;
-            uint8_t* st = smem + (size_t)s * stage_bytes;
-            uint8_t* a_hi = st;
-            uint8_t* a_lo = st + A_ATOM_BYTES;
-            uint8_t* b_hi = st + 2 * A_ATOM_BYTES;
-            uint8_t* b_lo = b_hi + b_atom_bytes;
-            // the MMAs that last read this stage must have completed
-            mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-            // B atom (hi | lo): straight copy of the pre-packed image
-            {
-                const float4* src = reinterpret_cast<const float4*>(p.b_packed) + (size_t)a * (2 * b_atom_bytes / 16);
-                float4* dst = reinterpret_cast<float4*>(b_hi);
-                for (int i = tid; i < 2 * b_atom_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
-            }
-            if (MODE == MODE_FWD_DENSE) {
-                produce_rows(p, a_hi, a_lo, tile0, a * ATOM_K);
-            } else if (MODE == MODE_FWD_GATHER) {
-                if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K);
-                else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K);
-            } else {
-                produce_dz(p, a_hi, a_lo, tile0, a * ATOM_K, red_s);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after_sync();
-                const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+
+    if (warp == NPW) {
+        // ------------------------------------------------------------------ MMA / TMA warp
+        const uint32_t idesc = make_idesc_tf32(TC_M, p.np);
+        uint32_t it = 0, tile_cnt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const uint32_t acc = tile_cnt & 1;
+            const uint32_t tmem_acc = tmem_base + acc * (uint32_t)p.np;
+            for (int a = 0; a < p.ka; ++a, ++it) {
+                const uint32_t s = it % (uint32_t)p.stages;
+                const uint32_t use = it / (uint32_t)p.stages;
+                if (lane == 0) {
+                    uint8_t* st = smem + (size_t)s * stage_bytes;
+                    uint8_t* b_hi = st + 2 * A_ATOM_BYTES;
+                    mbar_wait(&bar_empty[s], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[s], 2u * (uint32_t)b_atom_bytes);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.b_packed) + (size_t)a * 2 * b_atom_bytes;
+                    bulk_g2s(b_hi, src, (uint32_t)b_atom_bytes, &bar_full[s]);
+                    bulk_g2s(b_hi + b_atom_bytes, src + b_atom_bytes, (uint32_t)b_atom_bytes, &bar_full[s]);
+                    if (a == 0 && tile_cnt >= 2) mbar_wait(&bar_acc_free[acc], ((tile_cnt >> 1) - 1) & 1);
+                    mbar_wait(&bar_full[s], use & 1);
+                    tc_fence_after_sync();
+                    const uint32_t ah = smem_u32(st), al = ah + A_ATOM_BYTES, bh = smem_u32(b_hi), bl = bh + b_atom_bytes;
 #pragma unroll
-                for (int kk = 0; kk < ATOM_K / 8; ++kk) {
-                    const uint32_t ko = kk * 32;
-                    mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bh + ko), idesc, (a > 0 || kk > 0) ? 1u : 0u);
-                    mma_tf32(tmem_acc, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
-                    mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
+                    for (int kk = 0; kk < ATOM_K / 8; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bh + ko), idesc, (a > 0 || kk > 0) ? 1u : 0u);
+                        mma_tf32(tmem_acc, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
+                        mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
+                    }
+                    mma_commit(&bar_empty[s]);
+                    if (a == p.ka - 1) mma_commit(&bar_acc_full[acc]);
                 }
-                mma_commit(&bar_empty[s]);
-                if (a == p.ka - 1) mma_commit(&bar_acc[acc]);
+                __syncwarp();
             }
         }
-        if (MODE == MODE_BWD && my_db != nullptr) {
-            __syncthreads();
-            for (int c = tid; c < p.f_out; c += TC_THREADS) my_db[c] += (double)red_s[c];
+    } else {
+        // ------------------------------------------------------------------ producer warps
+        double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};
+        uint32_t it = 0, tile_cnt = 0;
+        int64_t prev_tile0 = -1;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const int64_t tile0 = tile * TC_M;
+            for (int a = 0; a < p.ka; ++a, ++it) {
+                const uint32_t s = it % (uint32_t)p.stages;
+                const uint32_t use = it / (uint32_t)p.stages;
+                uint8_t* a_hi = smem + (size_t)s * stage_bytes;
+                uint8_t* a_lo = a_hi + A_ATOM_BYTES;
+                mbar_wait(&bar_empty[s], (use & 1) ^ 1);
+                if (MODE == MODE_FWD_DENSE) {
+                    produce_rows(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
+                } else if (MODE == MODE_FWD_GATHER) {
+                    if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
+                    else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
+                } else {
+                    produce_dz(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane, p.db_partials ? red_db : nullptr);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[s]);
+            }
+            if (prev_tile0 >= 0) {
+                const uint32_t pacc = (tile_cnt - 1) & 1;
+                mbar_wait(&bar_acc_full[pacc], ((tile_cnt - 1) >> 1) & 1);
+                tc_fence_after_sync();
+                epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_acc_free[pacc]);
+            }
+            prev_tile0 = tile0;
         }
-        // deferred epilogue of the previous tile (its MMAs finished long ago)
         if (prev_tile0 >= 0) {
-            const uint32_t pacc = acc ^ 1;
-            mbar_wait(&bar_acc[pacc], ((tile_cnt - 1) >> 1) & 1);
+            const uint32_t pacc = (tile_cnt - 1) & 1;
+            mbar_wait(&bar_acc_full[pacc], ((tile_cnt - 1) >> 1) & 1);
             tc_fence_after_sync();
-            epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, red_s + (MODE == MODE_BWD ? 256 : 0), my_stats);
+            epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq);
         }
-        prev_tile0 = tile0;
-        ++tile_cnt;
-    }
-    if (prev_tile0 >= 0) {
-        const uint32_t pacc = (tile_cnt - 1) & 1;
-        mbar_wait(&bar_acc[pacc], ((tile_cnt - 1) >> 1) & 1);
-        tc_fence_after_sync();
-        epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, red_s + (MODE == MODE_BWD ? 256 : 0), my_stats);
+        if (MODE != MODE_BWD && p.stats != nullptr) {
+            const int grp = warp >> 2;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = (grp + 4 * j) * 32 + lane;
+                if (c < p.f_out) {
+                    atomicAdd(&red_st[c], st_sum[j]);
+                    atomicAdd(&red_st[256 + c], st_sq[j]);
+                }
+            }
+        }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (tid < 32) tmem_dealloc(tmem_base, 512);
+    if (MODE != MODE_BWD && p.stats != nullptr) {
+        double* my = p.stats + (size_t)blockIdx.x * 2 * p.f_out;
+        for (int c = tid; c < p.f_out; c += TC_THREADS) {
+            my[c] = red_st[c];
+            my[p.f_out + c] = red_st[256 + c];
+        }
+    }
+    if (MODE == MODE_BWD && p.db_partials != nullptr) {
+        double* my = p.db_partials + (size_t)blockIdx.x * p.f_out;
+        for (int c = tid; c < p.f_out; c += TC_THREADS) my[c] = (double)red_db[c];
+    }
+    if (warp == NPW) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- weight packing: w[n, k] (row stride ld) -> per K-atom swizzled hi / lo images ---------------
@@ -487,11 +526,13 @@ extern "C" int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len,
     return check_launch("dgnn_pack_b_tf32");
 }
 
+// ring depth: as deep as fits ~130 KB so that >= 90 KB of the SM's 228 KB stay L1 for the gather
 static int tc_stage_config(int np, int* stages, size_t* smem) {
     int stage_bytes = 2 * A_ATOM_BYTES + 2 * np * ATOM_ROW_BYTES;
-    int s = (200 * 1024) / stage_bytes;
-    if (s > 4) s = 4;
-    if (s < 2) return 1;
+    int s = (132 * 1024) / stage_bytes;
+    if (s > MAX_STAGES) s = MAX_STAGES;
+    if (s < 2) s = 2;
+    if ((size_t)s * stage_bytes + 1024 > 200 * 1024) return 1;
     *stages = s;
     *smem = (size_t)s * stage_bytes + 1024;
     return 0;
@@ -527,7 +568,7 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
     DGNN_REQUIRE(ceil32(f_out) <= 256, "f_out too wide for one UMMA tile");
     DGNN_REQUIRE(x_in && b_packed && out, "null pointer");
     if (w_e == nullptr) fe = 0;
-    DGNN_REQUIRE(fe == 0 || fe == 20 || fe % 4 == 0, "edge feature width must be a multiple of 4");
+    DGNN_REQUIRE(fe % 4 == 0 && fe <= 32, "edge feature width must be a multiple of 4 and <= 32");
     TcArgs p;
     memset(&p, 0, sizeof(p));
     p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;

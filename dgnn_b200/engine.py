@@ -312,9 +312,10 @@ def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, i
              ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, k_total, ptr(d_agg), ptr(d_self), ptr(db_p),
              _stream())
     db = _reduce(db_p)
-    splits = lib().dgnn_dw_splits(f_out, k_total)
+    tc_dw = use_tensor_cores() and lib().dgnn_dw_tc_supported(f_out, k_total)
+    splits = lib().dgnn_tc_grid() if tc_dw else lib().dgnn_dw_splits(f_out, k_total)
     dw_p = torch.empty((splits, f_out, k_total), dtype=torch.float32, device=dev)
-    call("dgnn_dw_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(agg), ptr(x_in),
+    call("dgnn_dw_bwd_tc" if tc_dw else "dgnn_dw_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(agg), ptr(x_in),
          ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None, int(relu_in), n_tgt, f_in,
          f_out, k_total, ptr(dw_p), _stream())
     dw = torch.empty((f_out, k_total), dtype=torch.float32, device=dev)

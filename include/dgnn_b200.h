@@ -122,6 +122,14 @@ int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const flo
                       const float* b_packed, const int32_t* nbr, int64_t n_tgt, int f_in, int f_out,
                       float* d_agg, float* d_self, double* db_partials, void* stream);
 
+/* dW on tensor cores with a TMEM-resident accumulator (f_out <= 128, k_total <= 256);
+ * partials float[dgnn_tc_grid(), f_out, k_total], summed by dgnn_reduce_partials_f32. */
+int dgnn_dw_tc_supported(int f_out, int k_total);
+int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
+                   const float* mean, const float* rstd,
+                   const float* agg, const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                   int64_t n_tgt, int f_in, int f_out, int k_total, float* partials, void* stream);
+
 /* Reduce per-CTA (sum, sum^2) partials and produce the normalisation's per-channel affine.
  * mode 0 = BatchNorm1d training statistics (biased var for normalisation; running_mean /
  *          running_var (unbiased) updated with `momentum` when non-NULL),

@@ -106,3 +106,31 @@ def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather):
     else:
         assert _rel(d_self, dA) < 3e-6
     np.testing.assert_allclose(db_p.sum(0).cpu().numpy(), dz.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,f_in,f_out,gather", [(1000, 28, 64, True), (5000, 128, 128, True), (515, 128, 64, False),
+                                                  (31, 64, 128, True), (40000, 64, 128, True)])
+def test_dw_tc_matches_fp64(n, f_in, f_out, gather):
+    from dgnn_b200._lib import call, lib, ptr
+    torch.manual_seed(3)
+    dy = torch.randn(n, f_out, device=DEV)
+    z = torch.randn(n, f_out, device=DEV)
+    gq, aq, bq = (torch.randn(f_out, device=DEV) for _ in range(3))
+    mean = torch.randn(f_out, device=DEV) * 0.1
+    rstd = torch.rand(f_out, device=DEV) + 0.5
+    x = torch.randn(n, f_in, device=DEV)
+    sc = torch.rand(f_in, device=DEV) + 0.5
+    sh = torch.randn(f_in, device=DEV) * 0.3
+    agg = torch.randn(n, f_in, device=DEV) if gather else None
+    k_total = 2 * f_in if gather else f_in
+    assert lib().dgnn_dw_tc_supported(f_out, k_total)
+    part = torch.empty(lib().dgnn_tc_grid(), f_out, k_total, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    call("dgnn_dw_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(mean), ptr(rstd), ptr(agg), ptr(x), ptr(sc),
+         ptr(sh), 1, n, f_in, f_out, k_total, ptr(part), st)
+    dw = part.double().sum(0)
+    dz = gq.double() * dy.double() - (aq.double() + (z.double() - mean.double()) * rstd.double() * bq.double())
+    h = torch.relu(x.double() * sc.double() + sh.double())
+    A = torch.cat([agg.double(), h], 1) if gather else h
+    ref = dz.t() @ A
+    assert _rel(dw, ref) < 5e-6
