@@ -2,9 +2,12 @@
 //
 //     dW[f_out, k_total] = sum over cells  dz[cell]^T . [agg | h][cell]
 //
-// Both operands are "MN-major" for this product (the contraction runs over cells, which is the
-// slow dimension of the row-major activations), which is exactly how the producer warps lay a
-// cell's row into shared memory: one 128-byte swizzled row of 32 channels per cell per block.
+// The contraction runs over cells, the slow dimension of the row-major activations, so both
+// operands must be transposed on their way into shared memory.  (tcgen05.mma kind::tf32 silently
+// yields zeros for MN-major descriptors on this part — measured with tools/probe_umma.py — so the
+// hardware transpose is not an option.)  The producer warps transpose in registers: 4 lanes hold
+// 4 channels x 1 cell each, two shuffle rounds turn that into 1 channel x 4 cells, i.e. one
+// 16-byte chunk of the K-major (K = cell) swizzled operand row of that channel.
 // The [128 x N] fp32 accumulator (N = k_total <= 256 TMEM columns) stays in TMEM for the whole
 // lifetime of the persistent CTA; it is read out once at the end as this CTA's partial, and the
 // partials of the 148 CTAs are summed by dgnn_reduce_partials_f32 (deterministic, no atomics).
@@ -19,8 +22,7 @@ using namespace umma;
 constexpr int DW_NPW = 16;
 constexpr int DW_THREADS = (DW_NPW + 1) * 32;
 constexpr int DW_CELLS = 32;                       // cells (K) per stage: 2 per producer warp
-constexpr int DW_BLOCK_BYTES = DW_CELLS * 128;     // one 32-channel block of a stage: 4 KB
-constexpr int DW_A_BYTES = 4 * DW_BLOCK_BYTES;     // M = 128 channels: 16 KB
+constexpr int DW_A_BYTES = 128 * 128;               // M = 128 channel rows x 32 cells (one K-atom): 16 KB
 
 struct DwTcArgs {
     const float* dy;
@@ -40,10 +42,24 @@ struct DwTcArgs {
     float* partials;  // [grid][f_out][k_total]
 };
 
-// byte offset of 16-byte chunk `chunk` (4 channels) of cell k inside a stage operand
-__device__ __forceinline__ uint32_t mn_off(int chunk, int k) {
-    return (uint32_t)(chunk >> 3) * DW_BLOCK_BYTES + (uint32_t)(k >> 3) * 1024u + (uint32_t)(k & 7) * 128u +
-           (uint32_t)(((chunk & 7) ^ (k & 7)) << 4);
+// 4x4 transpose across the 4 lanes 4q..4q+3: in: lane j holds (c0..c3) of cell j; out: lane j holds
+// channel j of cells 0..3
+__device__ __forceinline__ float4 transpose4(float4 v, int j) {
+    {
+        const bool up = (j & 2) != 0;
+        float a = up ? v.x : v.z, b = up ? v.y : v.w;
+        a = __shfl_xor_sync(0xffffffffu, a, 2);
+        b = __shfl_xor_sync(0xffffffffu, b, 2);
+        if (up) { v.x = a; v.y = b; } else { v.z = a; v.w = b; }
+    }
+    {
+        const bool up = (j & 1) != 0;
+        float a = up ? v.x : v.y, b = up ? v.z : v.w;
+        a = __shfl_xor_sync(0xffffffffu, a, 1);
+        b = __shfl_xor_sync(0xffffffffu, b, 1);
+        if (up) { v.x = a; v.z = b; } else { v.y = a; v.w = b; }
+    }
+    return v;
 }
 
 __device__ __forceinline__ void put_split4(uint8_t* hi, uint8_t* lo, uint32_t off, float4 v) {
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
     const int64_t my_groups = g_end > g_begin ? g_end - g_begin : 0;
 
     if (warp == DW_NPW) {
-        const uint32_t idesc = make_idesc_tf32_mn(128, p.np);
+        const uint32_t idesc = make_idesc_tf32(128, p.np);
         for (int64_t i = 0; i < my_groups; ++i) {
             const uint32_t s = (uint32_t)(i % p.stages), use = (uint32_t)(i / p.stages);
             if (lane == 0) {
@@ -96,13 +112,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                 const uint32_t bh = al + DW_A_BYTES, bl = bh + b_bytes;
 #pragma unroll
                 for (int kk = 0; kk < DW_CELLS / 8; ++kk) {
-                    const uint32_t ko = kk * 1024;
-                    mma_tf32(tmem_base, make_desc_mn(ah + ko, DW_BLOCK_BYTES, 1024), make_desc_mn(bh + ko, DW_BLOCK_BYTES, 1024),
-                             idesc, (i > 0 || kk > 0) ? 1u : 0u);
-                    mma_tf32(tmem_base, make_desc_mn(al + ko, DW_BLOCK_BYTES, 1024), make_desc_mn(bh + ko, DW_BLOCK_BYTES, 1024),
-                             idesc, 1u);
-                    mma_tf32(tmem_base, make_desc_mn(ah + ko, DW_BLOCK_BYTES, 1024), make_desc_mn(bl + ko, DW_BLOCK_BYTES, 1024),
-                             idesc, 1u);
+                    const uint32_t ko = kk * 32;
+                    mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bh + ko), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+                    mma_tf32(tmem_base, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
+                    mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
                 }
                 mma_commit(&bar_empty[s]);
                 if (i == my_groups - 1) mma_commit(&bar_done);
@@ -111,14 +124,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
         }
     } else {
         const bool relu = p.relu_in != 0;
-        const int fo4 = p.f_out >> 2, kt4 = p.k_total >> 2;
-        // per-lane constants of the dz transform (channel 4*lane)
-        float4 g = make_float4(1.f, 1.f, 1.f, 1.f), a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, m = a, rs = g;
-        const bool norm = p.ng != nullptr && lane < fo4;
-        if (norm) {
-            g = ldg4(p.ng + 4 * lane); a = ldg4(p.na + 4 * lane); b = ldg4(p.nb + 4 * lane);
-            m = ldg4(p.nmean + 4 * lane); rs = ldg4(p.nrstd + 4 * lane);
-        }
+        const int j = lane & 3, c = lane >> 2;       // cell within a group of 4, 16-byte chunk within a 32-channel block
+        const int nb_a = (p.f_out + 31) >> 5;        // 32-channel blocks of dz
+        const int n_items = 8 * (nb_a + (p.np >> 5));  // (cell group, channel block) pairs per stage
         for (int64_t i = 0; i < my_groups; ++i) {
             const uint32_t s = (uint32_t)(i % p.stages), use = (uint32_t)(i / p.stages);
             uint8_t* a_hi = smem + (size_t)s * stage_bytes;
@@ -126,36 +134,34 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             uint8_t* b_hi = a_lo + DW_A_BYTES;
             uint8_t* b_lo = b_hi + b_bytes;
             mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int k = warp * 2 + c;
-                const int64_t t = (g_begin + i) * DW_CELLS + k;
+            for (int item = warp; item < n_items; item += DW_NPW) {
+                const int g = item & 7, blk = item >> 3;
+                const int64_t t = (g_begin + i) * DW_CELLS + g * 4 + j;
                 const bool tv = t < p.n_tgt;
-                // dz row -> A operand
-                if (lane < fo4) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (tv) {
-                        float4 d = ldg4(p.dy + (size_t)t * p.f_out + 4 * lane);
-                        if (norm) {
-                            float4 zv = ldg4(p.z + (size_t)t * p.f_out + 4 * lane);
-                            v.x = g.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
-                            v.y = g.y * d.y - (a.y + (zv.y - m.y) * rs.y * b.y);
-                            v.z = g.z * d.z - (a.z + (zv.z - m.z) * rs.z * b.z);
-                            v.w = g.w * d.w - (a.w + (zv.w - m.w) * rs.w * b.w);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint8_t *dst_hi, *dst_lo;
+                int row;
+                if (blk < nb_a) {                       // dz block -> A operand rows (channels)
+                    const int ch = blk * 32 + c * 4;
+                    if (tv && ch < p.f_out) {
+                        float4 d = ldg4(p.dy + (size_t)t * p.f_out + ch);
+                        if (p.ng != nullptr) {
+                            float4 zv = ldg4(p.z + (size_t)t * p.f_out + ch);
+                            float4 gg = ldg4(p.ng + ch), a = ldg4(p.na + ch), b = ldg4(p.nb + ch), m = ldg4(p.nmean + ch),
+                                   rs = ldg4(p.nrstd + ch);
+                            v.x = gg.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
+                            v.y = gg.y * d.y - (a.y + (zv.y - m.y) * rs.y * b.y);
+                            v.z = gg.z * d.z - (a.z + (zv.z - m.z) * rs.z * b.z);
+                            v.w = gg.w * d.w - (a.w + (zv.w - m.w) * rs.w * b.w);
                         } else {
                             v = d;
                         }
                     }
-                    put_split4(a_hi, a_lo, mn_off(lane, k), v);
-                }
-                // [agg | h] row -> B operand
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int chunk = lane + 32 * h2;
-                    if (chunk >= kt4) continue;
-                    const int n = chunk * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (tv) {
+                    dst_hi = a_hi; dst_lo = a_lo;
+                    row = blk * 32 + c * 4 + j;
+                } else {                                // [agg | h] block -> B operand rows (columns of dW)
+                    const int n = (blk - nb_a) * 32 + c * 4;
+                    if (tv && n < p.k_total) {
                         if (p.agg != nullptr && n < p.f_in) {
                             v = ldg4(p.agg + (size_t)t * p.f_in + n);
                         } else {
@@ -170,8 +176,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                             }
                         }
                     }
-                    put_split4(b_hi, b_lo, mn_off(chunk, k), v);
+                    dst_hi = b_hi; dst_lo = b_lo;
+                    row = (blk - nb_a) * 32 + c * 4 + j;
                 }
+                v = transpose4(v, j);                   // now: channel `row`, cells 4g .. 4g+3
+                put_split4(dst_hi, dst_lo, (uint32_t)row * 128u + (uint32_t)((g ^ (row & 7)) << 4), v);
             }
             fence_proxy_async_smem();
             __syncwarp();

@@ -130,6 +130,10 @@ int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float*
                    const float* agg, const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
                    int64_t n_tgt, int f_in, int f_out, int k_total, float* partials, void* stream);
 
+/* development probe (tools/probe_umma.py): one tcgen05.mma on caller-provided smem images */
+int dgnn_debug_umma(const uint8_t* a_img, int a_bytes, const uint8_t* b_img, int b_bytes, uint64_t a_desc,
+                    uint64_t b_desc, uint32_t idesc, int n, float* out, void* stream);
+
 /* Reduce per-CTA (sum, sum^2) partials and produce the normalisation's per-channel affine.
  * mode 0 = BatchNorm1d training statistics (biased var for normalisation; running_mean /
  *          running_var (unbiased) updated with `momentum` when non-NULL),

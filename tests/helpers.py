@@ -55,8 +55,8 @@ def grad_close(g_new, g_ref, rtol=1e-2):
     <= 1e-3 of the gradient's RMS.  Returns (error, tolerance) with error > tolerance on failure."""
     g_new = g_new.detach().cpu().double(); g_ref = g_ref.detach().cpu().double()
     nr = float(g_ref.norm())
-    if nr < 1e-9:                       # analytically-zero gradient (bias in front of a BatchNorm)
-        return float((g_new - g_ref).abs().max()), 1e-6
+    if nr < 1e-6:                       # analytically-zero gradient (bias in front of a BatchNorm): both
+        return float((g_new - g_ref).abs().max()), 2e-5   # sides are rounding noise of a cancelling sum
     frob = float((g_new - g_ref).norm()) / nr
     rms = nr / (g_ref.numel() ** 0.5)
     med = float((g_new - g_ref).abs().median()) / rms
