@@ -39,6 +39,10 @@ SIGNATURES = {
     "dgnn_pack_b_tf32": [P, I, I, I, I, P, P],
     "dgnn_layer_fwd_tc": [P, P, P, I, P, P, I, P, P, P, P, P, P, I, L, I, I, P, P, P, P],
     "dgnn_dense_bwd_tc": [P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P],
+    "dgnn_gather_tc_supported": [I, I],
+    "dgnn_gather_tc_fwd": [P, P, P, I, P, P, I, P, P, L, I, P, P],
+    "dgnn_gather_tc_bwd": [P, P, P, P, I, P, P, P, P, P, P, P, I, L, L, I, P, P, P],
+    "dgnn_dense_fwd_tc": [P, P, P, P, I, P, P, P, P, I, L, I, I, P, P, P],
     "dgnn_dw_tc_supported": [I, I],
     "dgnn_dw_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P, P],
     "dgnn_debug_umma": [P, I, P, I, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, I, P, P],
@@ -60,6 +64,7 @@ SIGNATURES = {
     "dgnn_reduce_partials_f32": [P, I, L, P, P],
     "dgnn_gather_bwd_grid": [I],
     "dgnn_gather_bwd": [P, P, P, P, I, P, P, P, P, P, P, P, I, L, L, I, P, P, P],
+    "dgnn_edge_filter_bwd": [P, P, P, I, P, P, P, P, P, I, L, L, I, P, P],
     "dgnn_adam_step": [P, P, P, P, L, F, F, F, F, I, P],
     "dgnn_adam_multi": [P, I, L, F, F, F, F, I, P],
     "dgnn_argmax_labels": [P, L, I, P, P],

@@ -327,6 +327,7 @@ struct GatherBwdArgs {
     int f_in;
     float* dy_prev;
     double* partials;
+    int only_dwe;   // 1: only the edge-filter gradients (dW_e, db_e); dh / dy_prev / (S1,S2) are skipped
 };
 
 template <int FE>
@@ -397,10 +398,12 @@ __global__ void __launch_bounds__(NT, 2) gather_bwd_kernel(const GatherBwdArgs p
 #pragma unroll
                     for (int j = 0; j < FE; j += 4) {
                         float4 e = ldg4(er + j);
-                        ph0 = fmaf(we0[j], e.x, ph0); ph1 = fmaf(we1[j], e.x, ph1);
-                        ph0 = fmaf(we0[j + 1], e.y, ph0); ph1 = fmaf(we1[j + 1], e.y, ph1);
-                        ph0 = fmaf(we0[j + 2], e.z, ph0); ph1 = fmaf(we1[j + 2], e.z, ph1);
-                        ph0 = fmaf(we0[j + 3], e.w, ph0); ph1 = fmaf(we1[j + 3], e.w, ph1);
+                        if (!p.only_dwe) {
+                            ph0 = fmaf(we0[j], e.x, ph0); ph1 = fmaf(we1[j], e.x, ph1);
+                            ph0 = fmaf(we0[j + 1], e.y, ph0); ph1 = fmaf(we1[j + 1], e.y, ph1);
+                            ph0 = fmaf(we0[j + 2], e.z, ph0); ph1 = fmaf(we1[j + 2], e.z, ph1);
+                            ph0 = fmaf(we0[j + 3], e.w, ph0); ph1 = fmaf(we1[j + 3], e.w, ph1);
+                        }
                         dwe0[j] = fmaf(dp0, e.x, dwe0[j]); dwe1[j] = fmaf(dp1, e.x, dwe1[j]);
                         dwe0[j + 1] = fmaf(dp0, e.y, dwe0[j + 1]); dwe1[j + 1] = fmaf(dp1, e.y, dwe1[j + 1]);
                         dwe0[j + 2] = fmaf(dp0, e.z, dwe0[j + 2]); dwe1[j + 2] = fmaf(dp1, e.z, dwe1[j + 2]);
@@ -533,6 +536,14 @@ static int launch_gather_bwd(const GatherBwdArgs& p, cudaStream_t st) {
     return check_launch("dgnn_gather_bwd");
 }
 
+static int g_only_dwe = 0;
+
+// dW_e / db_e only (same partial layout as dgnn_gather_bwd; its S1/S2 part is zero)
+extern "C" int dgnn_edge_filter_bwd(const float* d_agg, const int32_t* onbr, const float* ea_own, int fe,
+                                    const float* w_e, const float* b_e, const float* x_in, const float* in_scale,
+                                    const float* in_shift, int relu_in, int64_t n_src, int64_t n_tgt, int f_in,
+                                    double* partials, void* stream);
+
 extern "C" int dgnn_gather_bwd(const float* d_agg, const float* d_self, const int32_t* onbr, const float* ea_own,
                                int fe, const float* w_e, const float* b_e, const float* x_in, const float* in_scale,
                                const float* in_shift, const float* in_mean, const float* in_rstd, int relu_in,
@@ -545,6 +556,7 @@ extern "C" int dgnn_gather_bwd(const float* d_agg, const float* d_self, const in
     p.d_agg = d_agg; p.d_self = d_self; p.onbr = onbr; p.ea_own = ea_own; p.w_e = w_e; p.b_e = b_e;
     p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.in_mean = in_mean; p.in_rstd = in_rstd;
     p.relu_in = relu_in; p.n_src = n_src; p.n_tgt = n_tgt; p.f_in = f_in; p.dy_prev = dy_prev; p.partials = partials;
+    p.only_dwe = (d_self == nullptr && dy_prev == nullptr && in_mean == nullptr && fe > 0) ? g_only_dwe : 0;
     cudaStream_t st = as_stream(stream);
     switch (fe) {
         case 0: return launch_gather_bwd<0>(p, st);
@@ -558,4 +570,16 @@ extern "C" int dgnn_gather_bwd(const float* d_agg, const float* d_self, const in
         case 32: return launch_gather_bwd<32>(p, st);
     }
     return fail("dgnn_gather_bwd", "unsupported edge feature width");
+}
+
+extern "C" int dgnn_edge_filter_bwd(const float* d_agg, const int32_t* onbr, const float* ea_own, int fe,
+                                    const float* w_e, const float* b_e, const float* x_in, const float* in_scale,
+                                    const float* in_shift, int relu_in, int64_t n_src, int64_t n_tgt, int f_in,
+                                    double* partials, void* stream) {
+    DGNN_REQUIRE(fe > 0 && w_e != nullptr, "no edge filter");
+    g_only_dwe = 1;
+    int rc = dgnn_gather_bwd(d_agg, nullptr, onbr, ea_own, fe, w_e, b_e, x_in, in_scale, in_shift, nullptr, nullptr,
+                             relu_in, n_src, n_tgt, f_in, nullptr, partials, stream);
+    g_only_dwe = 0;
+    return rc;
 }

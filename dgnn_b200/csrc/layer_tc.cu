@@ -35,6 +35,7 @@ enum { MODE_FWD_DENSE = 0, MODE_FWD_GATHER = 1, MODE_BWD = 2 };
 
 struct TcArgs {
     // forward producer
+    const float* agg_in;   // dense mode: first ka_agg atoms come from this matrix (no activation), may be NULL
     const float* x_in;
     const float* in_scale;
     const float* in_shift;
@@ -96,20 +97,22 @@ __device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, int r
 
 // warp `w` fills its 8 rows of the atom with h(x_in[row, f0 .. f0+32))
 __device__ __forceinline__ void produce_rows(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0,
-                                             int warp, int lane) {
-    const bool relu = p.relu_in != 0;
+                                             int warp, int lane, bool raw_agg = false) {
+    const bool relu = p.relu_in != 0 && !raw_agg;
     const int c = (lane & 7) * 4;
     const int f = f0 + c;
+    const float* src = raw_agg ? p.agg_in : p.x_in;
+    const bool affine = p.in_scale != nullptr && !raw_agg;
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.in_scale != nullptr && f < p.f_in) { sc = ldg4(p.in_scale + f); sh = ldg4(p.in_shift + f); }
+    if (affine && f < p.f_in) { sc = ldg4(p.in_scale + f); sh = ldg4(p.in_shift + f); }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int r = warp * 8 + (lane >> 3) + it * 4;
         const int64_t t = tile0 + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < p.n_tgt && f < p.f_in) {
-            v = ldg4(p.x_in + (size_t)t * p.f_in + f);
-            if (p.in_scale != nullptr) {
+            v = ldg4(src + (size_t)t * p.f_in + f);
+            if (affine) {
                 v.x = act(v.x, sc.x, sh.x, relu); v.y = act(v.y, sc.y, sh.y, relu);
                 v.z = act(v.z, sc.z, sh.z, relu); v.w = act(v.w, sc.w, sh.w, relu);
             } else if (relu) {
@@ -427,7 +430,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                 uint8_t* a_lo = a_hi + A_ATOM_BYTES;
                 mbar_wait(&bar_empty[s], (use & 1) ^ 1);
                 if (MODE == MODE_FWD_DENSE) {
-                    produce_rows(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
+                    if (a < p.ka_agg) produce_rows(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane, true);
+                    else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
                 } else if (MODE == MODE_FWD_GATHER) {
                     if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
                     else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
@@ -596,6 +600,30 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
         case 32: return launch_tc<MODE_FWD_GATHER, 32>(p, smem, st, "dgnn_layer_fwd_tc");
     }
     return fail("dgnn_layer_fwd_tc", "unsupported edge feature width");
+}
+
+// z = [agg | h(x_in)] . W^T with agg read from memory (agg may be NULL: plain dense layer)
+extern "C" int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const float* in_scale, const float* in_shift,
+                                 int relu_in, const float* b_packed, const float* bias, const float* out_scale,
+                                 const float* out_shift, int relu_out, int64_t n_tgt, int f_in, int f_out, float* out,
+                                 double* stats, void* stream) {
+    DGNN_REQUIRE(f_in % 4 == 0 && f_out % 4 == 0, "widths must be multiples of 4");
+    DGNN_REQUIRE(ceil32(f_out) <= 256, "f_out too wide for one UMMA tile");
+    DGNN_REQUIRE(x_in && b_packed && out, "null pointer");
+    TcArgs p;
+    memset(&p, 0, sizeof(p));
+    p.agg_in = agg; p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;
+    p.b_packed = b_packed;
+    const int seg = ceil32(f_in) / ATOM_K;
+    p.ka_agg = agg ? seg : 0;
+    p.ka = agg ? 2 * seg : seg;
+    p.np = ceil32(f_out);
+    p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
+    p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
+    p.out = out; p.stats = stats;
+    size_t smem;
+    DGNN_REQUIRE(tc_stage_config(p.np, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    return launch_tc<MODE_FWD_DENSE, 0>(p, smem, as_stream(stream), "dgnn_dense_fwd_tc");
 }
 
 extern "C" int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,

@@ -189,6 +189,24 @@ def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGra
     return out, agg, stats
 
 
+def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_aff, relu_out, want_stats):
+    """Tensor-core layer forward as two kernels: aggregation with the edge filter on tcgen05
+    (dgnn_gather_tc_fwd) -> agg, then z = [agg | h] . W^T (dgnn_dense_fwd_tc)."""
+    dev = x_in.device
+    n_tgt = g.n_tgt
+    agg = torch.empty((n_tgt, pk.f_in), dtype=torch.float32, device=dev)
+    sc = ptr(in_aff.scale) if in_aff else None
+    sh = ptr(in_aff.shift) if in_aff else None
+    call("dgnn_gather_tc_fwd", ptr(x_in), sc, sh, int(relu_in), ptr(g.nbr), ptr(g.ea_in), pk.fe, ptr(pk.w_e),
+         ptr(pk.b_e), n_tgt, pk.f_in, ptr(agg), _stream())
+    out = torch.empty((n_tgt, pk.f_out), dtype=torch.float32, device=dev)
+    stats = torch.empty((lib().dgnn_tc_grid(), 2, pk.f_out), dtype=torch.float64, device=dev) if want_stats else None
+    call("dgnn_dense_fwd_tc", ptr(agg), ptr(x_in), sc, sh, int(relu_in), ptr(pk.b_fwd), ptr(pk.bias),
+         ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None, int(relu_out), n_tgt,
+         pk.f_in, pk.f_out, ptr(out), ptr(stats), _stream())
+    return out, agg, stats
+
+
 def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: bool, save: bool):
     """Run all conv layers + decoder.  ``x0``: float32[n_src0, pad4(F0)] in the graphs' row order.
     Returns ``(logits, Saved or None)``.  In training mode the norms use batch statistics
@@ -212,17 +230,24 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             raise ValueError("layer %d expects %d input features, got %d" % (l, pk.f_in, h.shape[1]))
         if c.norm is None:
             raise NotImplementedError("normalization must be 'b' or 'l' (the reference crashes otherwise, Static:218)")
+        split = pk.b_fwd is not None and pk.fe > 0 and lib().dgnn_gather_tc_supported(pk.f_in, pk.fe)
         if batch_stats:
-            z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None, False,
-                                       g.n_tgt, pk.f_in, pk.f_out, save, True, b_packed=pk.b_fwd)
+            if split:
+                z, agg, stats = _gather_then_dense(h, in_aff, relu_in, g, pk, None, False, True)
+            else:
+                z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None,
+                                           False, g.n_tgt, pk.f_in, pk.f_out, save, True, b_packed=pk.b_fwd)
             aff = batch_affine(c.norm, stats, g.n_tgt, pk.f_out, dev, update_running=training)
             if save:
                 sv.z.append(z); sv.agg.append(agg); sv.aff.append(aff); sv.packed.append(pk)
             h, in_aff, relu_in = z, aff, True
         else:
             aff = eval_affine(c.norm, pk.f_out, dev)
-            h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
-                                 g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd)
+            if split:
+                h, _, _ = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False)
+            else:
+                h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
+                                     g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd)
             in_aff, relu_in = None, False
     n_out = graphs[-1].n_tgt
     f_last = spec.convs[-1].f_out
@@ -394,7 +419,30 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
         grads["convs.%d.w_j" % l] = dw[:, :c.f_in]
         grads["convs.%d.w_i" % l] = dw[:, pk.f_in:pk.f_in + c.f_in]
         need_prev = l > 0
-        if need_prev or pk.fe:
+        tc_gather = use_tensor_cores() and pk.fe > 0 and lib().dgnn_gather_tc_supported(pk.f_in, pk.fe)
+        if tc_gather:
+            # dh / dy_prev / (S1,S2) with the edge filter on tensor cores; dW_e, db_e by the FP32 kernel
+            if need_prev:
+                part = torch.empty((lib().dgnn_tc_grid(), 2 * pk.f_in), dtype=torch.float64, device=dev)
+                dy_prev = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev)
+                call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.ea_own), pk.fe, ptr(pk.w_e),
+                     ptr(pk.b_e), ptr(x_in), ptr(in_aff.scale), ptr(in_aff.shift), ptr(in_aff.mean), ptr(in_aff.rstd),
+                     1, g.n_src, g.n_tgt, pk.f_in, ptr(dy_prev), ptr(part), st)
+                r = _reduce(part)
+                s1, s2 = r[:pk.f_in], r[pk.f_in:]
+            grid = lib().dgnn_gather_bwd_grid(pk.f_in)
+            plen = pk.f_in * (pk.fe + 1) + 2 * pk.f_in
+            part = torch.empty((grid, plen), dtype=torch.float64, device=dev)
+            call("dgnn_edge_filter_bwd", ptr(d_agg), ptr(g.onbr), ptr(g.ea_own), pk.fe, ptr(pk.w_e), ptr(pk.b_e),
+                 ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+                 int(relu_in), g.n_src, g.n_tgt, pk.f_in, ptr(part), st)
+            r = _reduce(part)
+            fe_u = c.w_e.shape[1]
+            grads["convs.%d.w_e" % l] = r[:pk.f_in * pk.fe].view(pk.f_in, pk.fe)[:c.f_in, :fe_u]
+            grads["convs.%d.b_e" % l] = r[pk.f_in * pk.fe:pk.f_in * (pk.fe + 1)][:c.f_in]
+            if need_prev:
+                dy = dy_prev
+        elif need_prev or pk.fe:
             grid = lib().dgnn_gather_bwd_grid(pk.f_in)
             plen = pk.f_in * (pk.fe + 1) + 2 * pk.f_in
             part = torch.empty((grid, plen), dtype=torch.float64, device=dev)

@@ -122,6 +122,25 @@ int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const flo
                       const float* b_packed, const int32_t* nbr, int64_t n_tgt, int f_in, int f_out,
                       float* d_agg, float* d_self, double* db_partials, void* stream);
 
+/* Aggregation with the edge filter on tensor cores (f_in <= 128, 4 <= fe <= 28):
+ *   fwd: agg[t] = mean_k h(nbr[t,k]) (*) (w_e . ea[t,k] + b_e)
+ *   bwd: dh[s] = d_self[s] (s < n_tgt) + sum_k (w_e . ea_own[s,k] + b_e) (*) d_agg[onbr[s,k]];
+ *        dy_prev = relu'(z_prev*p_scale+p_shift) * dh, s_partials double[dgnn_tc_grid(), 2*f_in] = (S1, S2)
+ * followed by dgnn_dense_fwd_tc: z = [agg | h(x_in)] . W^T (+ epilogue as dgnn_layer_fwd). */
+int dgnn_gather_tc_supported(int f, int fe);
+int dgnn_gather_tc_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                       const int32_t* nbr, const float* ea, int fe, const float* w_e, const float* b_e,
+                       int64_t n_tgt, int f_in, float* agg, void* stream);
+int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const int32_t* onbr, const float* ea_own,
+                       int fe, const float* w_e, const float* b_e, const float* z_prev,
+                       const float* p_scale, const float* p_shift, const float* p_mean,
+                       const float* p_rstd, int p_relu, int64_t n_src, int64_t n_tgt, int f_in,
+                       float* dy_prev, double* s_partials, void* stream);
+int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const float* in_scale, const float* in_shift,
+                      int relu_in, const float* b_packed, const float* bias, const float* out_scale,
+                      const float* out_shift, int relu_out, int64_t n_tgt, int f_in, int f_out, float* out,
+                      double* stats, void* stream);
+
 /* dW on tensor cores with a TMEM-resident accumulator (f_out <= 128, k_total <= 256);
  * partials float[dgnn_tc_grid(), f_out, k_total], summed by dgnn_reduce_partials_f32. */
 int dgnn_dw_tc_supported(int f_out, int k_total);
@@ -218,6 +237,12 @@ int dgnn_gather_bwd(const float* d_agg, const float* d_self, const int32_t* onbr
                     const float* in_mean, const float* in_rstd, int relu_in,
                     int64_t n_src, int64_t n_tgt, int f_in,
                     float* dy_prev, double* partials, void* stream);
+
+/* edge-filter gradients only (dW_e, db_e; the S1/S2 part of the partials is zero) */
+int dgnn_edge_filter_bwd(const float* d_agg, const int32_t* onbr, const float* ea_own, int fe,
+                         const float* w_e, const float* b_e, const float* x_in, const float* in_scale,
+                         const float* in_shift, int relu_in, int64_t n_src, int64_t n_tgt, int f_in,
+                         double* partials, void* stream);
 
 /* ---- optimiser (torch.optim.Adam defaults, runModel.py:290) ------------------------------ */
 int dgnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

@@ -134,3 +134,61 @@ def test_dw_tc_matches_fp64(n, f_in, f_out, gather):
     A = torch.cat([agg.double(), h], 1) if gather else h
     ref = dz.t() @ A
     assert _rel(dw, ref) < 5e-6
+
+
+@pytest.mark.parametrize("f_in,fe,ragged", [(28, 20, False), (64, 20, True), (128, 20, False), (128, 4, True)])
+def test_gather_tc_forward_and_backward_match_generic_kernels(f_in, fe, ragged):
+    from dgnn_b200 import engine
+    from dgnn_b200._lib import call, lib, ptr
+    from dgnn_b200.graph import build_full_graph
+    g = make_graph(1100, seed=4)
+    n = g["n"]
+    ei = torch.from_numpy(g["adj"].T.astype(np.int64)).contiguous()
+    torch.manual_seed(5)
+    ea = torch.randn(4 * n, fe)
+    eg = build_full_graph(ei, ea, n, DEV, order="rcm")
+    if ragged:
+        eg.nbr = eg.nbr.clone(); eg.onbr = eg.nbr
+        eg.nbr[::3, 2] = -1
+        eg.nbr[::11] = -1
+    x = torch.randn(n, f_in, device=DEV)
+    w_e = torch.randn(f_in, fe, device=DEV) * 0.3
+    b_e = torch.randn(f_in, device=DEV)
+    sc = torch.rand(f_in, device=DEV) + 0.5
+    sh = torch.randn(f_in, device=DEV) * 0.3
+    st = torch.cuda.current_stream().cuda_stream
+    # forward: agg
+    f_out = 32
+    wt = torch.zeros(2 * f_in, f_out, device=DEV)
+    _, agg_ref, _ = engine._layer_fwd(x, engine.Affine(sc, sh), True, eg, wt, None, w_e, b_e, fe, None, False, n, f_in,
+                                      f_out, True, False)
+    agg = torch.empty(n, f_in, device=DEV)
+    call("dgnn_gather_tc_fwd", ptr(x), ptr(sc), ptr(sh), 1, ptr(eg.nbr), ptr(eg.ea_in), fe, ptr(w_e), ptr(b_e), n, f_in,
+         ptr(agg), st)
+    assert _rel(agg, agg_ref) < 3e-6
+    # backward: dy_prev, S1, S2
+    d_agg = torch.randn(n, f_in, device=DEV)
+    d_self = torch.randn(n, f_in, device=DEV)
+    mean = torch.randn(f_in, device=DEV) * 0.1
+    rstd = torch.rand(f_in, device=DEV) + 0.5
+    grid = lib().dgnn_gather_bwd_grid(f_in)
+    plen = f_in * (fe + 1) + 2 * f_in
+    part = torch.empty(grid, plen, dtype=torch.float64, device=DEV)
+    dy_ref = torch.empty(n, f_in, device=DEV)
+    call("dgnn_gather_bwd", ptr(d_agg), ptr(d_self), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x), ptr(sc),
+         ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f_in, ptr(dy_ref), ptr(part), st)
+    r = part.sum(0)
+    s1_ref, s2_ref = r[f_in * (fe + 1):f_in * (fe + 1) + f_in], r[f_in * (fe + 1) + f_in:]
+    dwe_ref = r[:f_in * (fe + 1)]
+    dy = torch.empty(n, f_in, device=DEV)
+    part2 = torch.empty(lib().dgnn_tc_grid(), 2 * f_in, dtype=torch.float64, device=DEV)
+    call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x),
+         ptr(sc), ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f_in, ptr(dy), ptr(part2), st)
+    assert _rel(dy, dy_ref) < 3e-6
+    r2 = part2.sum(0)
+    assert _rel(r2[:f_in], s1_ref) < 1e-5 and _rel(r2[f_in:], s2_ref) < 1e-5
+    # edge-filter gradients only
+    part3 = torch.empty(grid, plen, dtype=torch.float64, device=DEV)
+    call("dgnn_edge_filter_bwd", ptr(d_agg), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x), ptr(sc), ptr(sh),
+         1, n, n, f_in, ptr(part3), st)
+    assert _rel(part3.sum(0)[:f_in * (fe + 1)], dwe_ref) < 1e-6
