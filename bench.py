@@ -127,7 +127,7 @@ class ClockSampler:
 def algorithmic_bytes(name, a):
     """Compulsory HBM bytes of one launch (DESIGN.md section 'kernels'; SURVEY.md 8d per-layer
     figures split per kernel).  ``a`` = the ctypes argument list of the call."""
-    if name == "dgnn_layer_fwd":
+    if name in ("dgnn_layer_fwd", "dgnn_layer_fwd_tc"):
         n, f_in, f_out, fe = a[14], a[15], a[16], (a[6] if a[7] else 0)
         gather = a[4] is not None
         b = 4 * f_in + 4 * f_out
@@ -136,16 +136,32 @@ def algorithmic_bytes(name, a):
         if a[18] is not None:
             b += 4 * f_in
         return n * b, "f%d->%d" % (f_in, f_out)
+    if name == "dgnn_gather_tc_fwd":
+        n, f_in, fe = a[9], a[10], a[6]
+        return n * (16 + 16 * fe + 8 * f_in), "f%d" % f_in
+    if name == "dgnn_dense_fwd_tc":
+        n, f_in, f_out = a[10], a[11], a[12]
+        return n * ((8 if a[0] is not None else 4) * f_in + 4 * f_out), "f%d->%d" % (f_in, f_out)
     if name == "dgnn_dense_bwd":
         n, f_in, f_out = a[9], a[10], a[11]
         gather = a[8] is not None
         return n * (8 * f_out + (8 * f_in + 16 if gather else 4 * f_in)), "f%d->%d" % (f_in, f_out)
-    if name == "dgnn_dw_bwd":
+    if name == "dgnn_dense_bwd_tc":
+        n, f_in, f_out = a[9], a[10], a[11]
+        gather = a[8] is not None
+        return n * (8 * f_out + (8 * f_in + 16 if gather else 4 * f_in)), "f%d->%d" % (f_in, f_out)
+    if name in ("dgnn_dw_bwd", "dgnn_dw_bwd_tc"):
         n, f_in, f_out = a[12], a[13], a[14]
         return n * (8 * f_out + (8 * f_in if a[7] is not None else 4 * f_in)), "f%d->%d" % (f_in, f_out)
     if name == "dgnn_gather_bwd":
         n, f_in, fe = a[13], a[15], (a[4] if a[5] else 0)
         return n * (16 + 16 * fe + 12 * f_in + (4 * f_in if a[16] is not None else 0)), "f%d" % f_in
+    if name == "dgnn_gather_tc_bwd":
+        n, f_in, fe = a[13], a[15], a[4]
+        return n * (16 + 16 * fe + 16 * f_in), "f%d" % f_in
+    if name == "dgnn_edge_filter_bwd":
+        n, f_in, fe = a[10], a[12], a[3]
+        return n * (16 + 16 * fe + 8 * f_in), "f%d" % f_in
     return None, ""
 
 

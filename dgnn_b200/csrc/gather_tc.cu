@@ -55,7 +55,10 @@ struct GatherTcArgs {
     const float* p_rstd;
     int p_relu;
     double* s_partials;    // [grid, 2*f] (S1, S2), may be NULL
+    float* dwe_partials;   // [grid, f, 32]: dW_e (cols 0..fe-1) and db_e (col fe), may be NULL
 };
+
+constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;   // per row-quarter: P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
 
 // butterfly transpose-reduce over the warp's 32 rows of CPT columns held in v[0..CPT):
 // returns in lane l (l < CPT) ... implemented for CPT = 8, 16, 32 by padding to 32 lanes
@@ -84,25 +87,31 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ea_full[G_EA_STAGES], ea_empty[G_EA_STAGES];
     __shared__ uint64_t phi_full[8], phi_free[8];
+    __shared__ uint64_t p_full[4], p_empty[4], dwe_done;
     __shared__ uint32_t tmem_slot;
     __shared__ double red_s[2 * 128];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int FP = CPT * 4;
-    const int n_phi = 512 / FP > 8 ? 8 : 512 / FP;      // PHI buffers in TMEM
+    const bool with_dwe = MODE == 1 && p.dwe_partials != nullptr;
+    const int phi_cols = with_dwe ? 480 : 512;           // the last 32 TMEM columns hold the dW_e accumulator
+    const int n_phi = phi_cols / FP > 8 ? 8 : phi_cols / FP;   // PHI buffers in TMEM
     uint8_t* we_hi = smem;                               // [FP rows x 128 B]
     uint8_t* we_lo = we_hi + FP * 128;
     uint8_t* ea_base = we_lo + FP * 128;                 // stages of (hi 16 KB | lo 16 KB)
+    uint8_t* p_base = ea_base + G_EA_STAGES * 2 * G_ATOM;  // 4 x (P_hi | EA^T hi | EA^T lo), backward only
 
     if (tid == 0) {
         for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_full[s], G_NCW); mbar_init(&ea_empty[s], 1); }
         for (int b = 0; b < 8; ++b) { mbar_init(&phi_full[b], 1); mbar_init(&phi_free[b], G_NCW); }
+        for (int b = 0; b < 4; ++b) { mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1); }
+        mbar_init(&dwe_done, 1);
         fence_barrier_init();
     }
     for (int c = tid; c < 256; c += G_THREADS) red_s[c] = 0.0;
     // zero the EA stages (K padding columns stay zero) and build the WE operand:
     // WE[n][e] = w_e[n][e] (e < fe), WE[n][fe] = b_e[n], rest 0
-    for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM) / 16; i += G_THREADS)
+    for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM + (with_dwe ? 4 * G_P_BYTES : 0)) / 16; i += G_THREADS)
         reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int i = tid; i < p.f * (p.fe + 1); i += G_THREADS) {
@@ -119,6 +128,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         const int s = i / G_M, r = i % G_M;
         *reinterpret_cast<float*>(ea_base + (size_t)s * 2 * G_ATOM + atom_off(r, p.fe)) = 1.0f;
     }
+    if (with_dwe) {
+        // row fe of every EA^T operand is all ones: column fe of dW_e accumulates db_e = sum dphi
+        for (int i = tid; i < 4 * 32; i += G_THREADS) {
+            const int qq = i >> 5, cell = i & 31;
+            *reinterpret_cast<float*>(p_base + (size_t)qq * G_P_BYTES + G_ATOM + atom_off(p.fe, cell)) = 1.0f;
+        }
+    }
     fence_proxy_async_smem();
     if (warp == G_NCW) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
@@ -130,8 +146,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     if (warp == G_NCW) {
         // ---------------------------------------------------------------- MMA warp
         const uint32_t idesc = make_idesc_tf32(G_M, FP);
+        const uint32_t idesc_p = make_idesc_tf32(G_M, 32);
         const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
+        const uint32_t d_dwe = tmem_base + 480u;
         uint32_t it = 0;
+        // dW_e += P^T-stage . EA^T-stage for the slot `slot` (P filled by the 4 warps of every row quarter)
+        auto service_p = [&](uint32_t slot) {
+#pragma unroll 1
+            for (int qq = 0; qq < 4; ++qq) {
+                mbar_wait(&p_full[qq], slot & 1);
+                tc_fence_after_sync();
+                const uint32_t ph = smem_u32(p_base + (size_t)qq * G_P_BYTES), eh = ph + G_ATOM, el = eh + 32 * 128;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t ko = kk * 32;
+                    mma_tf32(d_dwe, make_desc(ph + ko), make_desc(eh + ko), idesc_p, (slot > 0 || qq > 0 || kk > 0) ? 1u : 0u);
+                    mma_tf32(d_dwe, make_desc(ph + ko), make_desc(el + ko), idesc_p, 1u);
+                }
+                mma_commit(&p_empty[qq]);
+            }
+        };
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int k = 0; k < 4; ++k, ++it) {
                 if (lane == 0) {
@@ -151,10 +185,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                     }
                     mma_commit(&ea_empty[s]);
                     mma_commit(&phi_full[b]);
+                    if (with_dwe && it > 0) service_p(it - 1);
                 }
                 __syncwarp();
             }
         }
+        if (lane == 0 && with_dwe && it > 0) {
+            service_p(it - 1);
+            mma_commit(&dwe_done);
+        }
+        __syncwarp();
     } else {
         // ---------------------------------------------------------------- compute warps
         const int q = warp & 3, grp = warp >> 2;
@@ -206,6 +246,29 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                     mbar_wait(&phi_full[b], bu & 1);
                     tc_fence_after_sync();
                     const int s_row = nbv[kc];
+                    if (MODE == 1 && with_dwe) {
+                        // the P / EA^T stage of this row quarter must have been consumed (slot itc - 1)
+                        mbar_wait(&p_empty[q], (itc & 1) ^ 1);
+                        // EA^T rows 8*grp .. 8*grp+7 for this thread's cell (column = lane)
+                        uint8_t* eh = p_base + (size_t)q * G_P_BYTES + G_ATOM;
+                        uint8_t* el = eh + 32 * 128;
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int e0 = grp * 8 + h2 * 4;
+                            if (e0 >= p.fe) continue;
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (tv && s_row >= 0) v = ldg4(p.ea + ((size_t)t * 4 + kc) * p.fe + e0);
+                            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float hi, lo;
+                                split_tf32(vv[i], hi, lo);
+                                const uint32_t off = atom_off(e0 + i, lane);
+                                *reinterpret_cast<float*>(eh + off) = hi;
+                                *reinterpret_cast<float*>(el + off) = lo;
+                            }
+                        }
+                    }
                     const uint32_t taddr = tmem_base + b * (uint32_t)FP + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
 #pragma unroll
                     for (int j = 0; j < CPT; j += 8) {
@@ -232,6 +295,36 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                             }
                         }
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (MODE == 1 && with_dwe) {
+                            // dphi = h(s) * d_agg[t_k]  ->  P^T (rows = features, columns = this quarter's 32 cells), TF32
+                            float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
+                            if (tv && f0 < p.f) {
+                                za = ldg4(p.z_prev + (size_t)t * p.f + f0);
+                                zb = ldg4(p.z_prev + (size_t)t * p.f + f0 + 4);
+                                if (p.p_scale != nullptr) {
+                                    float4 sa = ldg4(p.p_scale + f0), sb = ldg4(p.p_scale + f0 + 4);
+                                    float4 ha = ldg4(p.p_shift + f0), hb = ldg4(p.p_shift + f0 + 4);
+                                    za.x = fmaf(za.x, sa.x, ha.x); za.y = fmaf(za.y, sa.y, ha.y);
+                                    za.z = fmaf(za.z, sa.z, ha.z); za.w = fmaf(za.w, sa.w, ha.w);
+                                    zb.x = fmaf(zb.x, sb.x, hb.x); zb.y = fmaf(zb.y, sb.y, hb.y);
+                                    zb.z = fmaf(zb.z, sb.z, hb.z); zb.w = fmaf(zb.w, sb.w, hb.w);
+                                }
+                                if (p.p_relu) {
+                                    za.x = fmaxf(za.x, 0.f); za.y = fmaxf(za.y, 0.f); za.z = fmaxf(za.z, 0.f); za.w = fmaxf(za.w, 0.f);
+                                    zb.x = fmaxf(zb.x, 0.f); zb.y = fmaxf(zb.y, 0.f); zb.z = fmaxf(zb.z, 0.f); zb.w = fmaxf(zb.w, 0.f);
+                                }
+                            }
+                            const float dp[8] = {za.x * xa.x, za.y * xa.y, za.z * xa.z, za.w * xa.w,
+                                                 zb.x * xb.x, zb.y * xb.y, zb.z * xb.z, zb.w * xb.w};
+                            uint8_t* pq = p_base + (size_t)q * G_P_BYTES;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                // row = c0 + j + i (c0 + j is a multiple of 8, so row & 7 == i), column = lane
+                                const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)i) << 4) +
+                                                     (((uint32_t)lane & 3u) << 2);
+                                *reinterpret_cast<float*>(pq + off) = tf32_rna(dp[i]);
+                            }
+                        }
                         acc[j + 0] = fmaf(xa.x, __uint_as_float(ph[0]), acc[j + 0]);
                         acc[j + 1] = fmaf(xa.y, __uint_as_float(ph[1]), acc[j + 1]);
                         acc[j + 2] = fmaf(xa.z, __uint_as_float(ph[2]), acc[j + 2]);
@@ -242,8 +335,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                         acc[j + 7] = fmaf(xb.w, __uint_as_float(ph[7]), acc[j + 7]);
                     }
                     tc_fence_before_sync();
+                    if (MODE == 1 && with_dwe) fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&phi_free[b]);
+                    if (lane == 0) {
+                        mbar_arrive(&phi_free[b]);
+                        if (MODE == 1 && with_dwe) mbar_arrive(&p_full[q]);
+                    }
                 }
             }
             it += 4;
@@ -299,6 +396,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 }
             }
         }
+        if (MODE == 1 && with_dwe && grp == 0) {
+            float* outp = p.dwe_partials + (size_t)blockIdx.x * p.f * 32;
+            float v[32];
+            if (it > 0) {
+                mbar_wait(&dwe_done, 0);
+                tc_fence_after_sync();
+                tmem_ld32(tmem_base + 480u + ((uint32_t)(q * 32) << 16), v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (row < p.f) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(outp + (size_t)row * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
         if (MODE == 1 && p.s_partials != nullptr) {
             const int col = c0 + lane / (32 / CPT);
             if ((lane % (32 / CPT)) == 0 && col < p.f) {
@@ -329,13 +443,14 @@ extern "C" int dgnn_gather_tc_supported(int f, int fe) {
 
 static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
-    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + 1024;
+    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + 1024 +
+                  ((p.mode == 1 && p.dwe_partials) ? 4 * G_P_BYTES : 0);
 #define LAUNCH_G(CPT, MODE)                                                                                                \
     do {                                                                                                             \
         static bool configured = false;                                                                              \
         if (!configured) {                                                                                           \
             cudaError_t e = cudaFuncSetAttribute(gather_tc_kernel<CPT, MODE>,                                        \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);           \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);           \
             if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                          \
             configured = true;                                                                                       \
         }                                                                                                            \
@@ -377,7 +492,7 @@ extern "C" int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const
                                   int fe, const float* w_e, const float* b_e, const float* z_prev,
                                   const float* p_scale, const float* p_shift, const float* p_mean,
                                   const float* p_rstd, int p_relu, int64_t n_src, int64_t n_tgt, int f_in,
-                                  float* dy_prev, double* s_partials, void* stream) {
+                                  float* dy_prev, double* s_partials, float* dwe_partials, void* stream) {
     DGNN_REQUIRE(dgnn_gather_tc_supported(f_in, fe), "widths not supported by the tensor-core gather");
     DGNN_REQUIRE(d_agg && onbr && ea_own && w_e && b_e, "null pointer");
     GatherTcArgs p;
@@ -386,6 +501,7 @@ extern "C" int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const
     p.n_rows = n_src; p.f = f_in; p.fp = f_in <= 32 ? 32 : (f_in <= 64 ? 64 : 128); p.mode = 1; p.out = dy_prev;
     p.addend = d_self; p.n_add_rows = n_tgt;
     p.z_prev = z_prev; p.p_scale = p_scale; p.p_shift = p_shift; p.p_mean = p_mean; p.p_rstd = p_rstd;
-    p.p_relu = p_relu; p.s_partials = s_partials;
+    p.p_relu = p_relu; p.s_partials = s_partials; p.dwe_partials = dwe_partials;
+    DGNN_REQUIRE(dwe_partials == nullptr || z_prev != nullptr, "dW_e needs the layer input (z_prev)");
     return launch_gather_tc(p, as_stream(stream), "dgnn_gather_tc_bwd");
 }

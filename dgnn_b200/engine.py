@@ -421,26 +421,23 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
         need_prev = l > 0
         tc_gather = use_tensor_cores() and pk.fe > 0 and lib().dgnn_gather_tc_supported(pk.f_in, pk.fe)
         if tc_gather:
-            # dh / dy_prev / (S1,S2) with the edge filter on tensor cores; dW_e, db_e by the FP32 kernel
+            # dh / dy_prev / (S1,S2) and dW_e / db_e with the edge filter on tensor cores
+            tcg = lib().dgnn_tc_grid()
+            part = torch.empty((tcg, 2 * pk.f_in), dtype=torch.float64, device=dev) if need_prev else None
+            dy_prev = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev) if need_prev else None
+            dwe_p = torch.empty((tcg, pk.f_in, 32), dtype=torch.float32, device=dev)
+            call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.ea_own), pk.fe, ptr(pk.w_e),
+                 ptr(pk.b_e), ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+                 ptr(in_aff.mean) if in_aff else None, ptr(in_aff.rstd) if in_aff else None, int(relu_in),
+                 g.n_src, g.n_tgt, pk.f_in, ptr(dy_prev), ptr(part), ptr(dwe_p), st)
+            dwe = torch.empty((pk.f_in, 32), dtype=torch.float32, device=dev)
+            call("dgnn_reduce_partials_f32", ptr(dwe_p), tcg, pk.f_in * 32, ptr(dwe), st)
+            fe_u = c.w_e.shape[1]
+            grads["convs.%d.w_e" % l] = dwe[:c.f_in, :fe_u]
+            grads["convs.%d.b_e" % l] = dwe[:c.f_in, pk.fe]
             if need_prev:
-                part = torch.empty((lib().dgnn_tc_grid(), 2 * pk.f_in), dtype=torch.float64, device=dev)
-                dy_prev = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev)
-                call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.ea_own), pk.fe, ptr(pk.w_e),
-                     ptr(pk.b_e), ptr(x_in), ptr(in_aff.scale), ptr(in_aff.shift), ptr(in_aff.mean), ptr(in_aff.rstd),
-                     1, g.n_src, g.n_tgt, pk.f_in, ptr(dy_prev), ptr(part), st)
                 r = _reduce(part)
                 s1, s2 = r[:pk.f_in], r[pk.f_in:]
-            grid = lib().dgnn_gather_bwd_grid(pk.f_in)
-            plen = pk.f_in * (pk.fe + 1) + 2 * pk.f_in
-            part = torch.empty((grid, plen), dtype=torch.float64, device=dev)
-            call("dgnn_edge_filter_bwd", ptr(d_agg), ptr(g.onbr), ptr(g.ea_own), pk.fe, ptr(pk.w_e), ptr(pk.b_e),
-                 ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
-                 int(relu_in), g.n_src, g.n_tgt, pk.f_in, ptr(part), st)
-            r = _reduce(part)
-            fe_u = c.w_e.shape[1]
-            grads["convs.%d.w_e" % l] = r[:pk.f_in * pk.fe].view(pk.f_in, pk.fe)[:c.f_in, :fe_u]
-            grads["convs.%d.b_e" % l] = r[pk.f_in * pk.fe:pk.f_in * (pk.fe + 1)][:c.f_in]
-            if need_prev:
                 dy = dy_prev
         elif need_prev or pk.fe:
             grid = lib().dgnn_gather_bwd_grid(pk.f_in)

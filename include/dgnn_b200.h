@@ -125,7 +125,9 @@ int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const flo
 /* Aggregation with the edge filter on tensor cores (f_in <= 128, 4 <= fe <= 28):
  *   fwd: agg[t] = mean_k h(nbr[t,k]) (*) (w_e . ea[t,k] + b_e)
  *   bwd: dh[s] = d_self[s] (s < n_tgt) + sum_k (w_e . ea_own[s,k] + b_e) (*) d_agg[onbr[s,k]];
- *        dy_prev = relu'(z_prev*p_scale+p_shift) * dh, s_partials double[dgnn_tc_grid(), 2*f_in] = (S1, S2)
+ *        dy_prev = relu'(z_prev*p_scale+p_shift) * dh, s_partials double[dgnn_tc_grid(), 2*f_in] = (S1, S2);
+ *        dwe_partials float[dgnn_tc_grid(), f_in, 32] (nullable): columns 0..fe-1 = dW_e, column fe = db_e,
+ *        accumulated in TMEM from dphi = h(s) (*) d_agg (dphi rounded to TF32, ea split hi/lo)
  * followed by dgnn_dense_fwd_tc: z = [agg | h(x_in)] . W^T (+ epilogue as dgnn_layer_fwd). */
 int dgnn_gather_tc_supported(int f, int fe);
 int dgnn_gather_tc_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
@@ -135,7 +137,7 @@ int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const int32_t* o
                        int fe, const float* w_e, const float* b_e, const float* z_prev,
                        const float* p_scale, const float* p_shift, const float* p_mean,
                        const float* p_rstd, int p_relu, int64_t n_src, int64_t n_tgt, int f_in,
-                       float* dy_prev, double* s_partials, void* stream);
+                       float* dy_prev, double* s_partials, float* dwe_partials, void* stream);
 int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const float* in_scale, const float* in_shift,
                       int relu_in, const float* b_packed, const float* bias, const float* out_scale,
                       const float* out_shift, int relu_out, int64_t n_tgt, int f_in, int f_out, float* out,

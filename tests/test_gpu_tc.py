@@ -181,13 +181,19 @@ def test_gather_tc_forward_and_backward_match_generic_kernels(f_in, fe, ragged):
     s1_ref, s2_ref = r[f_in * (fe + 1):f_in * (fe + 1) + f_in], r[f_in * (fe + 1) + f_in:]
     dwe_ref = r[:f_in * (fe + 1)]
     dy = torch.empty(n, f_in, device=DEV)
-    part2 = torch.empty(lib().dgnn_tc_grid(), 2 * f_in, dtype=torch.float64, device=DEV)
+    tcg = lib().dgnn_tc_grid()
+    part2 = torch.empty(tcg, 2 * f_in, dtype=torch.float64, device=DEV)
+    dwe_p = torch.empty(tcg, f_in, 32, device=DEV)
     call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x),
-         ptr(sc), ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f_in, ptr(dy), ptr(part2), st)
+         ptr(sc), ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f_in, ptr(dy), ptr(part2), ptr(dwe_p), st)
     assert _rel(dy, dy_ref) < 3e-6
     r2 = part2.sum(0)
     assert _rel(r2[:f_in], s1_ref) < 1e-5 and _rel(r2[f_in:], s2_ref) < 1e-5
-    # edge-filter gradients only
+    # edge-filter gradients: dW_e (dphi rounded to TF32 -> ~1e-4 relative) and db_e (column fe)
+    dwe = dwe_p.double().sum(0)
+    assert _rel(dwe[:, :fe], dwe_ref[:f_in * fe].view(f_in, fe)) < 3e-4
+    assert _rel(dwe[:, fe], dwe_ref[f_in * fe:]) < 3e-4
+    # FP32 edge-filter-only kernel
     part3 = torch.empty(grid, plen, dtype=torch.float64, device=DEV)
     call("dgnn_edge_filter_bwd", ptr(d_agg), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x), ptr(sc), ptr(sh),
          1, n, n, f_in, ptr(part3), st)
