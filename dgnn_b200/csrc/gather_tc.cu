@@ -1,22 +1,24 @@
 // Edge-filtered neighbour aggregation with the edge filter on tensor cores.
 //
-//   agg[t] = (1/max(cnt,1)) * sum_{k: nbr[t,k]>=0}  h(nbr[t,k]) (*) phi_k,   phi_k = W_e . ea[t,k] + b_e
+//   MODE 0 (forward)   agg[t] = (1/max(cnt,1)) * sum_{k: nbr[t,k]>=0} h(nbr[t,k]) (*) phi_k,
+//                      phi_k = W_e . ea[t,k] + b_e
+//                      (learning/surfaceNetStaticEdgeFilters.py:75-96: lin_e, x_j * edge_attr, scatter-mean)
+//   MODE 1 (backward)  dh[s] = d_self[s] + sum_k phi(ea_own[s,k]) (*) d_agg[onbr[s,k]], then the ReLU mask of
+//                      the producer layer -> dy_prev, and the (S1, S2) sums of its normalisation
+//   dW_e kernel        dW_e[f,e] = sum_{s,k} h(s)[f] d_agg[onbr[s,k]][f] ea_own[s,k][e],  db_e[f] = sum dphi
 //
-// (learning/surfaceNetStaticEdgeFilters.py:75-96: lin_e, x_j * edge_attr, scatter-mean.)
 // Evaluating phi with FMAs costs 80 FMA per feature and cell and made the gather issue-bound
-// (profiles/r01_*); here phi_k for a tile of 128 cells is ONE small tcgen05 product
-//     PHI_k[128 cells x F] = EA_k[128 x 32] . WE[F x 32]^T        (K = 20 features + bias column, 3xTF32)
-// that lands in TMEM.  Each thread then owns one cell row and a strip of F/4 features: it reads its
-// strip of PHI_k from TMEM (tcgen05.ld), loads the same strip of the neighbour's row (128-bit loads,
-// norm-affine + ReLU of the producer layer applied on load), and accumulates h * phi in registers.
-// ~70 warp instructions per cell instead of ~750.
+// (profiles/r01_*).  Here PHI_k for a tile of 128 cells is one small tcgen05 product
+//     PHI_k[128 cells x F] = EA_k[128 x 32] . WE[F x 32]^T      (K = fe features + a bias column, 3xTF32)
+// that lands in TMEM (4 slots x F <= 512 columns).  Each thread then owns one cell row and a strip of
+// F/4 features; per 8 features it issues the 8 neighbour-row loads of all four slots (128-bit, the norm
+// affine + ReLU of the producer layer applied on load), reads the matching PHI strips from TMEM
+// (tcgen05.ld) and accumulates h * phi in registers.
+// dW_e is the product P^T . EA with P = dphi [edges x F]: both operands need the edge index contiguous,
+// so each thread scatters its strip of P (rounded to TF32) and of EA (hi / lo) transposed into K-major
+// shared-memory operands; the [F x 32] accumulator lives in TMEM for the whole kernel.
 //
-// The same kernel computes the backward gather  dh[s] = d_self[s] + sum_k phi(ea_own[s,k]) (*) d_agg[onbr[s,k]]
-// (mode 1: no mean, no activation on load, adds `addend`, applies the ReLU mask of the producer layer and
-// accumulates the (S1, S2) sums of its normalisation).
-//
-// Warp roles (one persistent CTA per SM): 16 compute warps (EA staging + strip accumulation),
-// 1 MMA warp.  Pipelines: EA ring (smem, 2 stages) and PHI ring (TMEM, 512 / F buffers).
+// Warp roles (one persistent CTA per SM): 16 compute warps, 1 MMA warp; no CTA-wide barrier in the loop.
 #include "umma.cuh"
 #include "common.cuh"
 
@@ -28,7 +30,8 @@ constexpr int G_NCW = 16;
 constexpr int G_THREADS = (G_NCW + 1) * 32;
 constexpr int G_M = 128;
 constexpr int G_EA_STAGES = 2;
-constexpr int G_ATOM = G_M * 128;  // 16 KB
+constexpr int G_ATOM = G_M * 128;                    // 16 KB
+constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
 
 struct GatherTcArgs {
     const float* x;        // rows to gather: h source (fwd) or d_agg (bwd)
@@ -42,31 +45,26 @@ struct GatherTcArgs {
     int fe;
     int64_t n_rows;
     int f;                 // feature width (multiple of 4, <= 128)
-    int fp;                // f padded to 32
-    int mode;              // 0: forward agg (mean);  1: backward dh
+    int fp;                // 32, 64 or 128
     float* out;            // fwd: agg [n_rows,f];  bwd: dy_prev [n_rows,f] (may be NULL)
     // backward extras
     const float* addend;   // d_self [n_add_rows, f] (rows >= n_add_rows add nothing), may be NULL
     int64_t n_add_rows;
-    const float* z_prev;   // pre-norm activations of the producer layer (mask + xhat), may be NULL
+    const float* z_prev;   // pre-norm activations of the producer layer = this layer's input (mask, xhat, h)
     const float* p_scale;  // producer norm affine (y = z*scale + shift), may be NULL
     const float* p_shift;
     const float* p_mean;
     const float* p_rstd;
     int p_relu;
     double* s_partials;    // [grid, 2*f] (S1, S2), may be NULL
-    float* dwe_partials;   // [grid, f, 32]: dW_e (cols 0..fe-1) and db_e (col fe), may be NULL
+    float* dwe_partials;   // dW_e kernel: [grid, f, 32]: dW_e (cols 0..fe-1) and db_e (col fe)
 };
 
-constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;   // per row-quarter: P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
-
-// butterfly transpose-reduce over the warp's 32 rows of CPT columns held in v[0..CPT):
-// returns in lane l (l < CPT) ... implemented for CPT = 8, 16, 32 by padding to 32 lanes
-template <int CPT>
-__device__ __forceinline__ float warp_colsum(float (&v)[CPT], int lane) {
-    // reduce rows pairwise until each of the CPT columns has 32/CPT partial copies, then finish by xor-shuffles
+// butterfly transpose-reduce of 8 columns over the warp's 32 rows: every lane l returns the sum of
+// column (l >> 2)
+__device__ __forceinline__ float warp_colsum8(float (&v)[8], int lane) {
 #pragma unroll
-    for (int off = 16, n = CPT / 2; n >= 1; off >>= 1, n >>= 1) {
+    for (int off = 16, n = 4; n >= 1; off >>= 1, n >>= 1) {
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int i = 0; i < n; ++i) {
@@ -75,43 +73,55 @@ __device__ __forceinline__ float warp_colsum(float (&v)[CPT], int lane) {
             v[i] = mine + __shfl_xor_sync(0xffffffffu, theirs, off);
         }
     }
-    // now v[0] holds, for column c(lane), the sum over a subset of rows; remaining lane bits below are still rows
     float s = v[0];
-#pragma unroll
-    for (int off = 16 / CPT; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    return s;  // column index = lane / (32 / CPT)   (every 32/CPT consecutive lanes hold the same column)
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
 }
 
-template <int CPT, int MODE>  // CPT: columns (features) per thread = fp / 4;  MODE 0 forward, 1 backward
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+
+__device__ __forceinline__ void act8(float4& a, float4& b, const float4& sa, const float4& sb, const float4& ha,
+                                     const float4& hb, bool affine, bool relu) {
+    if (affine) {
+        a.x = fmaf(a.x, sa.x, ha.x); a.y = fmaf(a.y, sa.y, ha.y); a.z = fmaf(a.z, sa.z, ha.z); a.w = fmaf(a.w, sa.w, ha.w);
+        b.x = fmaf(b.x, sb.x, hb.x); b.y = fmaf(b.y, sb.y, hb.y); b.z = fmaf(b.z, sb.z, hb.z); b.w = fmaf(b.w, sb.w, hb.w);
+    }
+    if (relu) {
+        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MODE 0 / 1: phi on tensor cores, strips accumulated in registers
+template <int CPT, int MODE>  // CPT: features per thread = fp / 4
 __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ea_full[G_EA_STAGES], ea_empty[G_EA_STAGES];
-    __shared__ uint64_t phi_full[8], phi_free[8];
-    __shared__ uint64_t p_full[4], p_empty[4], dwe_done;
+    __shared__ uint64_t phi_full, phi_free;
     __shared__ uint32_t tmem_slot;
     __shared__ double red_s[2 * 128];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int FP = CPT * 4;
-    const bool with_dwe = MODE == 1 && p.dwe_partials != nullptr;
-    const int phi_cols = with_dwe ? 480 : 512;           // the last 32 TMEM columns hold the dW_e accumulator
-    const int n_phi = phi_cols / FP > 8 ? 8 : phi_cols / FP;   // PHI buffers in TMEM
+    constexpr int FP = CPT * 4;
     uint8_t* we_hi = smem;                               // [FP rows x 128 B]
     uint8_t* we_lo = we_hi + FP * 128;
     uint8_t* ea_base = we_lo + FP * 128;                 // stages of (hi 16 KB | lo 16 KB)
-    uint8_t* p_base = ea_base + G_EA_STAGES * 2 * G_ATOM;  // 4 x (P_hi | EA^T hi | EA^T lo), backward only
 
     if (tid == 0) {
         for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_full[s], G_NCW); mbar_init(&ea_empty[s], 1); }
-        for (int b = 0; b < 8; ++b) { mbar_init(&phi_full[b], 1); mbar_init(&phi_free[b], G_NCW); }
-        for (int b = 0; b < 4; ++b) { mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1); }
-        mbar_init(&dwe_done, 1);
+        mbar_init(&phi_full, 1);
+        mbar_init(&phi_free, G_NCW);
         fence_barrier_init();
     }
     for (int c = tid; c < 256; c += G_THREADS) red_s[c] = 0.0;
-    // zero the EA stages (K padding columns stay zero) and build the WE operand:
-    // WE[n][e] = w_e[n][e] (e < fe), WE[n][fe] = b_e[n], rest 0
-    for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM + (with_dwe ? 4 * G_P_BYTES : 0)) / 16; i += G_THREADS)
+    // zero the operands (K padding stays zero), then WE[n][e] = w_e[n][e] (e < fe), WE[n][fe] = b_e[n]
+    for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM) / 16; i += G_THREADS)
         reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     for (int i = tid; i < p.f * (p.fe + 1); i += G_THREADS) {
@@ -123,17 +133,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         *reinterpret_cast<float*>(we_hi + off) = hi;
         *reinterpret_cast<float*>(we_lo + off) = lo;
     }
-    // the bias column of every EA stage: EA[r][fe] = 1
-    for (int i = tid; i < G_EA_STAGES * G_M; i += G_THREADS) {
+    for (int i = tid; i < G_EA_STAGES * G_M; i += G_THREADS) {   // bias column of every EA stage
         const int s = i / G_M, r = i % G_M;
         *reinterpret_cast<float*>(ea_base + (size_t)s * 2 * G_ATOM + atom_off(r, p.fe)) = 1.0f;
-    }
-    if (with_dwe) {
-        // row fe of every EA^T operand is all ones: column fe of dW_e accumulates db_e = sum dphi
-        for (int i = tid; i < 4 * 32; i += G_THREADS) {
-            const int qq = i >> 5, cell = i & 31;
-            *reinterpret_cast<float*>(p_base + (size_t)qq * G_P_BYTES + G_ATOM + atom_off(p.fe, cell)) = 1.0f;
-        }
     }
     fence_proxy_async_smem();
     if (warp == G_NCW) tmem_alloc(&tmem_slot, 512);
@@ -146,36 +148,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     if (warp == G_NCW) {
         // ---------------------------------------------------------------- MMA warp
         const uint32_t idesc = make_idesc_tf32(G_M, FP);
-        const uint32_t idesc_p = make_idesc_tf32(G_M, 32);
         const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
-        const uint32_t d_dwe = tmem_base + 480u;
-        uint32_t it = 0;
-        // dW_e += P^T-stage . EA^T-stage for the slot `slot` (P filled by the 4 warps of every row quarter)
-        auto service_p = [&](uint32_t slot) {
-#pragma unroll 1
-            for (int qq = 0; qq < 4; ++qq) {
-                mbar_wait(&p_full[qq], slot & 1);
-                tc_fence_after_sync();
-                const uint32_t ph = smem_u32(p_base + (size_t)qq * G_P_BYTES), eh = ph + G_ATOM, el = eh + 32 * 128;
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint32_t ko = kk * 32;
-                    mma_tf32(d_dwe, make_desc(ph + ko), make_desc(eh + ko), idesc_p, (slot > 0 || qq > 0 || kk > 0) ? 1u : 0u);
-                    mma_tf32(d_dwe, make_desc(ph + ko), make_desc(el + ko), idesc_p, 1u);
-                }
-                mma_commit(&p_empty[qq]);
-            }
-        };
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t it = 0, tile_cnt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
             for (int k = 0; k < 4; ++k, ++it) {
                 if (lane == 0) {
                     const uint32_t s = it % G_EA_STAGES, su = it / G_EA_STAGES;
-                    const uint32_t b = it % (uint32_t)n_phi, bu = it / (uint32_t)n_phi;
                     mbar_wait(&ea_full[s], su & 1);
-                    if (bu > 0) mbar_wait(&phi_free[b], (bu - 1) & 1);
+                    if (k == 0 && tile_cnt > 0) mbar_wait(&phi_free, (tile_cnt - 1) & 1);
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(ea_base + (size_t)s * 2 * G_ATOM), al = ah + G_ATOM;
-                    const uint32_t d = tmem_base + b * (uint32_t)FP;
+                    const uint32_t d = tmem_base + (uint32_t)(k * FP);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint32_t ko = kk * 32;
@@ -184,240 +167,163 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                         mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
                     }
                     mma_commit(&ea_empty[s]);
-                    mma_commit(&phi_full[b]);
-                    if (with_dwe && it > 0) service_p(it - 1);
+                    if (k == 3) mma_commit(&phi_full);
                 }
                 __syncwarp();
             }
         }
-        if (lane == 0 && with_dwe && it > 0) {
-            service_p(it - 1);
-            mma_commit(&dwe_done);
-        }
-        __syncwarp();
     } else {
         // ---------------------------------------------------------------- compute warps
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;                      // first feature of this thread's strip
         const bool relu = p.relu != 0;
+        const bool affine = p.scale != nullptr;
         const int fe4 = p.fe >> 2;
-        double s1d = 0.0, s2d = 0.0;   // running (S1, S2) of column c0 + lane / (32 / CPT)
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        double s1d[CPT / 8], s2d[CPT / 8];             // running (S1, S2) of column c0 + 8*jj + (lane >> 2)
+#pragma unroll
+        for (int i = 0; i < CPT / 8; ++i) s1d[i] = s2d[i] = 0.0;
+        uint32_t it = 0, tile_cnt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
             const int64_t tile0 = tile * G_M;
             const int64_t t = tile0 + row;
             const bool tv = t < p.n_rows;
             int4 nb4 = make_int4(-1, -1, -1, -1);
             if (tv) nb4 = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
             const int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-            float acc[CPT];
-#pragma unroll
-            for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
-            for (int k = 0; k <= 4; ++k) {
-                if (k < 4) {
-                    // ---- stage EA_k: rows of the tile, fe floats each, split into hi / lo
-                    const uint32_t itk = it + k;
-                    const uint32_t s = itk % G_EA_STAGES, su = itk / G_EA_STAGES;
-                    uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
-                    uint8_t* e_lo = e_hi + G_ATOM;
-                    mbar_wait(&ea_empty[s], (su & 1) ^ 1);
-                    for (int idx = tid; idx < G_M * fe4; idx += G_NCW * 32) {
-                        const int r = idx / fe4, c = idx % fe4;
-                        const int64_t tr = tile0 + r;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (tr < p.n_rows) v = ldg4(p.ea + ((size_t)tr * 4 + k) * p.fe + c * 4);
-                        float4 h, l;
-                        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                        const uint32_t off = atom_off(r, c * 4);
-                        *reinterpret_cast<float4*>(e_hi + off) = h;
-                        *reinterpret_cast<float4*>(e_lo + off) = l;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ea_full[s]);
+            // ---- stage EA_0..3 (rows of the tile, fe floats each, split hi / lo); the MMA warp follows
+            for (int k = 0; k < 4; ++k, ++it) {
+                const uint32_t s = it % G_EA_STAGES, su = it / G_EA_STAGES;
+                uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
+                uint8_t* e_lo = e_hi + G_ATOM;
+                mbar_wait(&ea_empty[s], (su & 1) ^ 1);
+                for (int idx = tid; idx < G_M * fe4; idx += G_NCW * 32) {
+                    const int r = idx / fe4, c = idx - r * fe4;
+                    const int64_t tr = tile0 + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (tr < p.n_rows) v = ldg4(p.ea + ((size_t)tr * 4 + k) * p.fe + c * 4);
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    const uint32_t off = atom_off(r, c * 4);
+                    *reinterpret_cast<float4*>(e_hi + off) = h;
+                    *reinterpret_cast<float4*>(e_lo + off) = l;
                 }
-                if (k > 0) {
-                    // ---- consume PHI_{k-1}
-                    const int kc = k - 1;
-                    const uint32_t itc = it + kc;
-                    const uint32_t b = itc % (uint32_t)n_phi, bu = itc / (uint32_t)n_phi;
-                    mbar_wait(&phi_full[b], bu & 1);
-                    tc_fence_after_sync();
-                    const int s_row = nbv[kc];
-                    if (MODE == 1 && with_dwe) {
-                        // the P / EA^T stage of this row quarter must have been consumed (slot itc - 1)
-                        mbar_wait(&p_empty[q], (itc & 1) ^ 1);
-                        // EA^T rows 8*grp .. 8*grp+7 for this thread's cell (column = lane)
-                        uint8_t* eh = p_base + (size_t)q * G_P_BYTES + G_ATOM;
-                        uint8_t* el = eh + 32 * 128;
-#pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            const int e0 = grp * 8 + h2 * 4;
-                            if (e0 >= p.fe) continue;
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (tv && s_row >= 0) v = ldg4(p.ea + ((size_t)t * 4 + kc) * p.fe + e0);
-                            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float hi, lo;
-                                split_tf32(vv[i], hi, lo);
-                                const uint32_t off = atom_off(e0 + i, lane);
-                                *reinterpret_cast<float*>(eh + off) = hi;
-                                *reinterpret_cast<float*>(el + off) = lo;
-                            }
-                        }
-                    }
-                    const uint32_t taddr = tmem_base + b * (uint32_t)FP + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-#pragma unroll
-                    for (int j = 0; j < CPT; j += 8) {
-                        uint32_t ph[8];
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                     : "=r"(ph[0]), "=r"(ph[1]), "=r"(ph[2]), "=r"(ph[3]), "=r"(ph[4]), "=r"(ph[5]),
-                                       "=r"(ph[6]), "=r"(ph[7])
-                                     : "r"(taddr + (uint32_t)j));
-                        float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-                        const int f0 = c0 + j;
-                        if (s_row >= 0 && f0 < p.f) {
-                            xa = ldg4(p.x + (size_t)s_row * p.f + f0);
-                            xb = ldg4(p.x + (size_t)s_row * p.f + f0 + 4);
-                            if (p.scale != nullptr) {
-                                float4 sa = ldg4(p.scale + f0), sb = ldg4(p.scale + f0 + 4);
-                                float4 ha = ldg4(p.shift + f0), hb = ldg4(p.shift + f0 + 4);
-                                xa.x = act(xa.x, sa.x, ha.x, relu); xa.y = act(xa.y, sa.y, ha.y, relu);
-                                xa.z = act(xa.z, sa.z, ha.z, relu); xa.w = act(xa.w, sa.w, ha.w, relu);
-                                xb.x = act(xb.x, sb.x, hb.x, relu); xb.y = act(xb.y, sb.y, hb.y, relu);
-                                xb.z = act(xb.z, sb.z, hb.z, relu); xb.w = act(xb.w, sb.w, hb.w, relu);
-                            } else if (relu) {
-                                xa.x = fmaxf(xa.x, 0.f); xa.y = fmaxf(xa.y, 0.f); xa.z = fmaxf(xa.z, 0.f); xa.w = fmaxf(xa.w, 0.f);
-                                xb.x = fmaxf(xb.x, 0.f); xb.y = fmaxf(xb.y, 0.f); xb.z = fmaxf(xb.z, 0.f); xb.w = fmaxf(xb.w, 0.f);
-                            }
-                        }
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (MODE == 1 && with_dwe) {
-                            // dphi = h(s) * d_agg[t_k]  ->  P^T (rows = features, columns = this quarter's 32 cells), TF32
-                            float4 za = make_float4(0.f, 0.f, 0.f, 0.f), zb = za;
-                            if (tv && f0 < p.f) {
-                                za = ldg4(p.z_prev + (size_t)t * p.f + f0);
-                                zb = ldg4(p.z_prev + (size_t)t * p.f + f0 + 4);
-                                if (p.p_scale != nullptr) {
-                                    float4 sa = ldg4(p.p_scale + f0), sb = ldg4(p.p_scale + f0 + 4);
-                                    float4 ha = ldg4(p.p_shift + f0), hb = ldg4(p.p_shift + f0 + 4);
-                                    za.x = fmaf(za.x, sa.x, ha.x); za.y = fmaf(za.y, sa.y, ha.y);
-                                    za.z = fmaf(za.z, sa.z, ha.z); za.w = fmaf(za.w, sa.w, ha.w);
-                                    zb.x = fmaf(zb.x, sb.x, hb.x); zb.y = fmaf(zb.y, sb.y, hb.y);
-                                    zb.z = fmaf(zb.z, sb.z, hb.z); zb.w = fmaf(zb.w, sb.w, hb.w);
-                                }
-                                if (p.p_relu) {
-                                    za.x = fmaxf(za.x, 0.f); za.y = fmaxf(za.y, 0.f); za.z = fmaxf(za.z, 0.f); za.w = fmaxf(za.w, 0.f);
-                                    zb.x = fmaxf(zb.x, 0.f); zb.y = fmaxf(zb.y, 0.f); zb.z = fmaxf(zb.z, 0.f); zb.w = fmaxf(zb.w, 0.f);
-                                }
-                            }
-                            const float dp[8] = {za.x * xa.x, za.y * xa.y, za.z * xa.z, za.w * xa.w,
-                                                 zb.x * xb.x, zb.y * xb.y, zb.z * xb.z, zb.w * xb.w};
-                            uint8_t* pq = p_base + (size_t)q * G_P_BYTES;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                // row = c0 + j + i (c0 + j is a multiple of 8, so row & 7 == i), column = lane
-                                const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ (uint32_t)i) << 4) +
-                                                     (((uint32_t)lane & 3u) << 2);
-                                *reinterpret_cast<float*>(pq + off) = tf32_rna(dp[i]);
-                            }
-                        }
-                        acc[j + 0] = fmaf(xa.x, __uint_as_float(ph[0]), acc[j + 0]);
-                        acc[j + 1] = fmaf(xa.y, __uint_as_float(ph[1]), acc[j + 1]);
-                        acc[j + 2] = fmaf(xa.z, __uint_as_float(ph[2]), acc[j + 2]);
-                        acc[j + 3] = fmaf(xa.w, __uint_as_float(ph[3]), acc[j + 3]);
-                        acc[j + 4] = fmaf(xb.x, __uint_as_float(ph[4]), acc[j + 4]);
-                        acc[j + 5] = fmaf(xb.y, __uint_as_float(ph[5]), acc[j + 5]);
-                        acc[j + 6] = fmaf(xb.z, __uint_as_float(ph[6]), acc[j + 6]);
-                        acc[j + 7] = fmaf(xb.w, __uint_as_float(ph[7]), acc[j + 7]);
-                    }
-                    tc_fence_before_sync();
-                    if (MODE == 1 && with_dwe) fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(&phi_free[b]);
-                        if (MODE == 1 && with_dwe) mbar_arrive(&p_full[q]);
-                    }
-                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ea_full[s]);
             }
-            it += 4;
-            // ---- finish the row strip
-            if (MODE == 0) {
-                const int cnt = (nbv[0] >= 0) + (nbv[1] >= 0) + (nbv[2] >= 0) + (nbv[3] >= 0);
-                const float d = (float)(cnt > 0 ? cnt : 1);
-                if (tv) {
+            // ---- consume: all four PHI_k of the tile are in TMEM
+            mbar_wait(&phi_full, tile_cnt & 1);
+            tc_fence_after_sync();
+            const int cnt = (nbv[0] >= 0) + (nbv[1] >= 0) + (nbv[2] >= 0) + (nbv[3] >= 0);
+            const float dcnt = (float)(cnt > 0 ? cnt : 1);
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
 #pragma unroll
-                    for (int j = 0; j < CPT; j += 4) {
-                        if (c0 + j >= p.f) continue;
-                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + c0 + j) =
-                            make_float4(acc[j] / d, acc[j + 1] / d, acc[j + 2] / d, acc[j + 3] / d);
-                    }
+            for (int j = 0; j < CPT; j += 8) {
+                const int f0 = c0 + j;
+                const bool fvalid = f0 < p.f, fvalid_b = f0 + 4 < p.f;   // the two 4-feature halves of the strip step
+                uint32_t ph[4][8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tmem_ld8(trow + (uint32_t)(k * FP + j), ph[k]);
+                float4 xa[4], xb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xb[k] = xa[k];
+                    if (nbv[k] >= 0 && fvalid) xa[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0);
+                    if (nbv[k] >= 0 && fvalid_b) xb[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0 + 4);
                 }
-            } else {
-                float dx[CPT];                       // dy * xhat (acc becomes dy)
+                float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), sb = sa, ha = make_float4(0.f, 0.f, 0.f, 0.f), hb = ha;
+                if (MODE == 0 && affine && fvalid) { sa = ldg4(p.scale + f0); ha = ldg4(p.shift + f0); }
+                if (MODE == 0 && affine && fvalid_b) { sb = ldg4(p.scale + f0 + 4); hb = ldg4(p.shift + f0 + 4); }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < CPT; j += 4) {
-                    const int f0 = c0 + j;
-                    float4 o = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-                    float4 ox = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!tv || f0 >= p.f) {
-                        o = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 4; ++k) {
+                    if (nbv[k] < 0) continue;
+                    if (MODE == 0) act8(xa[k], xb[k], sa, sb, ha, hb, affine, relu);
+                    acc[0] = fmaf(xa[k].x, __uint_as_float(ph[k][0]), acc[0]);
+                    acc[1] = fmaf(xa[k].y, __uint_as_float(ph[k][1]), acc[1]);
+                    acc[2] = fmaf(xa[k].z, __uint_as_float(ph[k][2]), acc[2]);
+                    acc[3] = fmaf(xa[k].w, __uint_as_float(ph[k][3]), acc[3]);
+                    acc[4] = fmaf(xb[k].x, __uint_as_float(ph[k][4]), acc[4]);
+                    acc[5] = fmaf(xb[k].y, __uint_as_float(ph[k][5]), acc[5]);
+                    acc[6] = fmaf(xb[k].z, __uint_as_float(ph[k][6]), acc[6]);
+                    acc[7] = fmaf(xb[k].w, __uint_as_float(ph[k][7]), acc[7]);
+                }
+                if (MODE == 0) {
+                    if (tv && fvalid)
+                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) =
+                            make_float4(acc[0] / dcnt, acc[1] / dcnt, acc[2] / dcnt, acc[3] / dcnt);
+                    if (tv && fvalid_b)
+                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) =
+                            make_float4(acc[4] / dcnt, acc[5] / dcnt, acc[6] / dcnt, acc[7] / dcnt);
+                } else {
+                    float dx[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dx[i] = 0.f;
+                    if (!tv || !fvalid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
                     } else {
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!fvalid_b) { acc[4] = acc[5] = acc[6] = acc[7] = 0.f; }
                         if (p.addend != nullptr && t < p.n_add_rows) {
                             float4 a = ldg4(p.addend + (size_t)t * p.f + f0);
-                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                            float4 b = fvalid_b ? ldg4(p.addend + (size_t)t * p.f + f0 + 4) : zero4;
+                            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+                            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
                         }
                         if (p.z_prev != nullptr) {
-                            float4 zv = ldg4(p.z_prev + (size_t)t * p.f + f0);
-                            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-                            float4 mu = sh, rs = sc;
-                            if (p.p_scale != nullptr) { sc = ldg4(p.p_scale + f0); sh = ldg4(p.p_shift + f0); }
-                            if (p.p_mean != nullptr) { mu = ldg4(p.p_mean + f0); rs = ldg4(p.p_rstd + f0); }
-                            if (p.p_relu) {
-                                if (!(fmaf(zv.x, sc.x, sh.x) > 0.f)) o.x = 0.f;
-                                if (!(fmaf(zv.y, sc.y, sh.y) > 0.f)) o.y = 0.f;
-                                if (!(fmaf(zv.z, sc.z, sh.z) > 0.f)) o.z = 0.f;
-                                if (!(fmaf(zv.w, sc.w, sh.w) > 0.f)) o.w = 0.f;
+                            float4 za = ldg4(p.z_prev + (size_t)t * p.f + f0);
+                            float4 zb = fvalid_b ? ldg4(p.z_prev + (size_t)t * p.f + f0 + 4) : zero4;
+                            const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                            float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            float mu[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rs[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+                            if (p.p_scale != nullptr) {
+                                float4 a = ldg4(p.p_scale + f0), b = fvalid_b ? ldg4(p.p_scale + f0 + 4) : zero4;
+                                float4 c = ldg4(p.p_shift + f0), d = fvalid_b ? ldg4(p.p_shift + f0 + 4) : zero4;
+                                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
+                                sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
                             }
-                            ox = make_float4(o.x * ((zv.x - mu.x) * rs.x), o.y * ((zv.y - mu.y) * rs.y),
-                                             o.z * ((zv.z - mu.z) * rs.z), o.w * ((zv.w - mu.w) * rs.w));
+                            if (p.p_mean != nullptr) {
+                                float4 a = ldg4(p.p_mean + f0), b = fvalid_b ? ldg4(p.p_mean + f0 + 4) : zero4;
+                                float4 c = ldg4(p.p_rstd + f0), d = fvalid_b ? ldg4(p.p_rstd + f0 + 4) : zero4;
+                                mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; mu[4] = b.x; mu[5] = b.y; mu[6] = b.z; mu[7] = b.w;
+                                rs[0] = c.x; rs[1] = c.y; rs[2] = c.z; rs[3] = c.w; rs[4] = d.x; rs[5] = d.y; rs[6] = d.z; rs[7] = d.w;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (p.p_relu && !(fmaf(zv[i], sc[i], sh[i]) > 0.f)) acc[i] = 0.f;
+                                if (i >= 4 && !fvalid_b) acc[i] = 0.f;
+                                dx[i] = acc[i] * ((zv[i] - mu[i]) * rs[i]);
+                            }
                         }
-                        if (p.out != nullptr) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = o;
+                        if (p.out != nullptr) {
+                            *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                            if (fvalid_b)
+                                *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                        }
                     }
-                    acc[j] = o.x; acc[j + 1] = o.y; acc[j + 2] = o.z; acc[j + 3] = o.w;
-                    dx[j] = ox.x; dx[j + 1] = ox.y; dx[j + 2] = ox.z; dx[j + 3] = ox.w;
-                }
-                if (p.s_partials != nullptr) {
-                    s1d += (double)warp_colsum<CPT>(acc, lane);
-                    s2d += (double)warp_colsum<CPT>(dx, lane);
+                    if (p.s_partials != nullptr) {
+                        s1d[j >> 3] += (double)warp_colsum8(acc, lane);
+                        s2d[j >> 3] += (double)warp_colsum8(dx, lane);
+                    }
                 }
             }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&phi_free);
         }
-        if (MODE == 1 && with_dwe && grp == 0) {
-            float* outp = p.dwe_partials + (size_t)blockIdx.x * p.f * 32;
-            float v[32];
-            if (it > 0) {
-                mbar_wait(&dwe_done, 0);
-                tc_fence_after_sync();
-                tmem_ld32(tmem_base + 480u + ((uint32_t)(q * 32) << 16), v);
-            } else {
+        if (MODE == 1 && p.s_partials != nullptr && (lane & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            }
-            if (row < p.f) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(outp + (size_t)row * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-        }
-        if (MODE == 1 && p.s_partials != nullptr) {
-            const int col = c0 + lane / (32 / CPT);
-            if ((lane % (32 / CPT)) == 0 && col < p.f) {
-                atomicAdd(&red_s[col], s1d);
-                atomicAdd(&red_s[128 + col], s2d);
+            for (int jj = 0; jj < CPT / 8; ++jj) {
+                const int col = c0 + jj * 8 + (lane >> 2);
+                if (col < p.f) {
+                    atomicAdd(&red_s[col], s1d[jj]);
+                    atomicAdd(&red_s[128 + col], s2d[jj]);
+                }
             }
         }
     }
@@ -433,6 +339,161 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     if (warp == G_NCW) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// dW_e / db_e.  Per slot and row quarter a double-buffered stage (P^T hi | EA^T hi | EA^T lo).
+template <int CPT>
+__global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t p_full[4][2], p_empty[4][2], dwe_done;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int qq = 0; qq < 4; ++qq)
+            for (int b = 0; b < 2; ++b) { mbar_init(&p_full[qq][b], 4); mbar_init(&p_empty[qq][b], 1); }
+        mbar_init(&dwe_done, 1);
+        fence_barrier_init();
+    }
+    for (int i = tid; i < 8 * G_P_BYTES / 16; i += G_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    // row fe of every EA^T operand is all ones: column fe of the accumulator collects db_e = sum dphi
+    for (int i = tid; i < 8 * 32; i += G_THREADS)
+        *reinterpret_cast<float*>(smem + (size_t)(i >> 5) * G_P_BYTES + G_ATOM + atom_off(p.fe, i & 31)) = 1.0f;
+    fence_proxy_async_smem();
+    if (warp == G_NCW) tmem_alloc(&tmem_slot, 32);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const int64_t n_tiles = (p.n_rows + G_M - 1) / G_M;
+
+    if (warp == G_NCW) {
+        const uint32_t idesc = make_idesc_tf32(G_M, 32);
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int k = 0; k < 4; ++k, ++it) {
+                if (lane == 0) {
+                    const uint32_t b = it & 1, bu = it >> 1;
+#pragma unroll 1
+                    for (int qq = 0; qq < 4; ++qq) {
+                        mbar_wait(&p_full[qq][b], bu & 1);
+                        tc_fence_after_sync();
+                        const uint32_t ph = smem_u32(smem + (size_t)(qq * 2 + b) * G_P_BYTES), eh = ph + G_ATOM, el = eh + 32 * 128;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t ko = kk * 32;
+                            mma_tf32(tmem_base, make_desc(ph + ko), make_desc(eh + ko), idesc, (it > 0 || qq > 0 || kk > 0) ? 1u : 0u);
+                            mma_tf32(tmem_base, make_desc(ph + ko), make_desc(el + ko), idesc, 1u);
+                        }
+                        mma_commit(&p_empty[qq][b]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0 && it > 0) mma_commit(&dwe_done);
+        __syncwarp();
+    } else {
+        const int q = warp & 3, grp = warp >> 2;
+        const int row = q * 32 + lane;
+        const int c0 = grp * CPT;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t t = tile * G_M + row;
+            const bool tv = t < p.n_rows;
+            int4 nb4 = make_int4(-1, -1, -1, -1);
+            if (tv) nb4 = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+            const int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+            // h strip of this row
+            float h[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; j += 4) {
+                const int f0 = c0 + j;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tv && f0 < p.f) {
+                    v = ldg4(p.z_prev + (size_t)t * p.f + f0);
+                    if (p.p_scale != nullptr) {
+                        float4 sc = ldg4(p.p_scale + f0), sh = ldg4(p.p_shift + f0);
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                    if (p.p_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+                h[j] = v.x; h[j + 1] = v.y; h[j + 2] = v.z; h[j + 3] = v.w;
+            }
+            for (int k = 0; k < 4; ++k, ++it) {
+                const uint32_t b = it & 1, bu = it >> 1;
+                uint8_t* pq = smem + (size_t)(q * 2 + b) * G_P_BYTES;
+                uint8_t* eh = pq + G_ATOM;
+                uint8_t* el = eh + 32 * 128;
+                const int s_row = nbv[k];
+                // gathered d_agg strip (all loads first), and this warp's share of the EA row
+                float4 da[CPT / 4];
+#pragma unroll
+                for (int j = 0; j < CPT; j += 4) {
+                    da[j >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s_row >= 0 && c0 + j < p.f) da[j >> 2] = ldg4(p.x + (size_t)s_row * p.f + c0 + j);
+                }
+                float4 ev[2];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int e0 = grp * 8 + h2 * 4;
+                    ev[h2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e0 < p.fe && tv && s_row >= 0) ev[h2] = ldg4(p.ea + ((size_t)t * 4 + k) * p.fe + e0);
+                }
+                mbar_wait(&p_empty[q][b], (bu & 1) ^ 1);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int e0 = grp * 8 + h2 * 4;
+                    if (e0 >= p.fe) continue;
+                    const float vv[4] = {ev[h2].x, ev[h2].y, ev[h2].z, ev[h2].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float hi, lo;
+                        split_tf32(vv[i], hi, lo);
+                        const uint32_t off = atom_off(e0 + i, lane);
+                        *reinterpret_cast<float*>(eh + off) = hi;
+                        *reinterpret_cast<float*>(el + off) = lo;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CPT; j += 4) {
+                    const float dp[4] = {h[j] * da[j >> 2].x, h[j + 1] * da[j >> 2].y, h[j + 2] * da[j >> 2].z, h[j + 3] * da[j >> 2].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // row = c0 + j + i, column = lane; c0 is a multiple of 8: row & 7 = (j & 4) + i
+                        const uint32_t r8 = (uint32_t)((j & 4) + i);
+                        const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ r8) << 4) + (((uint32_t)lane & 3u) << 2);
+                        *reinterpret_cast<float*>(pq + off) = tf32_rna(dp[i]);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[q][b]);
+            }
+        }
+        if (grp == 0) {
+            float* outp = p.dwe_partials + (size_t)blockIdx.x * p.f * 32;
+            float v[32];
+            if (it > 0) {
+                mbar_wait(&dwe_done, 0);
+                tc_fence_after_sync();
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (row < p.f) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(outp + (size_t)row * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == G_NCW) tmem_dealloc(tmem_base, 32);
+}
+
 }  // namespace dgnn
 
 using namespace dgnn;
@@ -441,37 +502,54 @@ extern "C" int dgnn_gather_tc_supported(int f, int fe) {
     return (f % 4 == 0 && f >= 4 && f <= 128 && fe % 4 == 0 && fe >= 4 && fe <= 28) ? 1 : 0;
 }
 
+static int fp_of(int f) { return f <= 32 ? 32 : (f <= 64 ? 64 : 128); }
+
+template <int MODE>
 static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
-    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + 1024 +
-                  ((p.mode == 1 && p.dwe_partials) ? 4 * G_P_BYTES : 0);
-#define LAUNCH_G(CPT, MODE)                                                                                                \
-    do {                                                                                                             \
-        static bool configured = false;                                                                              \
-        if (!configured) {                                                                                           \
-            cudaError_t e = cudaFuncSetAttribute(gather_tc_kernel<CPT, MODE>,                                        \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);           \
-            if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                          \
-            configured = true;                                                                                       \
-        }                                                                                                            \
-        gather_tc_kernel<CPT, MODE><<<sm_count(), G_THREADS, smem, st>>>(p);                                         \
+    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + 1024;
+#define LAUNCH_G(CPT)                                                                                          \
+    do {                                                                                                       \
+        static bool configured = false;                                                                        \
+        if (!configured) {                                                                                     \
+            cudaError_t e = cudaFuncSetAttribute(gather_tc_kernel<CPT, MODE>,                                  \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);     \
+            if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                    \
+            configured = true;                                                                                 \
+        }                                                                                                      \
+        gather_tc_kernel<CPT, MODE><<<sm_count(), G_THREADS, smem, st>>>(p);                                   \
     } while (0)
-    if (p.mode == 0) {
-        switch (cpt) {
-            case 8: LAUNCH_G(8, 0); break;
-            case 16: LAUNCH_G(16, 0); break;
-            case 32: LAUNCH_G(32, 0); break;
-            default: return fail(what, "unsupported feature width");
-        }
-    } else {
-        switch (cpt) {
-            case 8: LAUNCH_G(8, 1); break;
-            case 16: LAUNCH_G(16, 1); break;
-            case 32: LAUNCH_G(32, 1); break;
-            default: return fail(what, "unsupported feature width");
-        }
+    switch (cpt) {
+        case 8: LAUNCH_G(8); break;
+        case 16: LAUNCH_G(16); break;
+        case 32: LAUNCH_G(32); break;
+        default: return fail(what, "unsupported feature width");
     }
 #undef LAUNCH_G
+    return check_launch(what);
+}
+
+static int launch_dwe_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
+    const int cpt = p.fp / 4;
+    size_t smem = (size_t)8 * G_P_BYTES + 1024;
+#define LAUNCH_D(CPT)                                                                                          \
+    do {                                                                                                       \
+        static bool configured = false;                                                                        \
+        if (!configured) {                                                                                     \
+            cudaError_t e = cudaFuncSetAttribute(dwe_tc_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 210 * 1024);                                                  \
+            if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                    \
+            configured = true;                                                                                 \
+        }                                                                                                      \
+        dwe_tc_kernel<CPT><<<sm_count(), G_THREADS, smem, st>>>(p);                                            \
+    } while (0)
+    switch (cpt) {
+        case 8: LAUNCH_D(8); break;
+        case 16: LAUNCH_D(16); break;
+        case 32: LAUNCH_D(32); break;
+        default: return fail(what, "unsupported feature width");
+    }
+#undef LAUNCH_D
     return check_launch(what);
 }
 
@@ -484,8 +562,8 @@ extern "C" int dgnn_gather_tc_fwd(const float* x_in, const float* in_scale, cons
     memset(&p, 0, sizeof(p));
     p.x = x_in; p.scale = in_scale; p.shift = in_shift; p.relu = relu_in;
     p.nbr = nbr; p.ea = ea; p.w_e = w_e; p.b_e = b_e; p.fe = fe;
-    p.n_rows = n_tgt; p.f = f_in; p.fp = f_in <= 32 ? 32 : (f_in <= 64 ? 64 : 128); p.mode = 0; p.out = agg;
-    return launch_gather_tc(p, as_stream(stream), "dgnn_gather_tc_fwd");
+    p.n_rows = n_tgt; p.f = f_in; p.fp = fp_of(f_in); p.out = agg;
+    return launch_gather_tc<0>(p, as_stream(stream), "dgnn_gather_tc_fwd");
 }
 
 extern "C" int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const int32_t* onbr, const float* ea_own,
@@ -495,13 +573,19 @@ extern "C" int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const
                                   float* dy_prev, double* s_partials, float* dwe_partials, void* stream) {
     DGNN_REQUIRE(dgnn_gather_tc_supported(f_in, fe), "widths not supported by the tensor-core gather");
     DGNN_REQUIRE(d_agg && onbr && ea_own && w_e && b_e, "null pointer");
+    DGNN_REQUIRE(dwe_partials == nullptr || z_prev != nullptr, "dW_e needs the layer input (z_prev)");
     GatherTcArgs p;
     memset(&p, 0, sizeof(p));
     p.x = d_agg; p.nbr = onbr; p.ea = ea_own; p.w_e = w_e; p.b_e = b_e; p.fe = fe;
-    p.n_rows = n_src; p.f = f_in; p.fp = f_in <= 32 ? 32 : (f_in <= 64 ? 64 : 128); p.mode = 1; p.out = dy_prev;
+    p.n_rows = n_src; p.f = f_in; p.fp = fp_of(f_in); p.out = dy_prev;
     p.addend = d_self; p.n_add_rows = n_tgt;
     p.z_prev = z_prev; p.p_scale = p_scale; p.p_shift = p_shift; p.p_mean = p_mean; p.p_rstd = p_rstd;
     p.p_relu = p_relu; p.s_partials = s_partials; p.dwe_partials = dwe_partials;
-    DGNN_REQUIRE(dwe_partials == nullptr || z_prev != nullptr, "dW_e needs the layer input (z_prev)");
-    return launch_gather_tc(p, as_stream(stream), "dgnn_gather_tc_bwd");
+    cudaStream_t st = as_stream(stream);
+    if (dy_prev != nullptr || s_partials != nullptr) {
+        int rc = launch_gather_tc<1>(p, st, "dgnn_gather_tc_bwd");
+        if (rc) return rc;
+    }
+    if (dwe_partials != nullptr) return launch_dwe_tc(p, st, "dgnn_gather_tc_bwd(dW_e)");
+    return 0;
 }
