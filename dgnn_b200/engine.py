@@ -173,9 +173,10 @@ class Saved:
 
 
 def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGraph], pk_wt, pk_bias, w_e, b_e, fe,
-               out_aff: Optional[Affine], relu_out: bool, n_tgt, f_in, f_out, want_agg, want_stats, b_packed=None):
+               out_aff: Optional[Affine], relu_out: bool, n_tgt, f_in, f_out, want_agg, want_stats, b_packed=None,
+               out_rows=None):
     dev = x_in.device
-    out = torch.empty((n_tgt, f_out), dtype=torch.float32, device=dev)
+    out = torch.empty((out_rows or n_tgt, f_out), dtype=torch.float32, device=dev)
     agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if want_agg else None
     stats = None
     if want_stats:
@@ -189,7 +190,8 @@ def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGra
     return out, agg, stats
 
 
-def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_aff, relu_out, want_stats):
+def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_aff, relu_out, want_stats,
+                       out_rows=None):
     """Tensor-core layer forward as two kernels: aggregation with the edge filter on tcgen05
     (dgnn_gather_tc_fwd) -> agg, then z = [agg | h] . W^T (dgnn_dense_fwd_tc)."""
     dev = x_in.device
@@ -199,7 +201,7 @@ def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_a
     sh = ptr(in_aff.shift) if in_aff else None
     call("dgnn_gather_tc_fwd", ptr(x_in), sc, sh, int(relu_in), ptr(g.nbr), ptr(g.ea_in), pk.fe, ptr(pk.w_e),
          ptr(pk.b_e), n_tgt, pk.f_in, ptr(agg), _stream())
-    out = torch.empty((n_tgt, pk.f_out), dtype=torch.float32, device=dev)
+    out = torch.empty((out_rows or n_tgt, pk.f_out), dtype=torch.float32, device=dev)
     stats = torch.empty((lib().dgnn_tc_grid(), 2, pk.f_out), dtype=torch.float64, device=dev) if want_stats else None
     call("dgnn_dense_fwd_tc", ptr(agg), ptr(x_in), sc, sh, int(relu_in), ptr(pk.b_fwd), ptr(pk.bias),
          ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None, int(relu_out), n_tgt,
@@ -207,8 +209,10 @@ def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_a
     return out, agg, stats
 
 
-def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: bool, save: bool):
+def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: bool, save: bool, exchange=None):
     """Run all conv layers + decoder.  ``x0``: float32[n_src0, pad4(F0)] in the graphs' row order.
+    ``exchange`` (eval only): callable filling the halo rows ``h[n_tgt:]`` of a layer's output in place
+    (partitioned scenes, ``dgnn_b200.partition``); outputs are then allocated with ``n_src`` rows.
     Returns ``(logits, Saved or None)``.  In training mode the norms use batch statistics
     (and update the running buffers); in eval mode the running-statistic affine + ReLU is fused
     into each layer's epilogue."""
@@ -243,11 +247,14 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             h, in_aff, relu_in = z, aff, True
         else:
             aff = eval_affine(c.norm, pk.f_out, dev)
+            out_rows = g.n_src if (exchange is not None and l + 1 < L) else g.n_tgt
             if split:
-                h, _, _ = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False)
+                h, _, _ = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False, out_rows=out_rows)
             else:
                 h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
-                                     g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd)
+                                     g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd, out_rows=out_rows)
+            if exchange is not None and l + 1 < L:
+                exchange(h)
             in_aff, relu_in = None, False
     n_out = graphs[-1].n_tgt
     f_last = spec.convs[-1].f_out

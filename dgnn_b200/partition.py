@@ -1,0 +1,136 @@
+"""Spatial partition of a cell graph across the GPUs of one box with a per-layer halo exchange
+(north_star subsystem 4).
+
+Cells are ordered by the Morton code of their centroid and split into ``world_size`` contiguous
+ranges.  A rank owns one range and keeps, behind its owned rows, a *halo*: the remote cells adjacent
+to owned cells, grouped by owning rank (ascending global id).  Before every layer after the first,
+the boundary rows each peer needs are packed (``dgnn_gather_rows``), exchanged with ONE
+``all_to_all_single`` (NCCL over NVLink; gloo in the CPU tests) and land directly in the halo rows of
+the activation matrix, so the local ELL table indexes ``[owned | halo]`` without further copies.
+
+The maps are integer tables; ``tests/test_partition_cpu.py`` checks them bit-exactly against the NumPy
+oracle and runs the exchange with world_size 2 on gloo.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class HaloMaps:
+    rank: int
+    world: int
+    lo: int
+    hi: int
+    n_own: int
+    n_halo: int
+    local_nbr: torch.Tensor          # int32[n_own,4] ids into [owned | halo]
+    halo_gid: torch.Tensor           # int64[n_halo] global ids (partition order), ascending = grouped by owner
+    recv_counts: List[int]           # halo rows owned by each peer
+    send_idx: torch.Tensor           # int32[sum(send_counts)] local owned rows, grouped by destination peer
+    send_counts: List[int]
+
+
+def partition_bounds(n_cells: int, world: int) -> torch.Tensor:
+    return (torch.arange(world + 1, dtype=torch.int64) * n_cells) // world
+
+
+def build_halo_maps(nbr: torch.Tensor, bounds: torch.Tensor, rank: int) -> HaloMaps:
+    """``nbr`` int32[N,4]: the global ELL table in partition (Morton) order, on any device.
+    Every rank holds the whole table (replicated build, sharded compute)."""
+    world = bounds.numel() - 1
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    dev = nbr.device
+    own = nbr[lo:hi].to(torch.int64)
+    remote = (own < lo) | (own >= hi)
+    halo_gid = torch.unique(own[remote])                       # sorted ascending
+    local = own - lo
+    if halo_gid.numel():
+        local = torch.where(remote, (hi - lo) + torch.searchsorted(halo_gid, own), local)
+    b = bounds.to(dev)
+    owner = torch.searchsorted(b, halo_gid, right=True) - 1
+    recv_counts = torch.bincount(owner, minlength=world).tolist() if halo_gid.numel() else [0] * world
+    send, send_counts = [], []
+    for q in range(world):
+        if q == rank:
+            send_counts.append(0)
+            continue
+        theirs = nbr[int(bounds[q]):int(bounds[q + 1])].to(torch.int64)
+        need = torch.unique(theirs[(theirs >= lo) & (theirs < hi)]) - lo
+        send.append(need.to(torch.int32))
+        send_counts.append(int(need.numel()))
+    send_idx = torch.cat(send) if send else torch.zeros(0, dtype=torch.int32, device=dev)
+    return HaloMaps(rank, world, lo, hi, hi - lo, int(halo_gid.numel()), local.to(torch.int32).contiguous(), halo_gid,
+                    [int(c) for c in recv_counts], send_idx.contiguous(), send_counts)
+
+
+def exchange_halo(h: torch.Tensor, m: HaloMaps, group=None) -> None:
+    """Fill the halo rows ``h[n_own:]`` with the owners' rows.  ``h``: float32[n_own + n_halo, F]."""
+    if m.world == 1:
+        return
+    f = h.shape[1]
+    n_send = int(m.send_idx.numel())
+    if h.is_cuda:
+        from ._lib import call, ptr
+        send = torch.empty((n_send, f), dtype=h.dtype, device=h.device)
+        if n_send:
+            call("dgnn_gather_rows", ptr(h), ptr(m.send_idx), n_send, f, ptr(send), torch.cuda.current_stream().cuda_stream)
+    else:  # host logic of the CPU tests (gloo)
+        send = h.index_select(0, m.send_idx.long())
+    recv = h[m.n_own:]                                        # halo rows are contiguous and grouped by owner
+    dist.all_to_all_single(recv, send, output_split_sizes=m.recv_counts, input_split_sizes=m.send_counts, group=group)
+
+
+class PartitionedInference:
+    """Whole-scene inference of a ``SurfaceNet`` sharded over the ranks of the default process group.
+
+    Every rank calls ``run(data_all)`` with the same ``data_all`` (x, edge_index, edge_attr, pos) and gets
+    the logits of its owned cells plus their global (caller-order) indices."""
+
+    def __init__(self, model, group=None):
+        self.model = model
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._plan = None
+
+    def prepare(self, data_all):
+        from .graph import EllGraph, build_full_graph, pad4, pad_cols
+        net = self.model
+        dev = net._device()
+        cols = slice(1, None) if net.clf.regularization.cell_type else slice(None)
+        n = data_all.x.shape[0]
+        ea = None
+        if net.clf.model.edge_convs:
+            ea = data_all.edge_attr[:, 1:] if net.clf.regularization.edge_type else data_all.edge_attr
+        pos = getattr(data_all, "pos", None)
+        full = build_full_graph(data_all.edge_index.to(torch.long), ea, n, dev, pos=pos, order="auto", need_backward=False)
+        bounds = partition_bounds(n, self.world)
+        maps = build_halo_maps(full.nbr, bounds, self.rank)
+        lo, hi = maps.lo, maps.hi
+        g = EllGraph(n_src=maps.n_own + maps.n_halo, n_tgt=maps.n_own, fe=full.fe, nbr=maps.local_nbr,
+                     ea_in=full.ea_in[lo:hi].contiguous() if full.ea_in is not None else None)
+        x = data_all.x[:, cols].to(dev, dtype=torch.float32)
+        xp = full.permute_rows(pad_cols(x, pad4(x.shape[1])))
+        # layer-0 input for [owned | halo]: features are static, so the halo rows are taken locally
+        rows = torch.cat([torch.arange(lo, hi, device=dev), maps.halo_gid.to(dev)])
+        x0 = xp.index_select(0, rows).contiguous()
+        owned_caller_ids = full.perm[lo:hi].long() if full.perm is not None else torch.arange(lo, hi, device=dev)
+        self._plan = (g, maps, x0, owned_caller_ids)
+        return self._plan
+
+    @torch.no_grad()
+    def run(self, data_all):
+        from . import engine
+        if self._plan is None:
+            self.prepare(data_all)
+        g, maps, x0, ids = self._plan
+        net = self.model
+        with torch.cuda.device(x0.device):
+            out, _ = engine.forward(net._spec(), [g] * net.num_layers, x0, training=False, save=False,
+                                    exchange=lambda h: exchange_halo(h, maps, self.group))
+        return ids, out
