@@ -226,7 +226,42 @@ __global__ void __launch_bounds__(NT, 2) layer_fwd_kernel(const LayerFwdArgs p) 
     }
 }
 
-static int g_layer_grid = 0;
+// agg[t] = (1/max(cnt,1)) * sum_k h(x[nbr[t,k]]) (*) phi[t,k,:] with the edge filter given as a matrix
+// (the Updated-edge-filter variant carries the edge state from layer to layer,
+// learning/surfaceNetUpdatedEdgeFilters.py:157-176,236-241).  One thread per (cell, 4 features).
+__global__ void __launch_bounds__(256) gather_phi_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                         const float* __restrict__ sh, int relu,
+                                                         const int32_t* __restrict__ nbr, const float* __restrict__ phi,
+                                                         long long n_tgt, int f, float* __restrict__ agg) {
+    const int f4 = f >> 2;
+    const long long total = n_tgt * f4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / f4;
+        const int c = (int)(i % f4) * 4;
+        const int4 nb = __ldg(reinterpret_cast<const int4*>(nbr) + t);
+        const int nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sc) { s4 = ldg4(sc + c); h4 = ldg4(sh + c); }
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (nbv[k] < 0) continue;
+            ++cnt;
+            float4 v = ldg4(x + (size_t)nbv[k] * f + c);
+            float4 ph = ldg4(phi + ((size_t)t * 4 + k) * f + c);
+            if (sc) {
+                v.x = act(v.x, s4.x, h4.x, relu); v.y = act(v.y, s4.y, h4.y, relu);
+                v.z = act(v.z, s4.z, h4.z, relu); v.w = act(v.w, s4.w, h4.w, relu);
+            } else if (relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            a.x = fmaf(v.x, ph.x, a.x); a.y = fmaf(v.y, ph.y, a.y); a.z = fmaf(v.z, ph.z, a.z); a.w = fmaf(v.w, ph.w, a.w);
+        }
+        const float d = (float)(cnt > 0 ? cnt : 1);
+        *reinterpret_cast<float4*>(agg + (size_t)t * f + c) = make_float4(a.x / d, a.y / d, a.z / d, a.w / d);
+    }
+}
 
 }  // namespace dgnn
 
@@ -292,4 +327,17 @@ extern "C" int dgnn_layer_fwd(const float* x_in, const float* in_scale, const fl
         case 32: return launch_layer_fwd<32>(p, smem, grid, st);
     }
     return fail("dgnn_layer_fwd", "unsupported edge feature width");
+}
+
+extern "C" int dgnn_gather_phi_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                                   const int32_t* nbr, const float* phi, int64_t n_tgt, int f, float* agg,
+                                   void* stream) {
+    DGNN_REQUIRE(f % 4 == 0 && f > 0, "f must be a positive multiple of 4");
+    DGNN_REQUIRE(x_in && nbr && phi && agg, "null pointer");
+    if (n_tgt <= 0) return 0;
+    long long total = (long long)n_tgt * (f / 4);
+    long long g = (total + 255) / 256, cap = (long long)sm_count() * 16;
+    gather_phi_kernel<<<(int)(g < cap ? g : cap), 256, 0, as_stream(stream)>>>(x_in, in_scale, in_shift, relu_in, nbr, phi,
+                                                                              n_tgt, f, agg);
+    return check_launch("dgnn_gather_phi_fwd");
 }

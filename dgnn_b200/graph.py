@@ -56,6 +56,7 @@ class EllGraph:
     ea_own: Optional[torch.Tensor] = None
     perm: Optional[torch.Tensor] = None      # int32[n]: new -> old  (None = caller order)
     inv: Optional[torch.Tensor] = None       # int32[n]: old -> new
+    _eid_in: Optional[torch.Tensor] = None   # int32[n_tgt,4]: local edge id of every (target, slot), -1 = none
 
     def permute_rows(self, x: torch.Tensor) -> torch.Tensor:
         """Rows of ``x`` (caller order, width multiple of 4) in internal order."""
@@ -201,4 +202,4 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
         if need_backward:
             ea_own = torch.empty((n_src, 4, fe), dtype=torch.float32, device=dev)
             call("dgnn_gather_rows", ptr(ea), ptr(eid_out), n_src * 4, fe, ptr(ea_own), st)
-    return EllGraph(n_src=n_src, n_tgt=n_tgt, fe=fe, nbr=nbr, ea_in=ea_in, onbr=onbr, ea_own=ea_own)
+    return EllGraph(n_src=n_src, n_tgt=n_tgt, fe=fe, nbr=nbr, ea_in=ea_in, onbr=onbr, ea_own=ea_own, _eid_in=eid_in)

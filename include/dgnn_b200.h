@@ -155,6 +155,11 @@ int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float*
 int dgnn_debug_umma(const uint8_t* a_img, int a_bytes, const uint8_t* b_img, int b_bytes, uint64_t a_desc,
                     uint64_t b_desc, uint32_t idesc, int n, float* out, void* stream);
 
+/* Updated-edge-filter variant (learning/surfaceNetUpdatedEdgeFilters.py:157-176): aggregation with a
+ * materialised edge state phi float32[n_tgt,4,f]:  agg[t] = mean_k h(x_in[nbr[t,k]]) (*) phi[t,k,:] */
+int dgnn_gather_phi_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                        const int32_t* nbr, const float* phi, int64_t n_tgt, int f, float* agg, void* stream);
+
 /* Reduce per-CTA (sum, sum^2) partials and produce the normalisation's per-channel affine.
  * mode 0 = BatchNorm1d training statistics (biased var for normalisation; running_mean /
  *          running_var (unbiased) updated with `momentum` when non-NULL),

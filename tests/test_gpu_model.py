@@ -198,3 +198,24 @@ def test_unsupported_options_fail_loudly():
     net = SurfaceNet(make_clf(device=DEV, edge_convs=2)).to(DEV).eval()
     with pytest.raises(NotImplementedError):
         net.inference_layer(data_all(g))
+
+
+def test_updated_edge_filters_forward_matches_reference_golden(golden):
+    """Row U: the Updated-edge-filter variant (forward) against the reference's own output."""
+    from dgnn_b200.surfaceNetUpdatedEdgeFilters import SurfaceNet as UpdNet
+    d = golden_data(golden)
+    n_id = torch.from_numpy(golden["upd_n_id"])
+    bs, n_id2, adjs = next(iter(NeighborSampler(d.edge_index, [-1] * 4, 96, node_idx=torch.arange(40, 136),
+                                                num_nodes=d.x.shape[0])))
+    assert torch.equal(n_id, n_id2)
+    for tag, name in (("upd", "sage"), ("updp", "sage+")):
+        clf = to_attr(dict(training=dict(model_params=[16, 32, 32, 32], model_name=name),
+                           features=dict(normalization_feature=1, keep_normalization_feature=0),
+                           temp=dict(device=DEV)))
+        m = UpdNet(28, clf)
+        m.load_state_dict({k[len(tag) + 6:]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(tag + "_init.")},
+                          strict=True)
+        m.to(DEV)
+        y = m(to_attr(dict(x=d.x, edge_attr=d.edge_attr, n_id=n_id, adjs=adjs)))
+        err, ok = logits_close(y.cpu().numpy(), golden[tag + "_logits"])
+        assert ok, (name, err)
