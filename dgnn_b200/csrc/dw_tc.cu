@@ -133,8 +133,38 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             uint8_t* a_lo = a_hi + DW_A_BYTES;
             uint8_t* b_hi = a_lo + DW_A_BYTES;
             uint8_t* b_lo = b_hi + b_bytes;
+            // phase 1: all global loads of this warp's items (up to 6) go in flight together
+            constexpr int MAXI = 6;   // 8 * (4 + 8) items / 16 warps
+            float4 r0[MAXI], r1[MAXI];
+#pragma unroll
+            for (int u = 0; u < MAXI; ++u) {
+                const int item = warp + u * DW_NPW;
+                r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r1[u] = r0[u];
+                if (item >= n_items) continue;
+                const int g = item & 7, blk = item >> 3;
+                const int64_t t = (g_begin + i) * DW_CELLS + g * 4 + j;
+                if (t >= p.n_tgt) continue;
+                if (blk < nb_a) {
+                    const int ch = blk * 32 + c * 4;
+                    if (ch < p.f_out) {
+                        r0[u] = ldg4(p.dy + (size_t)t * p.f_out + ch);
+                        if (p.ng != nullptr) r1[u] = ldg4(p.z + (size_t)t * p.f_out + ch);
+                    }
+                } else {
+                    const int n = (blk - nb_a) * 32 + c * 4;
+                    if (n < p.k_total) {
+                        if (p.agg != nullptr && n < p.f_in) r0[u] = ldg4(p.agg + (size_t)t * p.f_in + n);
+                        else r0[u] = ldg4(p.x_in + (size_t)t * p.f_in + (p.agg != nullptr ? n - p.f_in : n));
+                    }
+                }
+            }
             mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-            for (int item = warp; item < n_items; item += DW_NPW) {
+            // phase 2: transform, transpose (4 channels x 1 cell -> 1 channel x 4 cells), split, store
+#pragma unroll
+            for (int u = 0; u < MAXI; ++u) {
+                const int item = warp + u * DW_NPW;
+                if (item >= n_items) continue;
                 const int g = item & 7, blk = item >> 3;
                 const int64_t t = (g_begin + i) * DW_CELLS + g * 4 + j;
                 const bool tv = t < p.n_tgt;
@@ -144,9 +174,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                 if (blk < nb_a) {                       // dz block -> A operand rows (channels)
                     const int ch = blk * 32 + c * 4;
                     if (tv && ch < p.f_out) {
-                        float4 d = ldg4(p.dy + (size_t)t * p.f_out + ch);
+                        const float4 d = r0[u];
                         if (p.ng != nullptr) {
-                            float4 zv = ldg4(p.z + (size_t)t * p.f_out + ch);
+                            const float4 zv = r1[u];
                             float4 gg = ldg4(p.ng + ch), a = ldg4(p.na + ch), b = ldg4(p.nb + ch), m = ldg4(p.nmean + ch),
                                    rs = ldg4(p.nrstd + ch);
                             v.x = gg.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
@@ -162,11 +192,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                 } else {                                // [agg | h] block -> B operand rows (columns of dW)
                     const int n = (blk - nb_a) * 32 + c * 4;
                     if (tv && n < p.k_total) {
-                        if (p.agg != nullptr && n < p.f_in) {
-                            v = ldg4(p.agg + (size_t)t * p.f_in + n);
-                        } else {
+                        v = r0[u];
+                        if (!(p.agg != nullptr && n < p.f_in)) {
                             const int col = p.agg != nullptr ? n - p.f_in : n;
-                            v = ldg4(p.x_in + (size_t)t * p.f_in + col);
                             if (p.in_scale != nullptr) {
                                 float4 sc = ldg4(p.in_scale + col), sh = ldg4(p.in_shift + col);
                                 v.x = act(v.x, sc.x, sh.x, relu); v.y = act(v.y, sc.y, sh.y, relu);

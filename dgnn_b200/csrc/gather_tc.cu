@@ -29,7 +29,7 @@ using namespace umma;
 constexpr int G_NCW = 16;
 constexpr int G_THREADS = (G_NCW + 1) * 32;
 constexpr int G_M = 128;
-constexpr int G_EA_STAGES = 2;
+constexpr int G_EA_STAGES = 4;                       // one tile (4 slots) of EA operands ahead
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
 constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
 
@@ -179,19 +179,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         const int c0 = grp * CPT;                      // first feature of this thread's strip
         const bool relu = p.relu != 0;
         const bool affine = p.scale != nullptr;
+        const bool al8 = (p.f & 7) == 0;
         const int fe4 = p.fe >> 2;
         double s1d[CPT / 8], s2d[CPT / 8];             // running (S1, S2) of column c0 + 8*jj + (lane >> 2)
 #pragma unroll
         for (int i = 0; i < CPT / 8; ++i) s1d[i] = s2d[i] = 0.0;
         uint32_t it = 0, tile_cnt = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
-            const int64_t tile0 = tile * G_M;
-            const int64_t t = tile0 + row;
-            const bool tv = t < p.n_rows;
-            int4 nb4 = make_int4(-1, -1, -1, -1);
-            if (tv) nb4 = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
-            const int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-            // ---- stage EA_0..3 (rows of the tile, fe floats each, split hi / lo); the MMA warp follows
+        // stage EA_0..3 of a tile (rows of the tile, fe floats each, split hi / lo); the MMA warp follows
+        auto stage_ea = [&](int64_t tile_s) {
+            const int64_t base = tile_s * G_M;
             for (int k = 0; k < 4; ++k, ++it) {
                 const uint32_t s = it % G_EA_STAGES, su = it / G_EA_STAGES;
                 uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
@@ -199,7 +195,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 mbar_wait(&ea_empty[s], (su & 1) ^ 1);
                 for (int idx = tid; idx < G_M * fe4; idx += G_NCW * 32) {
                     const int r = idx / fe4, c = idx - r * fe4;
-                    const int64_t tr = tile0 + r;
+                    const int64_t tr = base + r;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (tr < p.n_rows) v = ldg4(p.ea + ((size_t)tr * 4 + k) * p.fe + c * 4);
                     float4 h, l;
@@ -213,6 +209,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ea_full[s]);
             }
+        };
+        if ((int64_t)blockIdx.x < n_tiles) stage_ea(blockIdx.x);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const int64_t tile0 = tile * G_M;
+            const int64_t t = tile0 + row;
+            const bool tv = t < p.n_rows;
+            int4 nb4 = make_int4(-1, -1, -1, -1);
+            if (tv) nb4 = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+            const int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+            // EA of the next tile goes in flight before this tile is consumed (its MMAs wait for phi_free)
+            if (tile + gridDim.x < n_tiles) stage_ea(tile + gridDim.x);
             // ---- consume: all four PHI_k of the tile are in TMEM
             mbar_wait(&phi_full, tile_cnt & 1);
             tc_fence_after_sync();
@@ -231,8 +238,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 for (int k = 0; k < 4; ++k) {
                     xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                     xb[k] = xa[k];
-                    if (nbv[k] >= 0 && fvalid) xa[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0);
-                    if (nbv[k] >= 0 && fvalid_b) xb[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0 + 4);
+                    if (al8) {   // rows are 32-byte aligned: one 256-bit request instead of two 128-bit ones
+                        if (nbv[k] >= 0 && fvalid) ldg8(p.x + (size_t)nbv[k] * p.f + f0, xa[k], xb[k]);
+                    } else {
+                        if (nbv[k] >= 0 && fvalid) xa[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0);
+                        if (nbv[k] >= 0 && fvalid_b) xb[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0 + 4);
+                    }
                 }
                 float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), sb = sa, ha = make_float4(0.f, 0.f, 0.f, 0.f), hb = ha;
                 if (MODE == 0 && affine && fvalid) { sa = ldg4(p.scale + f0); ha = ldg4(p.shift + f0); }
@@ -429,9 +440,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                 // gathered d_agg strip (all loads first), and this warp's share of the EA row
                 float4 da[CPT / 4];
 #pragma unroll
-                for (int j = 0; j < CPT; j += 4) {
+                for (int j = 0; j < CPT; j += 8) {
                     da[j >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (s_row >= 0 && c0 + j < p.f) da[j >> 2] = ldg4(p.x + (size_t)s_row * p.f + c0 + j);
+                    da[(j >> 2) + 1] = da[j >> 2];
+                    if ((p.f & 7) == 0) {
+                        if (s_row >= 0 && c0 + j < p.f) ldg8(p.x + (size_t)s_row * p.f + c0 + j, da[j >> 2], da[(j >> 2) + 1]);
+                    } else {
+                        if (s_row >= 0 && c0 + j < p.f) da[j >> 2] = ldg4(p.x + (size_t)s_row * p.f + c0 + j);
+                        if (s_row >= 0 && c0 + j + 4 < p.f) da[(j >> 2) + 1] = ldg4(p.x + (size_t)s_row * p.f + c0 + j + 4);
+                    }
                 }
                 float4 ev[2];
 #pragma unroll

@@ -165,6 +165,100 @@ __device__ __forceinline__ void produce_dz(const TcArgs& p, uint8_t* a_hi, uint8
     }
 }
 
+// ---- two-phase producers (dense / dz): loads are issued one atom ahead of their use -------------------
+struct RawAtom {
+    float4 v[2];   // x / agg / dy for the thread's two rows
+    float4 z[2];   // z (backward with a normalisation)
+};
+
+template <int MODE>
+__device__ __forceinline__ void load_raw(const TcArgs& p, int64_t tile0, int a, int warp, int lane, RawAtom& r) {
+    const int c = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int64_t t = tile0 + warp * 8 + (lane >> 3) + it * 4;
+        r.v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.z[it] = r.v[it];
+        if (t >= p.n_tgt) continue;
+        if (MODE == MODE_BWD) {
+            const int f = a * ATOM_K + c;
+            if (f < p.f_out) {
+                r.v[it] = ldg4(p.dy + (size_t)t * p.f_out + f);
+                if (p.ng != nullptr) r.z[it] = ldg4(p.z + (size_t)t * p.f_out + f);
+            }
+        } else {
+            const bool raw_agg = a < p.ka_agg;
+            const int f = (raw_agg ? a : a - p.ka_agg) * ATOM_K + c;
+            if (f < p.f_in) r.v[it] = ldg4((raw_agg ? p.agg_in : p.x_in) + (size_t)t * p.f_in + f);
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void store_raw(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int a, int warp,
+                                          int lane, const RawAtom& r, float* red_db) {
+    const int c = (lane & 7) * 4;
+    if (MODE == MODE_BWD) {
+        const int f = a * ATOM_K + c;
+        const bool norm = p.ng != nullptr && f < p.f_out;
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f), aa = make_float4(0.f, 0.f, 0.f, 0.f), b = aa, m = aa, rs = g;
+        if (norm) { g = ldg4(p.ng + f); aa = ldg4(p.na + f); b = ldg4(p.nb + f); m = ldg4(p.nmean + f); rs = ldg4(p.nrstd + f); }
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int row = warp * 8 + (lane >> 3) + it * 4;
+            const int64_t t = tile0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < p.n_tgt && f < p.f_out) {
+                const float4 d = r.v[it], zv = r.z[it];
+                if (norm) {
+                    v.x = g.x * d.x - (aa.x + (zv.x - m.x) * rs.x * b.x);
+                    v.y = g.y * d.y - (aa.y + (zv.y - m.y) * rs.y * b.y);
+                    v.z = g.z * d.z - (aa.z + (zv.z - m.z) * rs.z * b.z);
+                    v.w = g.w * d.w - (aa.w + (zv.w - m.w) * rs.w * b.w);
+                } else {
+                    v = d;
+                }
+                cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+            }
+            store_split4(a_hi, a_lo, row, c, v);
+        }
+        if (red_db != nullptr) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+            if (lane < 8 && f < p.f_out) {
+                atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
+                atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
+            }
+        }
+    } else {
+        const bool raw_agg = a < p.ka_agg;
+        const int f = (raw_agg ? a : a - p.ka_agg) * ATOM_K + c;
+        const bool relu = p.relu_in != 0 && !raw_agg;
+        const bool affine = p.in_scale != nullptr && !raw_agg && f < p.f_in;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (affine) { sc = ldg4(p.in_scale + f); sh = ldg4(p.in_shift + f); }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int row = warp * 8 + (lane >> 3) + it * 4;
+            const int64_t t = tile0 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < p.n_tgt && f < p.f_in) {
+                v = r.v[it];
+                if (affine) {
+                    v.x = act(v.x, sc.x, sh.x, relu); v.y = act(v.y, sc.y, sh.y, relu);
+                    v.z = act(v.z, sc.z, sh.z, relu); v.w = act(v.w, sc.w, sh.w, relu);
+                } else if (relu) {
+                    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+            }
+            store_split4(a_hi, a_lo, row, c, v);
+        }
+    }
+}
+
 // warp `w` fills its 8 rows of the atom with agg[row, f0 .. f0+32): 16 lanes per cell, 2 features per
 // lane; the 4 passes are software-pipelined (indices for all passes up front, neighbour rows one pass ahead)
 template <int FE>
@@ -421,6 +515,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
         double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};
         uint32_t it = 0, tile_cnt = 0;
         int64_t prev_tile0 = -1;
+        RawAtom cur, nxt;
+        if (MODE != MODE_FWD_GATHER && (int64_t)blockIdx.x < n_tiles) load_raw<MODE>(p, (int64_t)blockIdx.x * TC_M, 0, warp, lane, cur);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
             const int64_t tile0 = tile * TC_M;
             for (int a = 0; a < p.ka; ++a, ++it) {
@@ -428,15 +524,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                 const uint32_t use = it / (uint32_t)p.stages;
                 uint8_t* a_hi = smem + (size_t)s * stage_bytes;
                 uint8_t* a_lo = a_hi + A_ATOM_BYTES;
+                if (MODE != MODE_FWD_GATHER) {
+                    // loads of the next atom (possibly of the next tile) go in flight before this one is processed
+                    const bool last = a + 1 == p.ka;
+                    const int64_t ntile = last ? tile + gridDim.x : tile;
+                    if (ntile < n_tiles) load_raw<MODE>(p, ntile * TC_M, last ? 0 : a + 1, warp, lane, nxt);
+                }
                 mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-                if (MODE == MODE_FWD_DENSE) {
-                    if (a < p.ka_agg) produce_rows(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane, true);
-                    else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
-                } else if (MODE == MODE_FWD_GATHER) {
+                if (MODE == MODE_FWD_GATHER) {
                     if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
                     else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
                 } else {
-                    produce_dz(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane, p.db_partials ? red_db : nullptr);
+                    store_raw<MODE>(p, a_hi, a_lo, tile0, a, warp, lane, cur, (MODE == MODE_BWD && p.db_partials) ? red_db : nullptr);
+                    cur = nxt;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();

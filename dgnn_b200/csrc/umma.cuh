@@ -46,22 +46,28 @@ __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 // Bounded wait: a pipeline bug must trap (surfacing as a CUDA error) instead of hanging the GPU.
+// A failed probe backs off with nanosleep so that waiting warps do not steal issue slots from working ones.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
+    if (mbar_try(addr, parity)) return;
+    uint32_t spins = 0;
     for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        __nanosleep(32);
+        if (mbar_try(addr, parity)) return;
+        if (++spins > (1u << 26)) __trap();
     }
 }
 
