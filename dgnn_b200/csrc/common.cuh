@@ -42,6 +42,13 @@ __device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
                  : "l"(p));
 }
 
+// 256-bit store (STG.E.256, sm_100+); p must be 32-byte aligned
+__device__ __forceinline__ void stg8(float* p, const float4& a, const float4& b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));

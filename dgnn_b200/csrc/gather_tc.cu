@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(ea_base + (size_t)s * 2 * G_ATOM), al = ah + G_ATOM;
                     const uint32_t d = tmem_base + (uint32_t)(k * FP);
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
+                    const int ksteps = (p.fe + 1 + 7) >> 3;     // fe features + bias column, 8 per k-step (3 for fe = 20)
+                    for (int kk = 0; kk < ksteps; ++kk) {
                         const uint32_t ko = kk * 32;
                         mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
                         mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;                      // first feature of this thread's strip
-        const bool relu = p.relu != 0;
+        const bool relu = (p.relu & 1) != 0;
+        const bool x_skip = (p.relu & 2) != 0, t_skip = (p.relu & 4) != 0, s_skip = (p.relu & 8) != 0;  // dev experiments
         const bool affine = p.scale != nullptr;
         const bool al8 = (p.f & 7) == 0;
         const int fe4 = p.fe >> 2;
@@ -188,22 +189,39 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         // stage EA_0..3 of a tile (rows of the tile, fe floats each, split hi / lo); the MMA warp follows
         auto stage_ea = [&](int64_t tile_s) {
             const int64_t base = tile_s * G_M;
+            // all loads of the four slots first (<= 2 float4 per thread and slot for fe <= 28) ...
+            float4 v[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int idx = tid + u * G_NCW * 32;
+                    v[k][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < G_M * fe4) {
+                        const int r = idx / fe4, c = idx - r * fe4;
+                        const int64_t tr = base + r;
+                        if (tr < p.n_rows) v[k][u] = ldg4(p.ea + ((size_t)tr * 4 + k) * p.fe + c * 4);
+                    }
+                }
+            // ... then per slot: wait for its stage, split hi / lo, store, arrive (the MMA warp follows)
+#pragma unroll
             for (int k = 0; k < 4; ++k, ++it) {
                 const uint32_t s = it % G_EA_STAGES, su = it / G_EA_STAGES;
                 uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
                 uint8_t* e_lo = e_hi + G_ATOM;
                 mbar_wait(&ea_empty[s], (su & 1) ^ 1);
-                for (int idx = tid; idx < G_M * fe4; idx += G_NCW * 32) {
-                    const int r = idx / fe4, c = idx - r * fe4;
-                    const int64_t tr = base + r;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (tr < p.n_rows) v = ldg4(p.ea + ((size_t)tr * 4 + k) * p.fe + c * 4);
-                    float4 h, l;
-                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                    const uint32_t off = atom_off(r, c * 4);
-                    *reinterpret_cast<float4*>(e_hi + off) = h;
-                    *reinterpret_cast<float4*>(e_lo + off) = l;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int idx = tid + u * G_NCW * 32;
+                    if (idx < G_M * fe4) {
+                        const int r = idx / fe4, c = idx - r * fe4;
+                        float4 h, l;
+                        split_tf32(v[k][u].x, h.x, l.x); split_tf32(v[k][u].y, h.y, l.y);
+                        split_tf32(v[k][u].z, h.z, l.z); split_tf32(v[k][u].w, h.w, l.w);
+                        const uint32_t off = atom_off(r, c * 4);
+                        *reinterpret_cast<float4*>(e_hi + off) = h;
+                        *reinterpret_cast<float4*>(e_lo + off) = l;
+                    }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -232,13 +250,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 const bool fvalid = f0 < p.f, fvalid_b = f0 + 4 < p.f;   // the two 4-feature halves of the strip step
                 uint32_t ph[4][8];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tmem_ld8(trow + (uint32_t)(k * FP + j), ph[k]);
+                for (int k = 0; k < 4; ++k) {
+                    if (!t_skip) tmem_ld8(trow + (uint32_t)(k * FP + j), ph[k]);
+                    else { for (int i = 0; i < 8; ++i) ph[k][i] = 0x3f800000u; }
+                }
                 float4 xa[4], xb[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                     xb[k] = xa[k];
-                    if (al8) {   // rows are 32-byte aligned: one 256-bit request instead of two 128-bit ones
+                    if (x_skip) {
+                        xa[k] = make_float4(1.f, 1.f, 1.f, 1.f); xb[k] = xa[k];
+                    } else if (al8) {   // rows are 32-byte aligned: one 256-bit request instead of two 128-bit ones
                         if (nbv[k] >= 0 && fvalid) ldg8(p.x + (size_t)nbv[k] * p.f + f0, xa[k], xb[k]);
                     } else {
                         if (nbv[k] >= 0 && fvalid) xa[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0);
@@ -264,12 +287,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                     acc[7] = fmaf(xb[k].w, __uint_as_float(ph[k][7]), acc[7]);
                 }
                 if (MODE == 0) {
-                    if (tv && fvalid)
-                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) =
-                            make_float4(acc[0] / dcnt, acc[1] / dcnt, acc[2] / dcnt, acc[3] / dcnt);
-                    if (tv && fvalid_b)
-                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) =
-                            make_float4(acc[4] / dcnt, acc[5] / dcnt, acc[6] / dcnt, acc[7] / dcnt);
+                    if (tv && fvalid && !s_skip) {
+                        const float4 oa = make_float4(acc[0] / dcnt, acc[1] / dcnt, acc[2] / dcnt, acc[3] / dcnt);
+                        const float4 ob = make_float4(acc[4] / dcnt, acc[5] / dcnt, acc[6] / dcnt, acc[7] / dcnt);
+                        if (al8) {
+                            stg8(p.out + (size_t)t * p.f + f0, oa, ob);      // one full 32-byte sector per thread
+                        } else {
+                            *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = oa;
+                            if (fvalid_b) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = ob;
+                        }
+                    }
                 } else {
                     float dx[8];
 #pragma unroll
@@ -312,9 +339,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                             }
                         }
                         if (p.out != nullptr) {
-                            *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                            if (fvalid_b)
-                                *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                            if (al8) {
+                                stg8(p.out + (size_t)t * p.f + f0, make_float4(acc[0], acc[1], acc[2], acc[3]),
+                                     make_float4(acc[4], acc[5], acc[6], acc[7]));
+                            } else {
+                                *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                                if (fvalid_b)
+                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                            }
                         }
                     }
                     if (p.s_partials != nullptr) {

@@ -399,6 +399,8 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                 v[i] += bi.x; v[i + 1] += bi.y; v[i + 2] += bi.z; v[i + 3] += bi.w;
             }
             if (tv) {
+                const bool al8 = (p.f_out & 7) == 0;
+                float4 held = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const int n = c0 + i;
@@ -412,7 +414,9 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                     if (p.relu_out) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
-                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f_out + n) = o;
+                    if (!al8) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f_out + n) = o;
+                    else if ((i & 4) == 0) held = o;                      // pair two float4 into one 32-byte store
+                    else stg8(p.out + (size_t)t * p.f_out + n - 4, held, o);
                 }
             }
             if (want_stats) {
