@@ -391,6 +391,22 @@ def main():
     prof.uninstall()
     roofline, table, kernel_ms = prof.summary(n_prof, peak, peak_src)
 
+    # secondary: eval-mode whole-batch inference (configs[0]/[2] shape of work), device resident
+    net.eval()
+    dall = to_attr({k: v for k, v in dres.items() if k != "n"})
+    with torch.no_grad():
+        for _ in range(3):
+            net.inference_layer(dall)
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(10):
+            net.inference_layer(dall)
+        i1.record()
+        torch.cuda.synchronize()
+    infer_ms = i0.elapsed_time(i1) / 10
+    net.train()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -415,6 +431,9 @@ def main():
            "roofline": roofline,
            "step_hbm_frac": round(n_cells * step_bytes_per_cell / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
            "kernel_ms_per_step": round(kernel_ms, 3),
+           "inference": {"cells_per_s_per_gpu": n_cells / (infer_ms * 1e-3), "ms": round(infer_ms, 3),
+                         "hbm_frac": round(n_cells * 4024 / (infer_ms * 1e-3) / 1e9 / peak, 4),
+                         "note": "eval-mode inference_layer on the same batch, device resident, 4 024 B/cell"},
            "kernels": table,
            "cpu_baseline": cpu}
     print(json.dumps(out))

@@ -11,8 +11,8 @@
 //     normalisation backward to dy (backward) — splits it into TF32 hi/lo parts and stores it
 //     straight into the 128B-swizzled UMMA layout of a ring stage, then arrives on the stage's
 //     `full` mbarrier.  Fast warps run ahead by the ring depth.
-//   * 1 MMA warp: for every stage it bulk-copies (TMA, cp.async.bulk) that atom's pre-packed
-//     weight slice next to the A slice, waits for `full`, issues the 12 tcgen05.mma of the stage
+//   * 1 TMA warp bulk-copies (cp.async.bulk) every atom's pre-packed weight slice next to the A slice,
+//     running a ring ahead; 1 MMA warp waits for `full`, issues the 12 tcgen05.mma of the stage
 //     (3xTF32: hi*hi + lo*hi + hi*lo, 4 k-steps) accumulating in TMEM, and tcgen05.commit's the
 //     stage's `empty` mbarrier.
 //   * accumulators are double-buffered in TMEM (2 x N columns): the producer warps run the
@@ -27,7 +27,7 @@ using namespace umma;
 
 constexpr int TC_M = 128;
 constexpr int NPW = 16;                        // producer warps
-constexpr int TC_THREADS = (NPW + 1) * 32;     // + 1 MMA / TMA warp
+constexpr int TC_THREADS = (NPW + 2) * 32;     // + 1 MMA warp + 1 TMA (weight slice) warp
 constexpr int A_ATOM_BYTES = TC_M * ATOM_ROW_BYTES;  // 16 KB
 constexpr int MAX_STAGES = 4;
 
@@ -492,11 +492,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                 if (lane == 0) {
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     uint8_t* b_hi = st + 2 * A_ATOM_BYTES;
-                    mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[s], 2u * (uint32_t)b_atom_bytes);
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.b_packed) + (size_t)a * 2 * b_atom_bytes;
-                    bulk_g2s(b_hi, src, (uint32_t)b_atom_bytes, &bar_full[s]);
-                    bulk_g2s(b_hi + b_atom_bytes, src + b_atom_bytes, (uint32_t)b_atom_bytes, &bar_full[s]);
                     if (a == 0 && tile_cnt >= 2) mbar_wait(&bar_acc_free[acc], ((tile_cnt >> 1) - 1) & 1);
                     mbar_wait(&bar_full[s], use & 1);
                     tc_fence_after_sync();
@@ -510,6 +505,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                     }
                     mma_commit(&bar_empty[s]);
                     if (a == p.ka - 1) mma_commit(&bar_acc_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == NPW + 1) {
+        // ------------------------------------------------------------------ TMA warp: weight slices, a ring ahead
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int a = 0; a < p.ka; ++a, ++it) {
+                if (lane == 0) {
+                    const uint32_t s = it % (uint32_t)p.stages;
+                    const uint32_t use = it / (uint32_t)p.stages;
+                    uint8_t* b_hi = smem + (size_t)s * stage_bytes + 2 * A_ATOM_BYTES;
+                    mbar_wait(&bar_empty[s], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[s], 2u * (uint32_t)b_atom_bytes);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.b_packed) + (size_t)a * 2 * b_atom_bytes;
+                    bulk_g2s(b_hi, src, (uint32_t)b_atom_bytes, &bar_full[s]);
+                    bulk_g2s(b_hi + b_atom_bytes, src + b_atom_bytes, (uint32_t)b_atom_bytes, &bar_full[s]);
                 }
                 __syncwarp();
             }
@@ -634,10 +647,11 @@ extern "C" int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len,
     return check_launch("dgnn_pack_b_tf32");
 }
 
-// ring depth: as deep as fits ~130 KB so that >= 90 KB of the SM's 228 KB stay L1 for the gather
-static int tc_stage_config(int np, int* stages, size_t* smem) {
+// ring depth: the gather mode keeps >= 90 KB of the SM's 228 KB as L1 for the neighbour rows; the streaming
+// (dense / backward) modes use all the shared memory they can get for a deeper ring
+static int tc_stage_config(int np, bool gather, int* stages, size_t* smem) {
     int stage_bytes = 2 * A_ATOM_BYTES + 2 * np * ATOM_ROW_BYTES;
-    int s = (132 * 1024) / stage_bytes;
+    int s = ((gather ? 132 : 200) * 1024) / stage_bytes;
     if (s > MAX_STAGES) s = MAX_STAGES;
     if (s < 2) s = 2;
     if ((size_t)s * stage_bytes + 1024 > 200 * 1024) return 1;
@@ -689,7 +703,7 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.agg_save = agg_save; p.stats = stats;
     size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    DGNN_REQUIRE(tc_stage_config(p.np, nbr != nullptr, &p.stages, &smem) == 0, "tile does not fit shared memory");
     cudaStream_t st = as_stream(stream);
     if (nbr == nullptr) return launch_tc<MODE_FWD_DENSE, 0>(p, smem, st, "dgnn_layer_fwd_tc");
     switch (fe) {
@@ -726,7 +740,7 @@ extern "C" int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const floa
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.stats = stats;
     size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem) == 0, "tile does not fit shared memory");
     return launch_tc<MODE_FWD_DENSE, 0>(p, smem, as_stream(stream), "dgnn_dense_fwd_tc");
 }
 
@@ -748,6 +762,6 @@ extern "C" int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g
     p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
     p.d_agg = d_agg; p.d_self = d_self; p.db_partials = db_partials;
     size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem) == 0, "tile does not fit shared memory");
     return launch_tc<MODE_BWD, 0>(p, smem, as_stream(stream), "dgnn_dense_bwd_tc");
 }

@@ -65,9 +65,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try(addr, parity)) return;
     uint32_t spins = 0;
     for (;;) {
-        __nanosleep(32);
+#ifdef DGNN_MBAR_BACKOFF
+        __nanosleep(DGNN_MBAR_BACKOFF);
+#endif
         if (mbar_try(addr, parity)) return;
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > (1u << 28)) __trap();
     }
 }
 
