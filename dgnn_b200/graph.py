@@ -57,6 +57,7 @@ class EllGraph:
     perm: Optional[torch.Tensor] = None      # int32[n]: new -> old  (None = caller order)
     inv: Optional[torch.Tensor] = None       # int32[n]: old -> new
     _eid_in: Optional[torch.Tensor] = None   # int32[n_tgt,4]: local edge id of every (target, slot), -1 = none
+    _eid_out: Optional[torch.Tensor] = None  # int32[n_src,4]: local edge id of every (source, out-slot), -1 = none
 
     def permute_rows(self, x: torch.Tensor) -> torch.Tensor:
         """Rows of ``x`` (caller order, width multiple of 4) in internal order."""
@@ -202,4 +203,5 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
         if need_backward:
             ea_own = torch.empty((n_src, 4, fe), dtype=torch.float32, device=dev)
             call("dgnn_gather_rows", ptr(ea), ptr(eid_out), n_src * 4, fe, ptr(ea_own), st)
-    return EllGraph(n_src=n_src, n_tgt=n_tgt, fe=fe, nbr=nbr, ea_in=ea_in, onbr=onbr, ea_own=ea_own, _eid_in=eid_in)
+    return EllGraph(n_src=n_src, n_tgt=n_tgt, fe=fe, nbr=nbr, ea_in=ea_in, onbr=onbr, ea_own=ea_own, _eid_in=eid_in,
+                    _eid_out=eid_out)

@@ -6,11 +6,14 @@ Same constructor (``SurfaceNet(n_node_features, clf)``, ``Updated:191-210``), mo
 ``forward(data_all)`` contract (``Updated:216-251``).  The reference's three inference methods call
 the conv without ``edge_attr`` and raise; they are not provided.
 
-Round-1 status: forward only (inference / evaluation of a trained model); per layer
-  e'  = lin_e(relu?(e_prev[e_id, :edge_in]))      dgnn_layer_fwd, dense mode over the edge rows
-  agg = mean_k relu?(x_src) (*) e'                 dgnn_gather_phi_fwd (edge state materialised, as the reference does)
+Per layer (edge state materialised as ``[E, F_in]``, as the reference does, ``Updated:236``):
+  e'  = lin_e(relu?(e_prev[e_id, :edge_in]))      dgnn_dense_fwd_tc / dgnn_layer_fwd over the edge rows
+  agg = mean_k relu?(x_src) (*) e'                 dgnn_gather_phi_fwd
   out = lin_l(agg) + lin_r(x_tgt)                  dgnn_dense_fwd_tc / dgnn_layer_fwd
-Calling ``backward`` through it raises (no CUDA backward for this variant yet).
+Backward (autograd Function ``_UpdFn``): dgnn_dense_bwd[_tc] + dgnn_dw_bwd[_tc] for the three linears,
+dgnn_upd_edge_bwd (d e', including the gradient that returns through the next layer's edge state) and
+dgnn_gather_phi_bwd (d x through the out-edge table, atomic-free).  The reference's own "sage+" head cannot
+run backward (in-place ReLU on a saved tensor, ``Updated:245-247``); here it can, pinned against the oracle.
 """
 from __future__ import annotations
 
@@ -78,7 +81,17 @@ class SurfaceNet(nn.Module):
         if clf.training.model_name[-1] == "+":
             self.out_net = nn.Sequential(nn.ReLU(True), nn.Linear(p[-1], 128), nn.ReLU(True), nn.Linear(128, 2))
 
-    @torch.no_grad()
+    def _params(self):
+        ps = []
+        for c in self.convs:
+            ps += [c.lin_l.weight, c.lin_l.bias, c.lin_r.weight, c.lin_e.weight, c.lin_e.bias]
+        if self._has_head():
+            ps += [self.out_net[1].weight, self.out_net[1].bias, self.out_net[3].weight, self.out_net[3].bias]
+        return ps
+
+    def _has_head(self):
+        return self.clf.training.model_name[-1] == "+"
+
     def forward(self, data_all):
         dev = torch.device(self.clf.temp.device)
         if dev.type != "cuda":
@@ -86,50 +99,150 @@ class SurfaceNet(nn.Module):
         check_device(dev.index or 0)
         if any(c.normalize for c in self.convs):
             raise NotImplementedError("normalize=True is never set by the reference model")
+        for c in self.convs:
+            if c.out_channels % 4:
+                raise NotImplementedError("hidden widths must be multiples of 4")
+        params = self._params()
+        if any(p.device != dev for p in params):
+            raise DgnnError("model parameters are not on clf.temp.device; call model.to(device) first")
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         with torch.cuda.device(dev):
-            f = self.clf.features
-            cols = slice(1, None) if (f.normalization_feature and not f.keep_normalization_feature) else slice(None)
-            n_id = data_all.n_id
-            x = data_all.x[n_id.to(data_all.x.device)][:, cols].to(dev, dtype=torch.float32)
-            x = pad_cols(x, pad4(x.shape[1]))
-            e_all = data_all.edge_attr.shape[0]
-            e_state = pad_cols(data_all.edge_attr[:, :2].to(dev, dtype=torch.float32), 4)   # layer 0 reads 2 columns
-            relu_in = False
-            for i, conv in enumerate(self.convs):
-                edge_index, e_id, size = data_all.adjs[i]
-                g = build_from_edges(edge_index, None, None, size[0], size[1], dev, need_backward=False)
-                n_tgt = size[1]
-                fi, fo = pad4(conv.in_channels), conv.out_channels
-                if fo % 4:
-                    raise NotImplementedError("hidden widths must be multiples of 4")
-                k_in = e_state.shape[1]
-                # rows of the edge state for every (target, slot): global edge id = e_id[local edge id]
-                eid_glob = torch.where(g_eid(g) >= 0, e_id.to(dev)[g_eid(g).clamp(min=0).long()].to(torch.int32),
-                                       torch.full_like(g_eid(g), -1))
-                ea = torch.empty((n_tgt * 4, k_in), dtype=torch.float32, device=dev)
-                call("dgnn_gather_rows", ptr(e_state), ptr(eid_glob), n_tgt * 4, k_in, ptr(ea), _stream())
-                w_e = engine._pad2(conv.lin_e.weight.detach(), fi, k_in).contiguous()
-                b_e = engine._pad1(conv.lin_e.bias.detach(), fi).contiguous()
-                e_new = _dense(ea, relu_in, w_e, b_e, n_tgt * 4, k_in, fi)            # pre-ReLU e' (Updated:157)
-                agg = torch.empty((n_tgt, fi), dtype=torch.float32, device=dev)
-                call("dgnn_gather_phi_fwd", ptr(x), None, None, int(relu_in), ptr(g.nbr), ptr(e_new), n_tgt, fi, ptr(agg),
-                     _stream())
-                w_cat = torch.cat([engine._pad2(conv.lin_l.weight.detach(), fo, fi),
-                                   engine._pad2(conv.lin_r.weight.detach(), fo, fi)], dim=1).contiguous()
-                x = _dense(x, relu_in, w_cat, conv.lin_l.bias.detach().contiguous(), n_tgt, fi, fo, agg=agg)
-                # new edge state, indexed by global edge id; edges outside this hop stay 0 (Updated:236-238)
-                e_state = torch.zeros((e_all, fi), dtype=torch.float32, device=dev)
-                call("dgnn_scatter_rows", ptr(e_new), ptr(eid_glob), n_tgt * 4, fi, ptr(e_state), _stream())
-                relu_in = True                                                        # x, e <- relu (applied on load)
-            if self.clf.training.model_name[-1] == "+":
-                n = x.shape[0]
-                h = _dense(x, True, self.out_net[1].weight.detach(), self.out_net[1].bias.detach().contiguous(), n,
-                           x.shape[1], 128)
-                out = torch.empty((n, 2), dtype=torch.float32, device=dev)
-                call("dgnn_rowdot_fwd", ptr(h), None, None, 1, ptr(self.out_net[3].weight.detach().contiguous()),
-                     ptr(self.out_net[3].bias.detach().contiguous()), n, 128, 2, ptr(out), _stream())
-                return out
-            return x
+            if not need_grad:
+                return _forward(self, data_all, dev, None)
+            return _UpdFn.apply(self, data_all, dev, *params)
+
+
+class _Saved:
+    pass
+
+
+def _forward(net, data_all, dev, sv):
+    """Forward on the device; ``sv`` (a list) receives what the backward needs, one entry per layer."""
+    f = net.clf.features
+    cols = slice(1, None) if (f.normalization_feature and not f.keep_normalization_feature) else slice(None)
+    n_id = data_all.n_id
+    x = data_all.x[n_id.to(data_all.x.device)][:, cols].to(dev, dtype=torch.float32)
+    x = pad_cols(x, pad4(x.shape[1]))
+    e_all = data_all.edge_attr.shape[0]
+    e_state = pad_cols(data_all.edge_attr[:, :2].to(dev, dtype=torch.float32), 4)   # layer 0 reads 2 columns
+    relu_in = False
+    for i, conv in enumerate(net.convs):
+        edge_index, e_id, size = data_all.adjs[i]
+        g = build_from_edges(edge_index, None, None, size[0], size[1], dev, need_backward=sv is not None)
+        n_tgt = size[1]
+        fi, fo = pad4(conv.in_channels), conv.out_channels
+        k_in = e_state.shape[1]
+        # rows of the edge state for every (target, slot): global edge id = e_id[local edge id]
+        eid_loc = g._eid_in
+        eid_glob = torch.where(eid_loc >= 0, e_id.to(dev)[eid_loc.clamp(min=0).long()].to(torch.int32),
+                               torch.full_like(eid_loc, -1))
+        ea = torch.empty((n_tgt * 4, k_in), dtype=torch.float32, device=dev)
+        call("dgnn_gather_rows", ptr(e_state), ptr(eid_glob), n_tgt * 4, k_in, ptr(ea), _stream())
+        w_e = engine._pad2(conv.lin_e.weight.detach(), fi, k_in).contiguous()
+        b_e = engine._pad1(conv.lin_e.bias.detach(), fi).contiguous()
+        e_new = _dense(ea, relu_in, w_e, b_e, n_tgt * 4, k_in, fi)            # pre-ReLU e' (Updated:157)
+        agg = torch.empty((n_tgt, fi), dtype=torch.float32, device=dev)
+        call("dgnn_gather_phi_fwd", ptr(x), None, None, int(relu_in), ptr(g.nbr), ptr(e_new), n_tgt, fi, ptr(agg),
+             _stream())
+        w_cat = torch.cat([engine._pad2(conv.lin_l.weight.detach(), fo, fi),
+                           engine._pad2(conv.lin_r.weight.detach(), fo, fi)], dim=1).contiguous()
+        out = _dense(x, relu_in, w_cat, conv.lin_l.bias.detach().contiguous(), n_tgt, fi, fo, agg=agg)
+        if sv is not None:
+            s = _Saved()
+            s.g, s.eid_glob, s.ea, s.phi, s.agg, s.x_in, s.out = g, eid_glob, ea, e_new, agg, x, out
+            s.relu_in, s.w_e, s.w_cat, s.fi, s.fo, s.k_in, s.e_all = relu_in, w_e, w_cat, fi, fo, k_in, e_all
+            # row 4t+k of e' for every out-edge (s,j): invert the (target,slot) -> local edge id table
+            row_of_edge = torch.full((edge_index.shape[1],), -1, dtype=torch.int32, device=dev)
+            flat = eid_loc.reshape(-1)
+            ok = flat >= 0
+            row_of_edge[flat[ok].long()] = torch.arange(flat.numel(), dtype=torch.int32, device=dev)[ok]
+            eo = g._eid_out
+            s.orow = torch.where(eo >= 0, row_of_edge[eo.clamp(min=0).long()], torch.full_like(eo, -1)).contiguous()
+            sv.append(s)
+        x = out
+        # new edge state, indexed by global edge id; edges outside this hop stay 0 (Updated:236-238)
+        e_state = torch.zeros((e_all, fi), dtype=torch.float32, device=dev)
+        call("dgnn_scatter_rows", ptr(e_new), ptr(eid_glob), n_tgt * 4, fi, ptr(e_state), _stream())
+        relu_in = True                                                        # x, e <- relu (applied on load)
+    if net._has_head():
+        n = x.shape[0]
+        w1 = net.out_net[1].weight.detach().contiguous()
+        h = _dense(x, True, w1, net.out_net[1].bias.detach().contiguous(), n, x.shape[1], 128)
+        logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        call("dgnn_rowdot_fwd", ptr(h), None, None, 1, ptr(net.out_net[3].weight.detach().contiguous()),
+             ptr(net.out_net[3].bias.detach().contiguous()), n, 128, 2, ptr(logits), _stream())
+        if sv is not None:
+            s = _Saved()
+            s.x_in, s.h, s.w1 = x, h, w1
+            sv.append(s)
+        return logits
+    return x
+
+
+_NOAFF = engine.Affine(None, None, None, None)
+_NOCOEF = (None, None, None)
+
+
+class _UpdFn(torch.autograd.Function):
+    """Autograd bridge: parameters enter as inputs so that ``loss.backward()`` fills their ``.grad``."""
+
+    @staticmethod
+    def forward(ctx, net, data_all, dev, *params):
+        sv = []
+        out = _forward(net, data_all, dev, sv)
+        ctx.net, ctx.sv, ctx.dev = net, sv, dev
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net, sv, dev = ctx.net, ctx.sv, ctx.dev
+        st = _stream()
+        grads = []
+        with torch.cuda.device(dev):
+            d_out = dout.contiguous().float()
+            head_grads = []
+            if net._has_head():
+                s = sv[-1]
+                n, f = s.x_in.shape
+                w3 = net.out_net[3].weight.detach().contiguous()
+                dy = torch.empty((n, 128), dtype=torch.float32, device=dev)
+                part = torch.empty((lib().dgnn_small_grid(), 2 * 128 + 2 + 2 * 128), dtype=torch.float64, device=dev)
+                call("dgnn_rowdot_bwd", ptr(d_out), ptr(s.h), None, None, None, None, 1, ptr(w3), n, 128, 2, ptr(dy),
+                     ptr(part), st)
+                r = engine._reduce(part)
+                dw3, db3 = r[:256].view(2, 128), r[256:258]
+                _, d_relu_x, db1, dw1 = engine._dense_and_dw(dy, s.h, _NOCOEF, _NOAFF, s.w1, None, None, s.x_in, None,
+                                                             True, n, f, 128)
+                d_out = torch.empty_like(d_relu_x)
+                call("dgnn_relu_mask", ptr(d_relu_x), ptr(s.x_in), d_relu_x.numel(), ptr(d_out), st)
+                head_grads = [dw1, db1, dw3, db3]
+            de_next = None
+            layer_grads = []
+            for i in range(len(net.convs) - 1, -1, -1):
+                s, conv = sv[i], net.convs[i]
+                g, n_tgt, n_src, fi, fo = s.g, s.g.n_tgt, s.g.n_src, s.fi, s.fo
+                d_agg, d_self, db_l, dw_cat = engine._dense_and_dw(d_out, s.out, _NOCOEF, _NOAFF, s.w_cat, g, s.agg,
+                                                                   s.x_in, None, s.relu_in, n_tgt, fi, fo)
+                dphi = torch.empty((n_tgt * 4, fi), dtype=torch.float32, device=dev)
+                call("dgnn_upd_edge_bwd", ptr(s.x_in), int(s.relu_in), ptr(g.nbr), ptr(d_agg), ptr(s.phi),
+                     ptr(de_next), ptr(s.eid_glob), n_tgt, fi, ptr(dphi), st)
+                _, d_ea, db_e, dw_e = engine._dense_and_dw(dphi, s.phi, _NOCOEF, _NOAFF, s.w_e, None, None, s.ea, None,
+                                                           s.relu_in, n_tgt * 4, s.k_in, fi)
+                ic, ec = conv.in_channels, conv.edge_in_channels
+                layer_grads.append([dw_cat[:, :ic].contiguous(), db_l, dw_cat[:, fi:fi + ic].contiguous(),
+                                    dw_e[:ic, :ec].contiguous(), db_e[:ic].contiguous()])
+                if i > 0:
+                    d_x = torch.empty((n_src, fi), dtype=torch.float32, device=dev)
+                    call("dgnn_gather_phi_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(s.orow), ptr(s.phi),
+                         ptr(s.x_in), int(s.relu_in), n_src, n_tgt, fi, ptr(d_x), st)
+                    d_out = d_x
+                    de_next = torch.zeros((s.e_all, s.k_in), dtype=torch.float32, device=dev)
+                    call("dgnn_scatter_rows", ptr(d_ea), ptr(s.eid_glob), n_tgt * 4, s.k_in, ptr(de_next), st)
+            for lg in reversed(layer_grads):
+                grads += lg
+            grads += head_grads
+        ctx.sv = None
+        return (None, None, None, *grads)
 
 
 def g_eid(g):

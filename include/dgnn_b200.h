@@ -159,6 +159,20 @@ int dgnn_debug_umma(const uint8_t* a_img, int a_bytes, const uint8_t* b_img, int
  * materialised edge state phi float32[n_tgt,4,f]:  agg[t] = mean_k h(x_in[nbr[t,k]]) (*) phi[t,k,:] */
 int dgnn_gather_phi_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
                         const int32_t* nbr, const float* phi, int64_t n_tgt, int f, float* agg, void* stream);
+/* Backward of that aggregation (autograd of Updated:157-176, :236-241 in the reference).
+ *   dphi[t,k,:] = h(x_in[nbr[t,k]]) (*) d_agg[t]  +  (phi[t,k,:] > 0) * de_next[eid[t,k],:]
+ * d_agg already divided by max(cnt,1) (dgnn_dense_bwd); de_next float32[E_all,f] indexed by the global
+ * edge id eid int32[n_tgt,4] = gradient arriving through relu(edge state) from the next layer (NULL: none). */
+int dgnn_upd_edge_bwd(const float* x_in, int relu_in, const int32_t* nbr, const float* d_agg,
+                      const float* phi, const float* de_next, const int32_t* eid, int64_t n_tgt, int f,
+                      float* dphi, void* stream);
+/*   dx[s] = relu'(x_in[s]) * ( d_self[s] (s < n_tgt) + sum_j phi[orow[s,j],:] (*) d_agg[onbr[s,j]] )
+ * onbr int32[n_src,4] = target of the j-th out-edge of s, orow = that edge's row 4t+k in phi (-1 = none). */
+int dgnn_gather_phi_bwd(const float* d_agg, const float* d_self, const int32_t* onbr, const int32_t* orow,
+                        const float* phi, const float* x_in, int relu_in, int64_t n_src, int64_t n_tgt,
+                        int f, float* dx, void* stream);
+/* dst = (z > 0) ? src : 0, elementwise over n_floats (multiple of 4); dst may alias src */
+int dgnn_relu_mask(const float* src, const float* z, int64_t n_floats, float* dst, void* stream);
 
 /* Reduce per-CTA (sum, sum^2) partials and produce the normalisation's per-channel affine.
  * mode 0 = BatchNorm1d training statistics (biased var for normalisation; running_mean /

@@ -217,5 +217,66 @@ def test_updated_edge_filters_forward_matches_reference_golden(golden):
                           strict=True)
         m.to(DEV)
         y = m(to_attr(dict(x=d.x, edge_attr=d.edge_attr, n_id=n_id, adjs=adjs)))
-        err, ok = logits_close(y.cpu().numpy(), golden[tag + "_logits"])
+        err, ok = logits_close(y.detach().cpu().numpy(), golden[tag + "_logits"])
         assert ok, (name, err)
+
+
+def _upd_clf(name, device, params=(16, 32, 32, 32)):
+    return to_attr(dict(training=dict(model_params=list(params), model_name=name),
+                        features=dict(normalization_feature=1, keep_normalization_feature=0),
+                        temp=dict(device=device)))
+
+
+def test_updated_edge_filters_gradients_match_reference_golden(golden):
+    """Row U, training: gradients of every parameter of the Updated-edge-filter model ("sage") against the
+    reference's own autograd on the sampled 4-hop closure of the golden graph (loss = sum(out^2))."""
+    from dgnn_b200.surfaceNetUpdatedEdgeFilters import SurfaceNet as UpdNet
+    d = golden_data(golden)
+    n_id = torch.from_numpy(golden["upd_n_id"])
+    _, _, adjs = next(iter(NeighborSampler(d.edge_index, [-1] * 4, 96, node_idx=torch.arange(40, 136),
+                                           num_nodes=d.x.shape[0])))
+    m = UpdNet(28, _upd_clf("sage", DEV))
+    m.load_state_dict({k[len("upd_init."):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith("upd_init.")},
+                      strict=True)
+    m.to(DEV)
+    y = m(to_attr(dict(x=d.x, edge_attr=d.edge_attr, n_id=n_id, adjs=adjs)))
+    assert y.requires_grad
+    y.square().sum().backward()
+    for k, p in m.named_parameters():
+        err, tol = grad_close(p.grad, torch.from_numpy(golden["upd_grad." + k]))
+        assert err <= tol, (k, err)
+
+
+@pytest.mark.parametrize("name", ["sage", "sage+"])
+def test_updated_edge_filters_full_graph_training_matches_oracle(name):
+    """Row U at cfg4 shape (whole graph as the batch, kf96-like widths): logits and every gradient against the
+    oracle; the "+" head, whose backward the reference itself cannot run, is pinned here."""
+    from dgnn_b200.surfaceNetUpdatedEdgeFilters import SurfaceNet as UpdNet
+    from oracle.updated_model import SurfaceNet as OracleUpd
+    gr = make_graph(700, seed=5)
+    d = data_all(gr)
+    n = d.x.shape[0]
+    e = d.edge_index.shape[1]
+    adjs = [(d.edge_index, torch.arange(e), (n, n))] * 4
+    batch = dict(x=d.x, edge_attr=d.edge_attr, n_id=torch.arange(n), adjs=adjs)
+    torch.manual_seed(3)
+    ref = OracleUpd(28, _upd_clf(name, "cpu", (64, 128, 128, 128)))
+    if name == "sage+":     # the in-place ReLUs of the head (Updated:210) break torch's own backward; same math
+        ref.out_net[0], ref.out_net[2] = torch.nn.ReLU(False), torch.nn.ReLU(False)
+    m = UpdNet(28, _upd_clf(name, DEV, (64, 128, 128, 128)))
+    m.load_state_dict(ref.state_dict(), strict=True)
+    m.to(DEV)
+    w = torch.linspace(0.5, 1.5, n)[:, None]
+    y_ref = ref(to_attr(batch))
+    (y_ref.square() * w).sum().backward()
+    y = m(to_attr(batch))
+    err, ok = logits_close(y.detach().cpu().numpy(), y_ref.detach().numpy())
+    assert ok, err
+    (y.square() * w.to(DEV)).sum().backward()
+    gref = dict(ref.named_parameters())
+    for k, p in m.named_parameters():
+        err, tol = grad_close(p.grad, gref[k].grad)
+        assert err <= tol, (name, k, err)
+    with torch.no_grad():
+        y2 = m(to_attr(batch))
+    assert torch.equal(y2, y.detach())
