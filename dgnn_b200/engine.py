@@ -209,10 +209,22 @@ def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_a
     return out, agg, stats
 
 
-def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: bool, save: bool, exchange=None):
+def _global_stats(stats, n_rows, comm):
+    """Batch statistics over all ranks of a partitioned scene: sum the per-CTA partials, all-reduce the
+    2 x C doubles, and count the rows of every rank."""
+    if comm is None:
+        return stats, n_rows
+    s = stats.sum(dim=0, keepdim=True).contiguous()
+    comm.allreduce(s)
+    return s, comm.n_rows
+
+
+def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: bool, save: bool, comm=None):
     """Run all conv layers + decoder.  ``x0``: float32[n_src0, pad4(F0)] in the graphs' row order.
-    ``exchange`` (eval only): callable filling the halo rows ``h[n_tgt:]`` of a layer's output in place
-    (partitioned scenes, ``dgnn_b200.partition``); outputs are then allocated with ``n_src`` rows.
+    ``comm`` (partitioned scenes, ``dgnn_b200.partition.HaloComm``): ``comm.exchange(h)`` fills the halo rows
+    ``h[n_tgt:]`` of a layer's output in place (outputs are then allocated with ``n_src`` rows),
+    ``comm.allreduce(t)`` sums a small tensor over the ranks (batch statistics), ``comm.n_rows`` = cells of
+    all ranks.
     Returns ``(logits, Saved or None)``.  In training mode the norms use batch statistics
     (and update the running buffers); in eval mode the running-statistic affine + ReLU is fused
     into each layer's epilogue."""
@@ -235,26 +247,30 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
         if c.norm is None:
             raise NotImplementedError("normalization must be 'b' or 'l' (the reference crashes otherwise, Static:218)")
         split = pk.b_fwd is not None and pk.fe > 0 and lib().dgnn_gather_tc_supported(pk.f_in, pk.fe)
+        out_rows = g.n_src if (comm is not None and l + 1 < L) else g.n_tgt
         if batch_stats:
             if split:
-                z, agg, stats = _gather_then_dense(h, in_aff, relu_in, g, pk, None, False, True)
+                z, agg, stats = _gather_then_dense(h, in_aff, relu_in, g, pk, None, False, True, out_rows=out_rows)
             else:
                 z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None,
-                                           False, g.n_tgt, pk.f_in, pk.f_out, save, True, b_packed=pk.b_fwd)
-            aff = batch_affine(c.norm, stats, g.n_tgt, pk.f_out, dev, update_running=training)
+                                           False, g.n_tgt, pk.f_in, pk.f_out, save, True, b_packed=pk.b_fwd,
+                                           out_rows=out_rows)
+            stats, n_rows = _global_stats(stats, g.n_tgt, comm)
+            aff = batch_affine(c.norm, stats, n_rows, pk.f_out, dev, update_running=training)
+            if comm is not None and l + 1 < L:
+                comm.exchange(z)                       # halo rows carry the owners' pre-norm z; the affine is global
             if save:
                 sv.z.append(z); sv.agg.append(agg); sv.aff.append(aff); sv.packed.append(pk)
             h, in_aff, relu_in = z, aff, True
         else:
             aff = eval_affine(c.norm, pk.f_out, dev)
-            out_rows = g.n_src if (exchange is not None and l + 1 < L) else g.n_tgt
             if split:
                 h, _, _ = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False, out_rows=out_rows)
             else:
                 h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
                                      g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd, out_rows=out_rows)
-            if exchange is not None and l + 1 < L:
-                exchange(h)
+            if comm is not None and l + 1 < L:
+                comm.exchange(h)
             in_aff, relu_in = None, False
     n_out = graphs[-1].n_tgt
     f_last = spec.convs[-1].f_out
@@ -282,7 +298,8 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
     if batch_stats:
         z_d, _, stats = _layer_fwd(h, in_aff, relu_in, None, wt, b0, None, None, 0, None, False, n_out, f_last, f_d,
                                    False, True, b_packed=bd)
-        aff_d = batch_affine(dn, stats, n_out, f_d, dev, update_running=training)
+        stats, n_rows = _global_stats(stats, n_out, comm)
+        aff_d = batch_affine(dn, stats, n_rows, f_d, dev, update_running=training)
         hd, hd_aff, hd_relu = z_d, aff_d, True
         if save:
             sv.z_d, sv.aff_d = z_d, aff_d
@@ -324,13 +341,15 @@ def _norm_coeffs(n: NormSpec, aff: Affine, s1, s2, n_rows, c):
     return buf[0], buf[1], buf[2]
 
 
-def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, in_aff, relu_in, n_tgt, f_in, f_out):
-    """dz . W (-> d_agg, d_self, db) and dz^T . [agg | h] (-> dW_cat)."""
+def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, in_aff, relu_in, n_tgt, f_in, f_out,
+                  agg_rows=None):
+    """dz . W (-> d_agg, d_self, db) and dz^T . [agg | h] (-> dW_cat).  ``agg_rows`` > n_tgt leaves room
+    behind d_agg for the halo rows of a partitioned scene."""
     dev = dy.device
     k_total = 2 * f_in if g is not None else f_in
     gq, aq, bq = coeffs
     d_self = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev)
-    d_agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if g is not None else None
+    d_agg = torch.empty((agg_rows or n_tgt, f_in), dtype=torch.float32, device=dev) if g is not None else None
     if use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 1 if g is not None else 0) and f_out <= 256:
         # operand B of the backward: [W_j | W_i]^T, i.e. rows = columns of d[agg|self], K = f_out
         b_bwd = pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
@@ -355,9 +374,21 @@ def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, i
     return d_agg, d_self, db, dw
 
 
-def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
+def _global_sums(s1, s2, comm):
+    """(S1, S2) of a norm backward over all ranks (the local ones stay the norm's own weight/bias gradient)."""
+    if comm is None:
+        return s1, s2
+    both = torch.cat([s1, s2])
+    comm.allreduce(both)
+    return both[:s1.numel()], both[s1.numel():]
+
+
+def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor, comm=None):
     """Gradients of every parameter given ``dout`` = dL/d(output of ``forward``).
-    Returns a dict name -> grad keyed like ``NetSpec`` fields (``convs.{l}.w_i`` ...)."""
+    Returns a dict name -> grad keyed like ``NetSpec`` fields (``convs.{l}.w_i`` ...).
+    With ``comm`` (partitioned scene) the returned gradients are this rank's share (sum them over ranks);
+    the norm statistics are all-reduced inside and d_agg crosses the partition boundary through the same
+    halo exchange as the forward activations."""
     dev = dout.device
     st = _stream()
     grads = {}
@@ -399,7 +430,8 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
         s1d, s2d = r[od * f_d + od:od * f_d + od + f_d], r[od * f_d + od + f_d:]
         grads["dec_norm_w"], grads["dec_norm_b"] = s2d, s1d
         _dbg("dy_d", dy_d)
-        coeffs = _norm_coeffs(spec.dec_norm, affd, s1d, s2d, n_out, f_d)
+        s1g, s2g = _global_sums(s1d, s2d, comm)
+        coeffs = _norm_coeffs(spec.dec_norm, affd, s1g, s2g, comm.n_rows if comm else n_out, f_d)
         _, dh, db0, dw0 = _dense_and_dw(dy_d, sv.z_d, coeffs, affd, spec.dec0_w.detach().contiguous(), None, None, zL,
                                         affL, True, n_out, f_last, f_d)
         grads["dec0_w"], grads["dec0_b"] = dw0, db0
@@ -415,12 +447,19 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
         c, pk, g, aff = spec.convs[l], sv.packed[l], sv.graphs[l], sv.aff[l]
         grads["convs.%d.norm_w" % l], grads["convs.%d.norm_b" % l] = s2, s1
         _dbg("dy_%d" % l, dy)
-        coeffs = _norm_coeffs(c.norm, aff, s1, s2, g.n_tgt, pk.f_out)
+        s1g, s2g = _global_sums(s1, s2, comm)
+        coeffs = _norm_coeffs(c.norm, aff, s1g, s2g, comm.n_rows if comm else g.n_tgt, pk.f_out)
         x_in = sv.z[l - 1] if l > 0 else sv.x0
         in_aff = sv.aff[l - 1] if l > 0 else None
         relu_in = l > 0
         d_agg, d_self, db, dw = _dense_and_dw(dy, sv.z[l], coeffs, aff, pk.w_cat, g, sv.agg[l], x_in, in_aff, relu_in,
-                                              g.n_tgt, pk.f_in, pk.f_out)
+                                              g.n_tgt, pk.f_in, pk.f_out, agg_rows=g.n_src if comm else None)
+        # sources whose gradient this rank produces: all of them, or (partitioned) the owned rows only, with the
+        # d_agg rows of halo targets fetched from their owners
+        n_srcs = g.n_src
+        if comm is not None:
+            comm.exchange(d_agg)
+            n_srcs = g.n_tgt
         grads["convs.%d.b_j" % l] = db
         _dbg("d_agg_%d" % l, d_agg); _dbg("d_self_%d" % l, d_self)
         grads["convs.%d.w_j" % l] = dw[:, :c.f_in]
@@ -431,12 +470,12 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
             # dh / dy_prev / (S1,S2) and dW_e / db_e with the edge filter on tensor cores
             tcg = lib().dgnn_tc_grid()
             part = torch.empty((tcg, 2 * pk.f_in), dtype=torch.float64, device=dev) if need_prev else None
-            dy_prev = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev) if need_prev else None
+            dy_prev = torch.empty((n_srcs, pk.f_in), dtype=torch.float32, device=dev) if need_prev else None
             dwe_p = torch.empty((tcg, pk.f_in, 32), dtype=torch.float32, device=dev)
             call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.ea_own), pk.fe, ptr(pk.w_e),
                  ptr(pk.b_e), ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
                  ptr(in_aff.mean) if in_aff else None, ptr(in_aff.rstd) if in_aff else None, int(relu_in),
-                 g.n_src, g.n_tgt, pk.f_in, ptr(dy_prev), ptr(part), ptr(dwe_p), st)
+                 n_srcs, g.n_tgt, pk.f_in, ptr(dy_prev), ptr(part), ptr(dwe_p), st)
             dwe = torch.empty((pk.f_in, 32), dtype=torch.float32, device=dev)
             call("dgnn_reduce_partials_f32", ptr(dwe_p), tcg, pk.f_in * 32, ptr(dwe), st)
             fe_u = c.w_e.shape[1]
@@ -450,11 +489,11 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor):
             grid = lib().dgnn_gather_bwd_grid(pk.f_in)
             plen = pk.f_in * (pk.fe + 1) + 2 * pk.f_in
             part = torch.empty((grid, plen), dtype=torch.float64, device=dev)
-            dy_prev = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev) if need_prev else None
+            dy_prev = torch.empty((n_srcs, pk.f_in), dtype=torch.float32, device=dev) if need_prev else None
             call("dgnn_gather_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.ea_own) if pk.fe else None, pk.fe,
                  ptr(pk.w_e), ptr(pk.b_e), ptr(x_in), ptr(in_aff.scale) if in_aff else None,
                  ptr(in_aff.shift) if in_aff else None, ptr(in_aff.mean) if in_aff else None,
-                 ptr(in_aff.rstd) if in_aff else None, int(relu_in), g.n_src, g.n_tgt, pk.f_in, ptr(dy_prev),
+                 ptr(in_aff.rstd) if in_aff else None, int(relu_in), n_srcs, g.n_tgt, pk.f_in, ptr(dy_prev),
                  ptr(part), st)
             r = _reduce(part)
             if pk.fe:

@@ -85,6 +85,102 @@ def exchange_halo(h: torch.Tensor, m: HaloMaps, group=None) -> None:
     dist.all_to_all_single(recv, send, output_split_sizes=m.recv_counts, input_split_sizes=m.send_counts, group=group)
 
 
+class HaloComm:
+    """What ``engine.forward`` / ``engine.backward`` need from a partition: the halo exchange (activations
+    forward, d_agg backward - the adjacency is symmetric, so it is the same exchange), a sum over ranks for the
+    normalisation statistics, and the number of cells of all ranks."""
+
+    def __init__(self, maps: HaloMaps, n_rows: int, group=None):
+        self.maps, self.n_rows, self.group = maps, int(n_rows), group
+
+    def exchange(self, h: torch.Tensor) -> None:
+        exchange_halo(h, self.maps, self.group)
+
+    def allreduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.maps.world > 1:
+            dist.all_reduce(t, group=self.group)
+        return t
+
+
+def _local_plan(net, data_all, world, rank, need_backward):
+    """Replicated graph build (Morton order), then this rank's [owned | halo] slice of it."""
+    from .graph import EllGraph, build_full_graph, pad4, pad_cols
+    dev = net._device()
+    cols = slice(1, None) if net.clf.regularization.cell_type else slice(None)
+    n = data_all.x.shape[0]
+    ea = None
+    if net.clf.model.edge_convs:
+        ea = data_all.edge_attr[:, 1:] if net.clf.regularization.edge_type else data_all.edge_attr
+    pos = getattr(data_all, "pos", None)
+    full = build_full_graph(data_all.edge_index.to(torch.long), ea, n, dev, pos=pos, order="auto",
+                            need_backward=need_backward)
+    bounds = partition_bounds(n, world)
+    maps = build_halo_maps(full.nbr, bounds, rank)
+    lo, hi = maps.lo, maps.hi
+    g = EllGraph(n_src=maps.n_own + maps.n_halo, n_tgt=maps.n_own, fe=full.fe, nbr=maps.local_nbr,
+                 ea_in=full.ea_in[lo:hi].contiguous() if full.ea_in is not None else None)
+    if need_backward:       # symmetric adjacency: the out-edge table of the owned rows is the in-edge table
+        g.onbr = maps.local_nbr
+        g.ea_own = full.ea_own[lo:hi].contiguous() if full.ea_own is not None else None
+    x = data_all.x[:, cols].to(dev, dtype=torch.float32)
+    xp = full.permute_rows(pad_cols(x, pad4(x.shape[1])))
+    # layer-0 input for [owned | halo]: features are static, so the halo rows are taken locally
+    rows = torch.cat([torch.arange(lo, hi, device=dev), maps.halo_gid.to(dev)])
+    x0 = xp.index_select(0, rows).contiguous()
+    owned_caller_ids = full.perm[lo:hi].long() if full.perm is not None else torch.arange(lo, hi, device=dev)
+    return g, maps, x0, owned_caller_ids, n
+
+
+class PartitionedTraining:
+    """Training of a ``SurfaceNet`` on ONE scene sharded over the ranks of the process group:
+    forward halo exchange of the pre-norm activations, normalisation statistics and loss normaliser summed over
+    ranks, backward halo exchange of d_agg, and one flat all-reduce of the gradients.
+
+        pt = PartitionedTraining(model)
+        ids, logits = pt.forward(data_all)          # logits of the owned cells, autograd-connected
+        loss = pt.loss(logits, data_all)            # the GLOBAL loss value (same on every rank)
+        optimizer.zero_grad(); loss.backward(); pt.allreduce_gradients(); optimizer.step()
+    """
+
+    def __init__(self, model, group=None):
+        self.model = model
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._plan = None
+
+    def prepare(self, data_all):
+        g, maps, x0, ids, n = _local_plan(self.model, data_all, self.world, self.rank, need_backward=True)
+        self._plan = (g, maps, x0, ids, HaloComm(maps, n, self.group))
+        return self._plan
+
+    def forward(self, data_all):
+        if self._plan is None:
+            self.prepare(data_all)
+        g, maps, x0, ids, comm = self._plan
+        net = self.model
+        with torch.cuda.device(x0.device):
+            out = net._run([g] * net.num_layers, x0, comm=comm)
+        return ids, out
+
+    def loss(self, logits, data_all):
+        from .runModel import cell_loss
+        ids = self._plan[3].to(data_all.y.device)
+        return cell_loss(logits, data_all.y[ids], data_all.x[ids], self.model.clf,
+                         group=self.group if self.world > 1 else None, distributed=self.world > 1)
+
+    def allreduce_gradients(self):
+        ps = [p for p in self.model.parameters() if p.grad is not None]
+        if self.world == 1 or not ps:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        dist.all_reduce(flat, group=self.group)
+        o = 0
+        for p in ps:
+            p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+            o += p.numel()
+
+
 class PartitionedInference:
     """Whole-scene inference of a ``SurfaceNet`` sharded over the ranks of the default process group.
 
@@ -99,28 +195,8 @@ class PartitionedInference:
         self._plan = None
 
     def prepare(self, data_all):
-        from .graph import EllGraph, build_full_graph, pad4, pad_cols
-        net = self.model
-        dev = net._device()
-        cols = slice(1, None) if net.clf.regularization.cell_type else slice(None)
-        n = data_all.x.shape[0]
-        ea = None
-        if net.clf.model.edge_convs:
-            ea = data_all.edge_attr[:, 1:] if net.clf.regularization.edge_type else data_all.edge_attr
-        pos = getattr(data_all, "pos", None)
-        full = build_full_graph(data_all.edge_index.to(torch.long), ea, n, dev, pos=pos, order="auto", need_backward=False)
-        bounds = partition_bounds(n, self.world)
-        maps = build_halo_maps(full.nbr, bounds, self.rank)
-        lo, hi = maps.lo, maps.hi
-        g = EllGraph(n_src=maps.n_own + maps.n_halo, n_tgt=maps.n_own, fe=full.fe, nbr=maps.local_nbr,
-                     ea_in=full.ea_in[lo:hi].contiguous() if full.ea_in is not None else None)
-        x = data_all.x[:, cols].to(dev, dtype=torch.float32)
-        xp = full.permute_rows(pad_cols(x, pad4(x.shape[1])))
-        # layer-0 input for [owned | halo]: features are static, so the halo rows are taken locally
-        rows = torch.cat([torch.arange(lo, hi, device=dev), maps.halo_gid.to(dev)])
-        x0 = xp.index_select(0, rows).contiguous()
-        owned_caller_ids = full.perm[lo:hi].long() if full.perm is not None else torch.arange(lo, hi, device=dev)
-        self._plan = (g, maps, x0, owned_caller_ids)
+        g, maps, x0, ids, n = _local_plan(self.model, data_all, self.world, self.rank, need_backward=False)
+        self._plan = (g, maps, x0, ids)
         return self._plan
 
     @torch.no_grad()
@@ -132,5 +208,5 @@ class PartitionedInference:
         net = self.model
         with torch.cuda.device(x0.device):
             out, _ = engine.forward(net._spec(), [g] * net.num_layers, x0, training=False, save=False,
-                                    exchange=lambda h: exchange_halo(h, maps, self.group))
+                                    comm=HaloComm(maps, 0, self.group))
         return ids, out

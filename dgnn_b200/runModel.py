@@ -27,7 +27,7 @@ def _strided(t: torch.Tensor, col0: int):
 
 class _KLCellLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, gt, weight, mode):
+    def forward(ctx, logits, gt, weight, mode, group=None, distributed=False):
         n = logits.shape[0]
         dev = logits.device
         logits = logits.contiguous()
@@ -36,6 +36,11 @@ class _KLCellLoss(torch.autograd.Function):
         w_ptr = ptr(weight) if weight is not None else None
         ws = weight.stride(0) if weight is not None else 0
         call("dgnn_kl_loss_fwd", ptr(logits), ptr(gt), gt.stride(0), w_ptr, ws, mode, n, ptr(part), _stream())
+        if distributed:           # partitioned scene: (sum w*l, sum w) over the cells of all ranks
+            import torch.distributed as dist
+            part = part.sum(dim=0, keepdim=True).contiguous()
+            dist.all_reduce(part, group=group)
+            grid = 1
         sums = torch.empty(3, dtype=torch.float32, device=dev)
         call("dgnn_kl_loss_finalize", ptr(part), grid, ptr(sums), _stream())
         ctx.save_for_backward(logits, gt, sums)
@@ -52,12 +57,14 @@ class _KLCellLoss(torch.autograd.Function):
         call("dgnn_kl_loss_bwd", ptr(logits), ptr(gt), gt.stride(0), ptr(weight) if weight is not None else None,
              weight.stride(0) if weight is not None else 0, ctx.mode, logits.shape[0], ptr(sums), ptr(gout), ptr(d),
              _stream())
-        return d, None, None, None
+        return d, None, None, None, None, None
 
 
-def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False):
+def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False, group=None, distributed=False):
     """``Trainer.calcLossAndOA`` (kl): ``batch_gt[:, :2]`` targets, ``batch_x[:, 0]`` raw volume.
-    ``batch_gt`` / ``batch_x`` may live on the host; they are moved to ``logits.device``."""
+    ``batch_gt`` / ``batch_x`` may live on the host; they are moved to ``logits.device``.
+    ``distributed``: the rows are one rank's share of a partitioned scene; the value returned is the loss over
+    the cells of all ranks of ``group`` (numerator and normaliser all-reduced)."""
     if clf.training.loss != "kl":
         raise NotImplementedError("only the 'kl' loss of the shipped configs has a CUDA kernel (got %r)"
                                   % clf.training.loss)
@@ -71,7 +78,7 @@ def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False):
         mode = _WEIGHT_MODE[clf.regularization.cell_norm]
     else:
         w, mode = None, 3
-    loss, sums = _KLCellLoss.apply(logits, gt, w, mode)
+    loss, sums = _KLCellLoss.apply(logits, gt, w, mode, group, distributed)
     return (loss, sums) if return_sums else loss
 
 

@@ -78,17 +78,17 @@ class _NetFn(torch.autograd.Function):
     aggregated messages; backward runs the hand-scheduled kernel sequence."""
 
     @staticmethod
-    def forward(ctx, net, graphs, x0, names, *params):
+    def forward(ctx, net, graphs, x0, names, comm, *params):
         spec = net._spec()
-        out, sv = engine.forward(spec, graphs, x0, training=net.training, save=True)
-        ctx.spec, ctx.sv, ctx.names = spec, sv, names
+        out, sv = engine.forward(spec, graphs, x0, training=net.training, save=True, comm=comm)
+        ctx.spec, ctx.sv, ctx.names, ctx.comm = spec, sv, names, comm
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        g = engine.backward(ctx.spec, ctx.sv, dout)
+        g = engine.backward(ctx.spec, ctx.sv, dout, comm=ctx.comm)
         ctx.sv = None
-        return (None, None, None, None) + tuple(g.get(n) for n in ctx.names)
+        return (None, None, None, None, None) + tuple(g.get(n) for n in ctx.names)
 
 
 class SurfaceNet(nn.Module):
@@ -198,11 +198,11 @@ class SurfaceNet(nn.Module):
         check_device(dev.index or 0)
         return dev
 
-    def _run(self, graphs, x0):
+    def _run(self, graphs, x0, comm=None):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             names, params = self._named_for_grad()
-            return _NetFn.apply(self, graphs, x0, names, *params)
-        out, _ = engine.forward(self._spec(), graphs, x0, training=self.training, save=False)
+            return _NetFn.apply(self, graphs, x0, names, comm, *params)
+        out, _ = engine.forward(self._spec(), graphs, x0, training=self.training, save=False, comm=comm)
         return out
 
     def _cached(self, holder, key, build):
