@@ -29,7 +29,7 @@ using namespace umma;
 constexpr int G_NCW = 16;
 constexpr int G_THREADS = (G_NCW + 1) * 32;
 constexpr int G_M = 128;
-constexpr int G_EA_STAGES = 4;                       // one tile (4 slots) of EA operands ahead
+constexpr int G_EA_STAGES = 2;                       // EA operand ring (hi | lo per stage)
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
 constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
 
@@ -98,28 +98,42 @@ __device__ __forceinline__ void act8(float4& a, float4& b, const float4& sa, con
 }
 
 // ---------------------------------------------------------------------------------------------------
-// MODE 0 / 1: phi on tensor cores, strips accumulated in registers
+// MODE 0 / 1: phi on tensor cores, strips accumulated in registers.
+//
+// Everything is pipelined per ITEM = (tile, slot k):
+//   x ring    the 32 rows x CPT features a warp consumes for one item are copied global -> shared with
+//             cp.async (16 B per lane, CH lanes per row => full 32..128-byte row segments per request instead
+//             of one sector per lane) into a warp-private, XOR-swizzled 2-stage ring; the copy of item n+1 is
+//             in flight while item n is consumed, with no registers held.  MODE 1 appends two plain items per
+//             tile: the rows' own d_self (k = 4) and z_prev (k = 5) strips.
+//   EA ring   2 stages of (hi | lo) K-major operands; the global loads of item n+3 are issued, and the
+//             registers of item n+2 stored, while item n is consumed.
+//   PHI ring  4 TMEM buffers of FP columns; the MMA warp runs up to 4 items ahead of the consumers.
 template <int CPT, int MODE>  // CPT: features per thread = fp / 4
 __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ea_full[G_EA_STAGES], ea_empty[G_EA_STAGES];
-    __shared__ uint64_t phi_full, phi_free;
+    __shared__ uint64_t phi_full[4], phi_free[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ double red_s[2 * 128];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int FP = CPT * 4;
+    constexpr int CH = CPT / 4;                          // 16-byte chunks per strip row (2, 4 or 8)
+    constexpr int RPI = 32 / CH;                         // rows copied by one cp.async warp instruction
+    constexpr int PITCH = CPT * 4;                       // bytes per strip row
+    constexpr int WSTAGE = 32 * PITCH;                   // bytes per warp and stage
+    constexpr int IPT = MODE == 0 ? 4 : 6;               // x-ring items per tile
     uint8_t* we_hi = smem;                               // [FP rows x 128 B]
     uint8_t* we_lo = we_hi + FP * 128;
     uint8_t* ea_base = we_lo + FP * 128;                 // stages of (hi 16 KB | lo 16 KB)
+    uint8_t* x_base = ea_base + (size_t)G_EA_STAGES * 2 * G_ATOM;   // [2 stages][G_NCW warps][32 rows x PITCH]
+    float* aff_s = reinterpret_cast<float*>(x_base + (size_t)2 * G_NCW * WSTAGE);   // MODE 0: scale[FP] | shift[FP]
 
     if (tid == 0) {
         for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_full[s], G_NCW); mbar_init(&ea_empty[s], 1); }
-        mbar_init(&phi_full, 1);
-        mbar_init(&phi_free, G_NCW);
+        for (int s = 0; s < 4; ++s) { mbar_init(&phi_full[s], 1); mbar_init(&phi_free[s], G_NCW); }
         fence_barrier_init();
     }
-    for (int c = tid; c < 256; c += G_THREADS) red_s[c] = 0.0;
     // zero the operands (K padding stays zero), then WE[n][e] = w_e[n][e] (e < fe), WE[n][fe] = b_e[n]
     for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM) / 16; i += G_THREADS)
         reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -137,6 +151,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         const int s = i / G_M, r = i % G_M;
         *reinterpret_cast<float*>(ea_base + (size_t)s * 2 * G_ATOM + atom_off(r, p.fe)) = 1.0f;
     }
+    if (MODE == 0) {                                             // producer norm affine, identity when absent / padded
+        for (int i = tid; i < FP; i += G_THREADS) {
+            const bool on = p.scale != nullptr && i < p.f;
+            aff_s[i] = on ? __ldg(p.scale + i) : 1.0f;
+            aff_s[FP + i] = on ? __ldg(p.shift + i) : 0.0f;
+        }
+    }
     fence_proxy_async_smem();
     if (warp == G_NCW) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
@@ -144,33 +165,33 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     const int64_t n_tiles = (p.n_rows + G_M - 1) / G_M;
+    // tiles of this CTA: blockIdx.x + i * gridDim.x, i < n_my;  PHI items: 4 per tile
+    const uint32_t n_my = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    const uint32_t n_phi = n_my * 4u;
 
     if (warp == G_NCW) {
         // ---------------------------------------------------------------- MMA warp
         const uint32_t idesc = make_idesc_tf32(G_M, FP);
         const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
-        uint32_t it = 0, tile_cnt = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
-            for (int k = 0; k < 4; ++k, ++it) {
-                if (lane == 0) {
-                    const uint32_t s = it % G_EA_STAGES, su = it / G_EA_STAGES;
-                    mbar_wait(&ea_full[s], su & 1);
-                    if (k == 0 && tile_cnt > 0) mbar_wait(&phi_free, (tile_cnt - 1) & 1);
-                    tc_fence_after_sync();
-                    const uint32_t ah = smem_u32(ea_base + (size_t)s * 2 * G_ATOM), al = ah + G_ATOM;
-                    const uint32_t d = tmem_base + (uint32_t)(k * FP);
-                    const int ksteps = (p.fe + 1 + 7) >> 3;     // fe features + bias column, 8 per k-step (3 for fe = 20)
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint32_t ko = kk * 32;
-                        mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
-                        mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
-                        mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
-                    }
-                    mma_commit(&ea_empty[s]);
-                    if (k == 3) mma_commit(&phi_full);
+        const int ksteps = (p.fe + 1 + 7) >> 3;          // fe features + bias column, 8 per k-step (3 for fe = 20)
+        for (uint32_t n = 0; n < n_phi; ++n) {
+            if (lane == 0) {
+                const uint32_t s = n % G_EA_STAGES, su = n / G_EA_STAGES, b = n & 3u, bu = n >> 2;
+                mbar_wait(&ea_full[s], su & 1);
+                if (bu > 0) mbar_wait(&phi_free[b], (bu - 1) & 1);
+                tc_fence_after_sync();
+                const uint32_t ah = smem_u32(ea_base + (size_t)s * 2 * G_ATOM), al = ah + G_ATOM;
+                const uint32_t d = tmem_base + b * (uint32_t)FP;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint32_t ko = kk * 32;
+                    mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
+                    mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+                    mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
                 }
-                __syncwarp();
+                mma_commit(&ea_empty[s]);
+                mma_commit(&phi_full[b]);
             }
+            __syncwarp();
         }
     } else {
         // ---------------------------------------------------------------- compute warps
@@ -178,195 +199,256 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;                      // first feature of this thread's strip
         const bool relu = (p.relu & 1) != 0;
-        const bool x_skip = (p.relu & 2) != 0, t_skip = (p.relu & 4) != 0, s_skip = (p.relu & 8) != 0;  // dev experiments
         const bool affine = p.scale != nullptr;
         const bool al8 = (p.f & 7) == 0;
         const int fe4 = p.fe >> 2;
+        uint8_t* xw = x_base + (size_t)warp * WSTAGE;                  // + stage * G_NCW * WSTAGE
+        const uint32_t swz_l = ((uint32_t)lane / (8 / CH)) & (CH - 1); // chunk swizzle of this thread's row
+        const int c_row = lane / CH, c_ch = lane % CH;                 // copy role: row within an instruction, chunk
         double s1d[CPT / 8], s2d[CPT / 8];             // running (S1, S2) of column c0 + 8*jj + (lane >> 2)
 #pragma unroll
         for (int i = 0; i < CPT / 8; ++i) s1d[i] = s2d[i] = 0.0;
-        uint32_t it = 0, tile_cnt = 0;
-        // stage EA_0..3 of a tile (rows of the tile, fe floats each, split hi / lo); the MMA warp follows
-        auto stage_ea = [&](int64_t tile_s) {
-            const int64_t base = tile_s * G_M;
-            // all loads of the four slots first (<= 2 float4 per thread and slot for fe <= 28) ...
-            float4 v[4][2];
+
+        auto tile_of = [&](uint32_t tc) { return (int64_t)blockIdx.x + (int64_t)tc * gridDim.x; };
+        auto load_nbr = [&](uint32_t tc) {
+            int4 nb = make_int4(-1, -1, -1, -1);
+            if (tc < n_my) {
+                const int64_t t = tile_of(tc) * G_M + row;
+                if (t < p.n_rows) nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+            }
+            return nb;
+        };
+        // ---- EA staging, one PHI item at a time
+        float4 ev[2];
+        int e_r[2], e_c4[2];                           // this thread's (row, first feature) of the two float4 it stages
+        uint32_t e_off[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+        for (int u = 0; u < 2; ++u) {
+            const int idx = tid + u * G_NCW * 32;
+            e_r[u] = idx < G_M * fe4 ? idx / fe4 : -1;
+            e_c4[u] = idx < G_M * fe4 ? (idx - e_r[u] * fe4) * 4 : 0;
+            e_off[u] = atom_off(e_r[u] < 0 ? 0 : e_r[u], e_c4[u]);
+        }
+        auto ea_load = [&](uint32_t n) {               // global loads of PHI item n into registers
+            const int64_t r0 = tile_of(n >> 2) * G_M;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int idx = tid + u * G_NCW * 32;
-                    v[k][u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < G_M * fe4) {
-                        const int r = idx / fe4, c = idx - r * fe4;
-                        const int64_t tr = base + r;
-                        if (tr < p.n_rows) v[k][u] = ldg4(p.ea + ((size_t)tr * 4 + k) * p.fe + c * 4);
-                    }
-                }
-            // ... then per slot: wait for its stage, split hi / lo, store, arrive (the MMA warp follows)
-#pragma unroll
-            for (int k = 0; k < 4; ++k, ++it) {
-                const uint32_t s = it % G_EA_STAGES, su = it / G_EA_STAGES;
-                uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
-                uint8_t* e_lo = e_hi + G_ATOM;
-                mbar_wait(&ea_empty[s], (su & 1) ^ 1);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int idx = tid + u * G_NCW * 32;
-                    if (idx < G_M * fe4) {
-                        const int r = idx / fe4, c = idx - r * fe4;
-                        float4 h, l;
-                        split_tf32(v[k][u].x, h.x, l.x); split_tf32(v[k][u].y, h.y, l.y);
-                        split_tf32(v[k][u].z, h.z, l.z); split_tf32(v[k][u].w, h.w, l.w);
-                        const uint32_t off = atom_off(r, c * 4);
-                        *reinterpret_cast<float4*>(e_hi + off) = h;
-                        *reinterpret_cast<float4*>(e_lo + off) = l;
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ea_full[s]);
+            for (int u = 0; u < 2; ++u) {
+                ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n < n_phi && e_r[u] >= 0 && r0 + e_r[u] < p.n_rows)
+                    ev[u] = ldg4(p.ea + ((size_t)(r0 + e_r[u]) * 4 + (n & 3u)) * p.fe + e_c4[u]);
             }
         };
-        if ((int64_t)blockIdx.x < n_tiles) stage_ea(blockIdx.x);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
-            const int64_t tile0 = tile * G_M;
-            const int64_t t = tile0 + row;
-            const bool tv = t < p.n_rows;
-            int4 nb4 = make_int4(-1, -1, -1, -1);
-            if (tv) nb4 = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
-            const int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-            // EA of the next tile goes in flight before this tile is consumed (its MMAs wait for phi_free)
-            if (tile + gridDim.x < n_tiles) stage_ea(tile + gridDim.x);
-            // ---- consume: all four PHI_k of the tile are in TMEM
-            mbar_wait(&phi_full, tile_cnt & 1);
-            tc_fence_after_sync();
-            const int cnt = (nbv[0] >= 0) + (nbv[1] >= 0) + (nbv[2] >= 0) + (nbv[3] >= 0);
-            const float dcnt = (float)(cnt > 0 ? cnt : 1);
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        auto ea_store = [&](uint32_t n) {              // registers -> (hi | lo) operand stage, then signal the MMA warp
+            if (n >= n_phi) return;
+            const uint32_t s = n % G_EA_STAGES, su = n / G_EA_STAGES;
+            uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
+            uint8_t* e_lo = e_hi + G_ATOM;
+            mbar_wait(&ea_empty[s], (su & 1) ^ 1);
 #pragma unroll
-            for (int j = 0; j < CPT; j += 8) {
-                const int f0 = c0 + j;
-                const bool fvalid = f0 < p.f, fvalid_b = f0 + 4 < p.f;   // the two 4-feature halves of the strip step
-                uint32_t ph[4][8];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (!t_skip) tmem_ld8(trow + (uint32_t)(k * FP + j), ph[k]);
-                    else { for (int i = 0; i < 8; ++i) ph[k][i] = 0x3f800000u; }
+            for (int u = 0; u < 2; ++u) {
+                if (e_r[u] >= 0) {
+                    float4 h, l;
+                    split_tf32(ev[u].x, h.x, l.x); split_tf32(ev[u].y, h.y, l.y);
+                    split_tf32(ev[u].z, h.z, l.z); split_tf32(ev[u].w, h.w, l.w);
+                    *reinterpret_cast<float4*>(e_hi + e_off[u]) = h;
+                    *reinterpret_cast<float4*>(e_lo + e_off[u]) = l;
                 }
-                float4 xa[4], xb[4];
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ea_full[s]);
+        };
+        // ---- x ring: cp.async of item (tile count tc, slot k) into stage `st`
+        auto x_issue = [&](uint32_t tc, int k, const int (&nbv)[4], uint32_t st) {
+            if (tc < n_my) {
+                uint8_t* dst = xw + (size_t)st * G_NCW * WSTAGE;
+                const int64_t t0 = tile_of(tc) * G_M + q * 32;
+                const int fcol = c0 + c_ch * 4;
+                const int mine = k < 4 ? nbv[k < 4 ? k : 0] : 0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    xb[k] = xa[k];
-                    if (x_skip) {
-                        xa[k] = make_float4(1.f, 1.f, 1.f, 1.f); xb[k] = xa[k];
-                    } else if (al8) {   // rows are 32-byte aligned: one 256-bit request instead of two 128-bit ones
-                        if (nbv[k] >= 0 && fvalid) ldg8(p.x + (size_t)nbv[k] * p.f + f0, xa[k], xb[k]);
-                    } else {
-                        if (nbv[k] >= 0 && fvalid) xa[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0);
-                        if (nbv[k] >= 0 && fvalid_b) xb[k] = ldg4(p.x + (size_t)nbv[k] * p.f + f0 + 4);
+                for (int i = 0; i < CH; ++i) {
+                    const int r = i * RPI + c_row;     // row of the quadrant handled by this lane
+                    int64_t sr = -1;
+                    const float* base = p.x;
+                    if (k < 4) {
+                        sr = __shfl_sync(0xffffffffu, mine, r);
+                    } else if (MODE == 1 && k == 4) {
+                        base = p.addend;
+                        if (base != nullptr && t0 + r < p.n_add_rows && t0 + r < p.n_rows) sr = t0 + r;
+                    } else if (MODE == 1) {
+                        base = p.z_prev;
+                        if (base != nullptr && t0 + r < p.n_rows) sr = t0 + r;
                     }
-                }
-                float4 sa = make_float4(1.f, 1.f, 1.f, 1.f), sb = sa, ha = make_float4(0.f, 0.f, 0.f, 0.f), hb = ha;
-                if (MODE == 0 && affine && fvalid) { sa = ldg4(p.scale + f0); ha = ldg4(p.shift + f0); }
-                if (MODE == 0 && affine && fvalid_b) { sb = ldg4(p.scale + f0 + 4); hb = ldg4(p.shift + f0 + 4); }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (nbv[k] < 0) continue;
-                    if (MODE == 0) act8(xa[k], xb[k], sa, sb, ha, hb, affine, relu);
-                    acc[0] = fmaf(xa[k].x, __uint_as_float(ph[k][0]), acc[0]);
-                    acc[1] = fmaf(xa[k].y, __uint_as_float(ph[k][1]), acc[1]);
-                    acc[2] = fmaf(xa[k].z, __uint_as_float(ph[k][2]), acc[2]);
-                    acc[3] = fmaf(xa[k].w, __uint_as_float(ph[k][3]), acc[3]);
-                    acc[4] = fmaf(xb[k].x, __uint_as_float(ph[k][4]), acc[4]);
-                    acc[5] = fmaf(xb[k].y, __uint_as_float(ph[k][5]), acc[5]);
-                    acc[6] = fmaf(xb[k].z, __uint_as_float(ph[k][6]), acc[6]);
-                    acc[7] = fmaf(xb[k].w, __uint_as_float(ph[k][7]), acc[7]);
-                }
-                if (MODE == 0) {
-                    if (tv && fvalid && !s_skip) {
-                        const float4 oa = make_float4(acc[0] / dcnt, acc[1] / dcnt, acc[2] / dcnt, acc[3] / dcnt);
-                        const float4 ob = make_float4(acc[4] / dcnt, acc[5] / dcnt, acc[6] / dcnt, acc[7] / dcnt);
-                        if (al8) {
-                            stg8(p.out + (size_t)t * p.f + f0, oa, ob);      // one full 32-byte sector per thread
-                        } else {
-                            *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = oa;
-                            if (fvalid_b) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = ob;
-                        }
-                    }
-                } else {
-                    float dx[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dx[i] = 0.f;
-                    if (!tv || !fvalid) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                    } else {
-                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (!fvalid_b) { acc[4] = acc[5] = acc[6] = acc[7] = 0.f; }
-                        if (p.addend != nullptr && t < p.n_add_rows) {
-                            float4 a = ldg4(p.addend + (size_t)t * p.f + f0);
-                            float4 b = fvalid_b ? ldg4(p.addend + (size_t)t * p.f + f0 + 4) : zero4;
-                            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-                            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-                        }
-                        if (p.z_prev != nullptr) {
-                            float4 za = ldg4(p.z_prev + (size_t)t * p.f + f0);
-                            float4 zb = fvalid_b ? ldg4(p.z_prev + (size_t)t * p.f + f0 + 4) : zero4;
-                            const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
-                            float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            float mu[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rs[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-                            if (p.p_scale != nullptr) {
-                                float4 a = ldg4(p.p_scale + f0), b = fvalid_b ? ldg4(p.p_scale + f0 + 4) : zero4;
-                                float4 c = ldg4(p.p_shift + f0), d = fvalid_b ? ldg4(p.p_shift + f0 + 4) : zero4;
-                                sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = b.x; sc[5] = b.y; sc[6] = b.z; sc[7] = b.w;
-                                sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
-                            }
-                            if (p.p_mean != nullptr) {
-                                float4 a = ldg4(p.p_mean + f0), b = fvalid_b ? ldg4(p.p_mean + f0 + 4) : zero4;
-                                float4 c = ldg4(p.p_rstd + f0), d = fvalid_b ? ldg4(p.p_rstd + f0 + 4) : zero4;
-                                mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; mu[4] = b.x; mu[5] = b.y; mu[6] = b.z; mu[7] = b.w;
-                                rs[0] = c.x; rs[1] = c.y; rs[2] = c.z; rs[3] = c.w; rs[4] = d.x; rs[5] = d.y; rs[6] = d.z; rs[7] = d.w;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (p.p_relu && !(fmaf(zv[i], sc[i], sh[i]) > 0.f)) acc[i] = 0.f;
-                                if (i >= 4 && !fvalid_b) acc[i] = 0.f;
-                                dx[i] = acc[i] * ((zv[i] - mu[i]) * rs[i]);
-                            }
-                        }
-                        if (p.out != nullptr) {
-                            if (al8) {
-                                stg8(p.out + (size_t)t * p.f + f0, make_float4(acc[0], acc[1], acc[2], acc[3]),
-                                     make_float4(acc[4], acc[5], acc[6], acc[7]));
-                            } else {
-                                *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                                if (fvalid_b)
-                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                            }
-                        }
-                    }
-                    if (p.s_partials != nullptr) {
-                        s1d[j >> 3] += (double)warp_colsum8(acc, lane);
-                        s2d[j >> 3] += (double)warp_colsum8(dx, lane);
+                    if (sr >= 0 && fcol < p.f) {
+                        const uint32_t sw = ((uint32_t)r / (8 / CH)) & (CH - 1);
+                        cp_async16(dst + r * PITCH + (((uint32_t)c_ch ^ sw) << 4), base + (size_t)sr * p.f + fcol);
                     }
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&phi_free);
+            cp_async_commit();
+        };
+
+        // ---- prologue
+        int4 nb4 = load_nbr(0);
+        int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+        ea_load(0); ea_store(0);
+        ea_load(1); ea_store(1);
+        ea_load(2);
+        uint32_t xi = 0;                               // x items consumed so far (stage = xi & 1)
+        x_issue(0, 0, nbv, 0);
+        uint32_t pn = 0;                               // PHI items consumed so far
+        for (uint32_t tc = 0; tc < n_my; ++tc) {
+            const int64_t t = tile_of(tc) * G_M + row;
+            const bool tv = t < p.n_rows;
+            const int4 nbn4 = load_nbr(tc + 1);        // neighbours of the next tile (its first copy is issued in this one)
+            const int nbn[4] = {nbn4.x, nbn4.y, nbn4.z, nbn4.w};
+            const int cnt = (nbv[0] >= 0) + (nbv[1] >= 0) + (nbv[2] >= 0) + (nbv[3] >= 0);
+            const float rcnt = cnt > 1 ? (cnt == 2 ? 0.5f : (cnt == 3 ? (1.0f / 3.0f) : 0.25f)) : 1.0f;   // 1 / max(cnt, 1)
+            float acc[CPT];
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k, ++xi) {
+                // next item's copy goes in flight (the other stage was released by the __syncwarp below)
+                if (k + 1 < IPT) x_issue(tc, k + 1, nbv, (xi + 1) & 1);
+                else x_issue(tc + 1, 0, nbn, (xi + 1) & 1);
+                cp_async_wait<1>();
+                __syncwarp();
+                const uint8_t* xs = xw + (size_t)(xi & 1) * G_NCW * WSTAGE + lane * PITCH;
+                if (k < 4) {
+                    const uint32_t b = pn & 3u, bu = pn >> 2;
+                    mbar_wait(&phi_full[b], bu & 1);
+                    tc_fence_after_sync();
+                    // MMA of item pn is done => EA stage (pn + 2) % 2 is free: store item pn + 2, fetch item pn + 3
+                    ea_store(pn + 2);
+                    ea_load(pn + 3);
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)FP + (uint32_t)c0;
+                    const bool valid = nbv[k] >= 0;
+#pragma unroll
+                    for (int j = 0; j < CPT; j += 8) {
+                        const int f0 = c0 + j;
+                        uint32_t ph[8];
+                        tmem_ld8(trow + (uint32_t)j, ph);
+                        float4 xa = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                        float4 xb = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4));
+                        if (MODE == 0 && affine) {               // warp-uniform addresses: shared-memory broadcasts
+                            const float4 sa = *reinterpret_cast<const float4*>(aff_s + f0);
+                            const float4 sb = *reinterpret_cast<const float4*>(aff_s + f0 + 4);
+                            const float4 ha = *reinterpret_cast<const float4*>(aff_s + FP + f0);
+                            const float4 hb = *reinterpret_cast<const float4*>(aff_s + FP + f0 + 4);
+                            act8(xa, xb, sa, sb, ha, hb, true, relu);
+                        } else if (MODE == 0) {
+                            act8(xa, xb, xa, xa, xa, xa, false, relu);
+                        }
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (valid) {
+                            acc[j + 0] = fmaf(xa.x, __uint_as_float(ph[0]), acc[j + 0]);
+                            acc[j + 1] = fmaf(xa.y, __uint_as_float(ph[1]), acc[j + 1]);
+                            acc[j + 2] = fmaf(xa.z, __uint_as_float(ph[2]), acc[j + 2]);
+                            acc[j + 3] = fmaf(xa.w, __uint_as_float(ph[3]), acc[j + 3]);
+                            acc[j + 4] = fmaf(xb.x, __uint_as_float(ph[4]), acc[j + 4]);
+                            acc[j + 5] = fmaf(xb.y, __uint_as_float(ph[5]), acc[j + 5]);
+                            acc[j + 6] = fmaf(xb.z, __uint_as_float(ph[6]), acc[j + 6]);
+                            acc[j + 7] = fmaf(xb.w, __uint_as_float(ph[7]), acc[j + 7]);
+                        }
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&phi_free[b]);
+                    ++pn;
+                    if (MODE == 0 && k == 3) {
+#pragma unroll
+                        for (int j = 0; j < CPT; j += 8) {
+                            const int f0 = c0 + j;
+                            if (tv && f0 < p.f) {
+                                const float4 oa = make_float4(acc[j] * rcnt, acc[j + 1] * rcnt, acc[j + 2] * rcnt, acc[j + 3] * rcnt);
+                                const float4 ob = make_float4(acc[j + 4] * rcnt, acc[j + 5] * rcnt, acc[j + 6] * rcnt, acc[j + 7] * rcnt);
+                                if (al8) {
+                                    stg8(p.out + (size_t)t * p.f + f0, oa, ob);      // one full 32-byte sector per thread
+                                } else {
+                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = oa;
+                                    if (f0 + 4 < p.f) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = ob;
+                                }
+                            }
+                        }
+                    }
+                } else if (MODE == 1 && k == 4) {
+                    if (p.addend != nullptr && tv && t < p.n_add_rows) {
+#pragma unroll
+                        for (int j = 0; j < CPT; j += 4) {
+                            if (c0 + j < p.f) {
+                                const float4 a = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                                acc[j] += a.x; acc[j + 1] += a.y; acc[j + 2] += a.z; acc[j + 3] += a.w;
+                            }
+                        }
+                    }
+                } else if (MODE == 1) {
+#pragma unroll
+                    for (int j = 0; j < CPT; j += 8) {
+                        const int f0 = c0 + j;
+                        const bool fvalid = f0 < p.f, fvalid_b = f0 + 4 < p.f;
+                        float a8[8], dx[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { a8[i] = 0.f; dx[i] = 0.f; }
+                        if (tv && fvalid) {
+                            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) a8[i] = (i < 4 || fvalid_b) ? acc[j + i] : 0.f;
+                            if (p.z_prev != nullptr) {
+                                const float4 za = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                                const float4 zb = fvalid_b ? *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4)) : zero4;
+                                const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                                float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                float mu[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rs[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+                                if (p.p_scale != nullptr) {
+                                    float4 a = ldg4(p.p_scale + f0), bq = fvalid_b ? ldg4(p.p_scale + f0 + 4) : zero4;
+                                    float4 c = ldg4(p.p_shift + f0), d = fvalid_b ? ldg4(p.p_shift + f0 + 4) : zero4;
+                                    sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = bq.x; sc[5] = bq.y; sc[6] = bq.z; sc[7] = bq.w;
+                                    sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
+                                }
+                                if (p.p_mean != nullptr) {
+                                    float4 a = ldg4(p.p_mean + f0), bq = fvalid_b ? ldg4(p.p_mean + f0 + 4) : zero4;
+                                    float4 c = ldg4(p.p_rstd + f0), d = fvalid_b ? ldg4(p.p_rstd + f0 + 4) : zero4;
+                                    mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; mu[4] = bq.x; mu[5] = bq.y; mu[6] = bq.z; mu[7] = bq.w;
+                                    rs[0] = c.x; rs[1] = c.y; rs[2] = c.z; rs[3] = c.w; rs[4] = d.x; rs[5] = d.y; rs[6] = d.z; rs[7] = d.w;
+                                }
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    if (p.p_relu && !(fmaf(zv[i], sc[i], sh[i]) > 0.f)) a8[i] = 0.f;
+                                    if (i >= 4 && !fvalid_b) a8[i] = 0.f;
+                                    dx[i] = a8[i] * ((zv[i] - mu[i]) * rs[i]);
+                                }
+                            }
+                            if (p.out != nullptr) {
+                                if (al8) {
+                                    stg8(p.out + (size_t)t * p.f + f0, make_float4(a8[0], a8[1], a8[2], a8[3]),
+                                         make_float4(a8[4], a8[5], a8[6], a8[7]));
+                                } else {
+                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = make_float4(a8[0], a8[1], a8[2], a8[3]);
+                                    if (fvalid_b)
+                                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+                                }
+                            }
+                        }
+                        if (p.s_partials != nullptr) {
+                            s1d[j >> 3] += (double)warp_colsum8(a8, lane);
+                            s2d[j >> 3] += (double)warp_colsum8(dx, lane);
+                        }
+                    }
+                }
+                __syncwarp();                          // every lane is done with stage xi & 1 before it is refilled
+            }
+            nbv[0] = nbn[0]; nbv[1] = nbn[1]; nbv[2] = nbn[2]; nbv[3] = nbn[3];
         }
+        cp_async_wait<0>();
+        __syncwarp();
+        // per-warp (S1, S2) partials into the warp's own (now idle) x-ring stage: doubles [2][CPT]
         if (MODE == 1 && p.s_partials != nullptr && (lane & 3) == 0) {
+            double* mine = reinterpret_cast<double*>(xw);
 #pragma unroll
             for (int jj = 0; jj < CPT / 8; ++jj) {
-                const int col = c0 + jj * 8 + (lane >> 2);
-                if (col < p.f) {
-                    atomicAdd(&red_s[col], s1d[jj]);
-                    atomicAdd(&red_s[128 + col], s2d[jj]);
-                }
+                mine[jj * 8 + (lane >> 2)] = s1d[jj];
+                mine[CPT + jj * 8 + (lane >> 2)] = s2d[jj];
             }
         }
     }
@@ -375,8 +457,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     if (MODE == 1 && p.s_partials != nullptr) {
         double* my = p.s_partials + (size_t)blockIdx.x * 2 * p.f;
         for (int c = tid; c < p.f; c += G_THREADS) {
-            my[c] = red_s[c];
-            my[p.f + c] = red_s[128 + c];
+            const int g = c / CPT, cl = c % CPT;
+            double a = 0.0, b2 = 0.0;
+            for (int qq = 0; qq < 4; ++qq) {           // the four row quadrants of feature group g, fixed order
+                const double* w = reinterpret_cast<const double*>(x_base + (size_t)(g * 4 + qq) * WSTAGE);
+                a += w[cl];
+                b2 += w[CPT + cl];
+            }
+            my[c] = a;
+            my[p.f + c] = b2;
         }
     }
     if (warp == G_NCW) tmem_dealloc(tmem_base, 512);
@@ -556,13 +645,13 @@ static int fp_of(int f) { return f <= 32 ? 32 : (f <= 64 ? 64 : 128); }
 template <int MODE>
 static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
-    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + 1024;
+    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + (size_t)2 * G_NCW * 32 * p.fp + (size_t)8 * p.fp + 1024;
 #define LAUNCH_G(CPT)                                                                                          \
     do {                                                                                                       \
         static bool configured = false;                                                                        \
         if (!configured) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(gather_tc_kernel<CPT, MODE>,                                  \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);     \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);     \
             if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                    \
             configured = true;                                                                                 \
         }                                                                                                      \
