@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdgnn_b200.so")
+# DGNN_B200_LIB: development override (kernel variants built by tools/build_variant.sh)
+LIB_PATH = os.environ.get("DGNN_B200_LIB") or os.path.join(_HERE, "csrc", "libdgnn_b200.so")
 
 P = c_void_p
 I = c_int

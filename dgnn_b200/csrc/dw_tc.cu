@@ -19,9 +19,9 @@ namespace dgnn {
 
 using namespace umma;
 
-constexpr int DW_NPW = 16;
-constexpr int DW_THREADS = (DW_NPW + 1) * 32;
-constexpr int DW_CELLS = 32;                       // cells (K) per stage: 2 per producer warp
+constexpr int DW_NPW = 12;                         // producer warps: one per 32-channel operand block at 128 -> 128
+constexpr int DW_THREADS = (DW_NPW + 1) * 32;      // 13 warps: at most 4 per scheduler => 128 registers per thread
+constexpr int DW_CELLS = 32;                       // cells (K) per stage = 8 groups of 4 cells
 constexpr int DW_A_BYTES = 128 * 128;               // M = 128 channel rows x 32 cells (one K-atom): 16 KB
 
 struct DwTcArgs {
@@ -39,6 +39,7 @@ struct DwTcArgs {
     int relu_in;
     int64_t n_tgt;
     int f_in, f_out, k_total, np, stages;
+    int wpb, active_warps;   // producer warps per 32-channel block; warps that produce (the rest idle)
     float* partials;  // [grid][f_out][k_total]
 };
 
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
     const int b_bytes = p.np * 128;
     const int stage_bytes = 2 * DW_A_BYTES + 2 * b_bytes;
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&bar_full[s], DW_NPW); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_full[s], p.active_warps); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
@@ -103,10 +104,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
 
     if (warp == DW_NPW) {
         const uint32_t idesc = make_idesc_tf32(128, p.np);
+        uint32_t s = 0, ph = 0;
         for (int64_t i = 0; i < my_groups; ++i) {
-            const uint32_t s = (uint32_t)(i % p.stages), use = (uint32_t)(i / p.stages);
             if (lane == 0) {
-                mbar_wait(&bar_full[s], use & 1);
+                mbar_wait(&bar_full[s], ph);
                 tc_fence_after_sync();
                 const uint32_t ah = smem_u32(smem + (size_t)s * stage_bytes), al = ah + DW_A_BYTES;
                 const uint32_t bh = al + DW_A_BYTES, bl = bh + b_bytes;
@@ -121,99 +122,124 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                 if (i == my_groups - 1) mma_commit(&bar_done);
             }
             __syncwarp();
+            if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
         }
-    } else {
+    } else if (warp < p.active_warps) {
+        // Every producer thread owns ONE 4-channel chunk of one 32-channel operand block for the whole kernel
+        // (block = warp / wpb), so source pointer, row stride, activation / normalisation coefficients and the
+        // destination row are loop invariants; per 32-cell stage it handles the cell groups gsub, gsub + wpb, ...
         const bool relu = p.relu_in != 0;
-        const int j = lane & 3, c = lane >> 2;       // cell within a group of 4, 16-byte chunk within a 32-channel block
-        const int nb_a = (p.f_out + 31) >> 5;        // 32-channel blocks of dz
-        const int n_items = 8 * (nb_a + (p.np >> 5));  // (cell group, channel block) pairs per stage
-        for (int64_t i = 0; i < my_groups; ++i) {
-            const uint32_t s = (uint32_t)(i % p.stages), use = (uint32_t)(i / p.stages);
-            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
-            uint8_t* a_lo = a_hi + DW_A_BYTES;
-            uint8_t* b_hi = a_lo + DW_A_BYTES;
-            uint8_t* b_lo = b_hi + b_bytes;
-            // phase 1: all global loads of this warp's items (up to 6) go in flight together
-            constexpr int MAXI = 6;   // 8 * (4 + 8) items / 16 warps
-            float4 r0[MAXI], r1[MAXI];
-#pragma unroll
-            for (int u = 0; u < MAXI; ++u) {
-                const int item = warp + u * DW_NPW;
-                r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                r1[u] = r0[u];
-                if (item >= n_items) continue;
-                const int g = item & 7, blk = item >> 3;
-                const int64_t t = (g_begin + i) * DW_CELLS + g * 4 + j;
-                if (t >= p.n_tgt) continue;
-                if (blk < nb_a) {
-                    const int ch = blk * 32 + c * 4;
-                    if (ch < p.f_out) {
-                        r0[u] = ldg4(p.dy + (size_t)t * p.f_out + ch);
-                        if (p.ng != nullptr) r1[u] = ldg4(p.z + (size_t)t * p.f_out + ch);
-                    }
-                } else {
-                    const int n = (blk - nb_a) * 32 + c * 4;
-                    if (n < p.k_total) {
-                        if (p.agg != nullptr && n < p.f_in) r0[u] = ldg4(p.agg + (size_t)t * p.f_in + n);
-                        else r0[u] = ldg4(p.x_in + (size_t)t * p.f_in + (p.agg != nullptr ? n - p.f_in : n));
-                    }
+        const int j = lane & 3, c = lane >> 2;       // cell within a group of 4, 16-byte chunk within the block
+        const int nb_a = (p.f_out + 31) >> 5;        // 32-channel blocks of dz (A operand); then np/32 blocks of [agg | h]
+        const int wpb = p.wpb;
+        const int blk = warp / wpb, gsub = warp % wpb;
+        const bool is_a = blk < nb_a;
+        const int ch = (is_a ? blk : blk - nb_a) * 32 + c * 4;        // first channel of the chunk in its operand
+        // kind: 0 = dz, 1 = agg (raw), 2 = h(x) ; -1 = padding chunk (zeros)
+        int kind = -1, stride = 0;
+        const float* src = nullptr;
+        const float* src2 = nullptr;
+        float4 k0 = make_float4(1.f, 1.f, 1.f, 1.f), k1 = make_float4(0.f, 0.f, 0.f, 0.f), k2 = k1, k3 = k1, k4 = k0;
+        if (is_a) {
+            if (ch < p.f_out) {
+                kind = 0; stride = p.f_out; src = p.dy + ch;
+                if (p.ng != nullptr) {
+                    src2 = p.z + ch;
+                    k0 = ldg4(p.ng + ch); k1 = ldg4(p.na + ch); k2 = ldg4(p.nb + ch); k3 = ldg4(p.nmean + ch); k4 = ldg4(p.nrstd + ch);
+                    // dz = g*dy - (a + (z - m)*rs*b) = g*dy - z*(rs*b) - (a - m*rs*b)
+                    k2 = make_float4(k4.x * k2.x, k4.y * k2.y, k4.z * k2.z, k4.w * k2.w);
+                    k1 = make_float4(k1.x - k3.x * k2.x, k1.y - k3.y * k2.y, k1.z - k3.z * k2.z, k1.w - k3.w * k2.w);
                 }
             }
-            mbar_wait(&bar_empty[s], (use & 1) ^ 1);
-            // phase 2: transform, transpose (4 channels x 1 cell -> 1 channel x 4 cells), split, store
-#pragma unroll
-            for (int u = 0; u < MAXI; ++u) {
-                const int item = warp + u * DW_NPW;
-                if (item >= n_items) continue;
-                const int g = item & 7, blk = item >> 3;
-                const int64_t t = (g_begin + i) * DW_CELLS + g * 4 + j;
-                const bool tv = t < p.n_tgt;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                uint8_t *dst_hi, *dst_lo;
-                int row;
-                if (blk < nb_a) {                       // dz block -> A operand rows (channels)
-                    const int ch = blk * 32 + c * 4;
-                    if (tv && ch < p.f_out) {
-                        const float4 d = r0[u];
-                        if (p.ng != nullptr) {
-                            const float4 zv = r1[u];
-                            float4 gg = ldg4(p.ng + ch), a = ldg4(p.na + ch), b = ldg4(p.nb + ch), m = ldg4(p.nmean + ch),
-                                   rs = ldg4(p.nrstd + ch);
-                            v.x = gg.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
-                            v.y = gg.y * d.y - (a.y + (zv.y - m.y) * rs.y * b.y);
-                            v.z = gg.z * d.z - (a.z + (zv.z - m.z) * rs.z * b.z);
-                            v.w = gg.w * d.w - (a.w + (zv.w - m.w) * rs.w * b.w);
-                        } else {
-                            v = d;
-                        }
-                    }
-                    dst_hi = a_hi; dst_lo = a_lo;
-                    row = blk * 32 + c * 4 + j;
-                } else {                                // [agg | h] block -> B operand rows (columns of dW)
-                    const int n = (blk - nb_a) * 32 + c * 4;
-                    if (tv && n < p.k_total) {
-                        v = r0[u];
-                        if (!(p.agg != nullptr && n < p.f_in)) {
-                            const int col = p.agg != nullptr ? n - p.f_in : n;
-                            if (p.in_scale != nullptr) {
-                                float4 sc = ldg4(p.in_scale + col), sh = ldg4(p.in_shift + col);
-                                v.x = act(v.x, sc.x, sh.x, relu); v.y = act(v.y, sc.y, sh.y, relu);
-                                v.z = act(v.z, sc.z, sh.z, relu); v.w = act(v.w, sc.w, sh.w, relu);
-                            } else if (relu) {
-                                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                            }
-                        }
-                    }
-                    dst_hi = b_hi; dst_lo = b_lo;
-                    row = (blk - nb_a) * 32 + c * 4 + j;
-                }
-                v = transpose4(v, j);                   // now: channel `row`, cells 4g .. 4g+3
-                put_split4(dst_hi, dst_lo, (uint32_t)row * 128u + (uint32_t)((g ^ (row & 7)) << 4), v);
+        } else if (ch < p.k_total) {
+            stride = p.f_in;
+            if (p.agg != nullptr && ch < p.f_in) { kind = 1; src = p.agg + ch; }
+            else {
+                const int col = p.agg != nullptr ? ch - p.f_in : ch;
+                kind = 2; src = p.x_in + col;
+                if (p.in_scale != nullptr) { k0 = ldg4(p.in_scale + col); k1 = ldg4(p.in_shift + col); }
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[s]);
         }
+        const bool affine = kind == 2 && p.in_scale != nullptr;
+        const bool norm = kind == 0 && p.ng != nullptr;
+        const int row = (is_a ? blk : blk - nb_a) * 32 + c * 4 + j;   // operand row this thread writes after the transpose
+        const uint32_t dst0 = (is_a ? 0u : 2u * DW_A_BYTES) + (uint32_t)row * 128u;
+        const uint32_t lo_off = is_a ? (uint32_t)DW_A_BYTES : (uint32_t)b_bytes;
+        const uint32_t rsw = (uint32_t)(row & 7);
+        // items (cell groups of 4) per stage: 8 / wpb, processed in batches of <= 4 whose global loads are issued one
+        // batch ahead of their use (software pipeline across batches and stages)
+        const int n_it = 8 / wpb;
+        const int bs = n_it < 4 ? n_it : 4;          // items per batch
+        const int bps = n_it / bs;                   // batches per stage (1 or 2)
+        const int64_t n_batches = my_groups * bps;
+        constexpr int MAXB = 4;
+        struct Batch { float4 r0[MAXB], r1[MAXB]; };
+        const int n_tgt32 = (int)p.n_tgt;            // < 2^31 cells per GPU (checked by the launcher)
+        const int cell_first = (int)(g_begin * DW_CELLS) + j + gsub * 4;
+        const int ustep = wpb * 4;                   // cells between consecutive items of a thread
+        // batch (stage i, half h): first cell = cell_first + i*32 + h*bs*ustep
+        auto load_batch = [&](int tb, bool live, Batch& r) {
+#pragma unroll
+            for (int u = 0; u < MAXB; ++u) {
+                r.r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                r.r1[u] = r.r0[u];
+                if (u < bs && live) {
+                    const int t = tb + u * ustep;
+                    if (t < n_tgt32) {
+                        r.r0[u] = ldg4(src + (size_t)t * stride);
+                        if (norm) r.r1[u] = ldg4(src2 + (size_t)t * stride);
+                    }
+                }
+            }
+        };
+        uint32_t s = 0, ph = 0;
+        Batch cur, nxt;
+        const bool on = kind >= 0;
+        load_batch(cell_first, on && n_batches > 0, cur);
+        int h = 0;
+        int tb = cell_first;                         // first cell of the current batch; hstep to the next one
+        const int hstep = bs * ustep, sstep = DW_CELLS - (bps - 1) * hstep;
+        for (int64_t bi = 0; bi < n_batches; ++bi) {
+            const int tb_next = tb + (h + 1 == bps ? sstep : hstep);
+            load_batch(tb_next, on && bi + 1 < n_batches, nxt);
+            uint8_t* stg = smem + (size_t)s * stage_bytes;
+            if (h == 0) mbar_wait(&bar_empty[s], ph ^ 1);
+#pragma unroll
+            for (int u = 0; u < MAXB; ++u) {
+                if (u < bs) {
+                    const int g = gsub + (h * bs + u) * wpb;
+                    float4 v = cur.r0[u];
+                    if (norm) {
+                        const float4 zv = cur.r1[u];
+                        const bool tv = tb + u * ustep < n_tgt32;  // padding rows must stay zero (k1 != 0)
+                        v.x = tv ? fmaf(k0.x, v.x, -fmaf(zv.x, k2.x, k1.x)) : 0.f;
+                        v.y = tv ? fmaf(k0.y, v.y, -fmaf(zv.y, k2.y, k1.y)) : 0.f;
+                        v.z = tv ? fmaf(k0.z, v.z, -fmaf(zv.z, k2.z, k1.z)) : 0.f;
+                        v.w = tv ? fmaf(k0.w, v.w, -fmaf(zv.w, k2.w, k1.w)) : 0.f;
+                    } else if (affine) {
+                        const bool tv = tb + u * ustep < n_tgt32;
+                        v.x = tv ? act(v.x, k0.x, k1.x, relu) : 0.f; v.y = tv ? act(v.y, k0.y, k1.y, relu) : 0.f;
+                        v.z = tv ? act(v.z, k0.z, k1.z, relu) : 0.f; v.w = tv ? act(v.w, k0.w, k1.w, relu) : 0.f;
+                    } else if (kind == 2 && relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                    v = transpose4(v, j);                   // now: channel `row`, cells 4g .. 4g+3
+                    const uint32_t off = dst0 + ((((uint32_t)g) ^ rsw) << 4);
+                    put_split4(stg + off, stg + off + lo_off, 0u, v);
+                }
+            }
+            tb = tb_next;
+            if (++h == bps) {
+                h = 0;
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[s]);
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+            }
+            cur = nxt;
+        }
+    }
+    if (warp < DW_NPW) {
         // read this CTA's partial out of TMEM
         float* out = p.partials + (size_t)blockIdx.x * p.f_out * p.k_total;
         const int q = warp & 3, grp = warp >> 2;
@@ -223,8 +249,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             tc_fence_after_sync();
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int c0 = (grp + 4 * j) * 32;
+        for (int j = 0; j < 3; ++j) {
+            const int c0 = (grp + 3 * j) * 32;
             if (c0 >= p.np) break;
             float v[32];
             if (my_groups > 0) {
@@ -265,6 +291,7 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
     DGNN_REQUIRE(dgnn_dw_tc_supported(f_out, k_total), "widths not supported by the tensor-core dW kernel");
     DGNN_REQUIRE(k_total == (agg ? 2 * f_in : f_in), "k_total mismatch");
     DGNN_REQUIRE(dy && x_in && partials, "null pointer");
+    DGNN_REQUIRE(n_tgt < (int64_t)1 << 31, "more than 2^31 cells on one GPU");
     DwTcArgs p;
     p.dy = dy; p.z = z; p.ng = g; p.na = a; p.nb = b; p.nmean = mean; p.nrstd = rstd;
     p.agg = agg; p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;
@@ -272,6 +299,9 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
     p.np = ceil32i(k_total);
     p.stages = 2;
     p.partials = partials;
+    const int nb = (f_out + 31) / 32 + p.np / 32;      // operand blocks of 32 channels (<= 12)
+    p.wpb = nb * 4 <= DW_NPW ? 4 : (nb * 2 <= DW_NPW ? 2 : 1);
+    p.active_warps = nb * p.wpb;
     size_t smem = (size_t)p.stages * (2 * DW_A_BYTES + 2 * p.np * 128) + 1024;
     static bool configured = false;
     if (!configured) {

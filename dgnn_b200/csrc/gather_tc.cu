@@ -205,9 +205,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         uint8_t* xw = x_base + (size_t)warp * WSTAGE;                  // + stage * G_NCW * WSTAGE
         const uint32_t swz_l = ((uint32_t)lane / (8 / CH)) & (CH - 1); // chunk swizzle of this thread's row
         const int c_row = lane / CH, c_ch = lane % CH;                 // copy role: row within an instruction, chunk
-        double s1d[CPT / 8], s2d[CPT / 8];             // running (S1, S2) of column c0 + 8*jj + (lane >> 2)
-#pragma unroll
-        for (int i = 0; i < CPT / 8; ++i) s1d[i] = s2d[i] = 0.0;
+        float s1d[CPT / 8], s2d[CPT / 8];              // running (S1, S2) of column c0 + 8*jj + (lane >> 2): per-CTA
+#pragma unroll                                         // share of one column (<= 64 tiles x 32 rows) in fp32, doubles after
+        for (int i = 0; i < CPT / 8; ++i) s1d[i] = s2d[i] = 0.f;
 
         auto tile_of = [&](uint32_t tc) { return (int64_t)blockIdx.x + (int64_t)tc * gridDim.x; };
         auto load_nbr = [&](uint32_t tc) {
@@ -398,25 +398,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                                 const float4 za = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
                                 const float4 zb = fvalid_b ? *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4)) : zero4;
                                 const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                                // ReLU mask of the producer layer; S2 is accumulated as sum(dh * z) and turned into
+                                // sum(dh * xhat) = rstd * (sum(dh * z) - mean * S1) when the CTA partial is written
                                 float sc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, sh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                                float mu[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, rs[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
                                 if (p.p_scale != nullptr) {
                                     float4 a = ldg4(p.p_scale + f0), bq = fvalid_b ? ldg4(p.p_scale + f0 + 4) : zero4;
                                     float4 c = ldg4(p.p_shift + f0), d = fvalid_b ? ldg4(p.p_shift + f0 + 4) : zero4;
                                     sc[0] = a.x; sc[1] = a.y; sc[2] = a.z; sc[3] = a.w; sc[4] = bq.x; sc[5] = bq.y; sc[6] = bq.z; sc[7] = bq.w;
                                     sh[0] = c.x; sh[1] = c.y; sh[2] = c.z; sh[3] = c.w; sh[4] = d.x; sh[5] = d.y; sh[6] = d.z; sh[7] = d.w;
                                 }
-                                if (p.p_mean != nullptr) {
-                                    float4 a = ldg4(p.p_mean + f0), bq = fvalid_b ? ldg4(p.p_mean + f0 + 4) : zero4;
-                                    float4 c = ldg4(p.p_rstd + f0), d = fvalid_b ? ldg4(p.p_rstd + f0 + 4) : zero4;
-                                    mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w; mu[4] = bq.x; mu[5] = bq.y; mu[6] = bq.z; mu[7] = bq.w;
-                                    rs[0] = c.x; rs[1] = c.y; rs[2] = c.z; rs[3] = c.w; rs[4] = d.x; rs[5] = d.y; rs[6] = d.z; rs[7] = d.w;
-                                }
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
                                     if (p.p_relu && !(fmaf(zv[i], sc[i], sh[i]) > 0.f)) a8[i] = 0.f;
                                     if (i >= 4 && !fvalid_b) a8[i] = 0.f;
-                                    dx[i] = a8[i] * ((zv[i] - mu[i]) * rs[i]);
+                                    dx[i] = a8[i] * zv[i];
                                 }
                             }
                             if (p.out != nullptr) {
@@ -431,8 +426,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                             }
                         }
                         if (p.s_partials != nullptr) {
-                            s1d[j >> 3] += (double)warp_colsum8(a8, lane);
-                            s2d[j >> 3] += (double)warp_colsum8(dx, lane);
+                            s1d[j >> 3] += warp_colsum8(a8, lane);
+                            s2d[j >> 3] += warp_colsum8(dx, lane);
                         }
                     }
                 }
@@ -447,8 +442,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             double* mine = reinterpret_cast<double*>(xw);
 #pragma unroll
             for (int jj = 0; jj < CPT / 8; ++jj) {
-                mine[jj * 8 + (lane >> 2)] = s1d[jj];
-                mine[CPT + jj * 8 + (lane >> 2)] = s2d[jj];
+                mine[jj * 8 + (lane >> 2)] = (double)s1d[jj];
+                mine[CPT + jj * 8 + (lane >> 2)] = (double)s2d[jj];
             }
         }
     }
@@ -465,7 +460,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 b2 += w[CPT + cl];
             }
             my[c] = a;
-            my[p.f + c] = b2;
+            const double mu = p.p_mean != nullptr ? (double)__ldg(p.p_mean + c) : 0.0;
+            const double rs = p.p_rstd != nullptr ? (double)__ldg(p.p_rstd + c) : 1.0;
+            my[p.f + c] = rs * (b2 - mu * a);          // sum(dh * xhat), xhat = (z - mean) * rstd
         }
     }
     if (warp == G_NCW) tmem_dealloc(tmem_base, 512);

@@ -123,48 +123,6 @@ __device__ __forceinline__ void produce_rows(const TcArgs& p, uint8_t* a_hi, uin
     }
 }
 
-// warp `w` fills its 8 rows of the atom with dz[row, f0 .. f0+32); column sums go to red_db (shared)
-__device__ __forceinline__ void produce_dz(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int f0,
-                                           int warp, int lane, float* red_db) {
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int c = (lane & 7) * 4;
-    const int f = f0 + c;
-    float4 g = make_float4(1.f, 1.f, 1.f, 1.f), a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, m = a, rs = g;
-    const bool norm = p.ng != nullptr && f < p.f_out;
-    if (norm) { g = ldg4(p.ng + f); a = ldg4(p.na + f); b = ldg4(p.nb + f); m = ldg4(p.nmean + f); rs = ldg4(p.nrstd + f); }
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int r = warp * 8 + (lane >> 3) + it * 4;
-        const int64_t t = tile0 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (t < p.n_tgt && f < p.f_out) {
-            float4 d = ldg4(p.dy + (size_t)t * p.f_out + f);
-            if (norm) {
-                float4 zv = ldg4(p.z + (size_t)t * p.f_out + f);
-                v.x = g.x * d.x - (a.x + (zv.x - m.x) * rs.x * b.x);
-                v.y = g.y * d.y - (a.y + (zv.y - m.y) * rs.y * b.y);
-                v.z = g.z * d.z - (a.z + (zv.z - m.z) * rs.z * b.z);
-                v.w = g.w * d.w - (a.w + (zv.w - m.w) * rs.w * b.w);
-            } else {
-                v = d;
-            }
-            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-        }
-        store_split4(a_hi, a_lo, r, c, v);
-    }
-    if (red_db != nullptr) {
-        // lanes l, l+8, l+16, l+24 share the column group
-        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-        if (lane < 8 && f < p.f_out) {
-            atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
-            atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
-        }
-    }
-}
-
 // ---- two-phase producers (dense / dz): loads are issued one atom ahead of their use -------------------
 struct RawAtom {
     float4 v[2];   // x / agg / dy for the thread's two rows
@@ -196,7 +154,7 @@ __device__ __forceinline__ void load_raw(const TcArgs& p, int64_t tile0, int a, 
 
 template <int MODE>
 __device__ __forceinline__ void store_raw(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int a, int warp,
-                                          int lane, const RawAtom& r, float* red_db) {
+                                          int lane, const RawAtom& r, float* red_db, float4 (&dbacc)[4]) {
     const int c = (lane & 7) * 4;
     if (MODE == MODE_BWD) {
         const int f = a * ATOM_K + c;
@@ -224,13 +182,21 @@ __device__ __forceinline__ void store_raw(const TcArgs& p, uint8_t* a_hi, uint8_
             store_split4(a_hi, a_lo, row, c, v);
         }
         if (red_db != nullptr) {
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-            if (lane < 8 && f < p.f_out) {
-                atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
-                atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
+            if (a < 4) {
+                // column sums of dz (-> db) stay in registers for the first 4 atoms (f_out <= 128): one running
+                // float4 per atom and thread, reduced over rows / warps once at the end of the kernel
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (a == k) { dbacc[k].x += cs.x; dbacc[k].y += cs.y; dbacc[k].z += cs.z; dbacc[k].w += cs.w; }
+            } else {
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+                if (lane < 8 && f < p.f_out) {
+                    atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
+                    atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
+                }
             }
         }
     } else {
@@ -370,15 +336,14 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
 // st_sum / st_sq: per-lane running column sums (chunk slot j = (chunk - grp)/4), kept across tiles
 template <int MODE>
 __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int64_t tile0, int warp, int lane,
-                                         double (&st_sum)[2], double (&st_sq)[2]) {
+                                         double (&st_sum)[2], double (&st_sq)[2], const int4 nb) {
     const int q = warp & 3, grp = warp >> 2;
     const int r = q * 32 + lane;
     const int64_t t = tile0 + r;
     const bool tv = t < p.n_tgt;
     const int n_real = MODE == MODE_BWD ? (p.nbr ? 2 * p.f_in : p.f_in) : p.f_out;
     float icnt = 1.f;
-    if (MODE == MODE_BWD && p.nbr != nullptr && tv) {
-        int4 nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+    if (MODE == MODE_BWD && p.nbr != nullptr && tv) {   // nb = nbr[t], loaded by the caller a tile earlier
         int cnt = (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
         icnt = 1.f / (float)(cnt > 0 ? cnt : 1);
     }
@@ -482,13 +447,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
     if (warp == NPW) {
         // ------------------------------------------------------------------ MMA / TMA warp
         const uint32_t idesc = make_idesc_tf32(TC_M, p.np);
-        uint32_t it = 0, tile_cnt = 0;
+        uint32_t tile_cnt = 0, s = 0, use = 0;       // ring stage and how often it has been used (parity = use & 1)
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
             const uint32_t acc = tile_cnt & 1;
             const uint32_t tmem_acc = tmem_base + acc * (uint32_t)p.np;
-            for (int a = 0; a < p.ka; ++a, ++it) {
-                const uint32_t s = it % (uint32_t)p.stages;
-                const uint32_t use = it / (uint32_t)p.stages;
+            for (int a = 0; a < p.ka; ++a) {
                 if (lane == 0) {
                     uint8_t* st = smem + (size_t)s * stage_bytes;
                     uint8_t* b_hi = st + 2 * A_ATOM_BYTES;
@@ -507,16 +470,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                     if (a == p.ka - 1) mma_commit(&bar_acc_full[acc]);
                 }
                 __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ++use; }
             }
         }
     } else if (warp == NPW + 1) {
         // ------------------------------------------------------------------ TMA warp: weight slices, a ring ahead
-        uint32_t it = 0;
+        uint32_t s = 0, use = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int a = 0; a < p.ka; ++a, ++it) {
+            for (int a = 0; a < p.ka; ++a) {
                 if (lane == 0) {
-                    const uint32_t s = it % (uint32_t)p.stages;
-                    const uint32_t use = it / (uint32_t)p.stages;
                     uint8_t* b_hi = smem + (size_t)s * stage_bytes + 2 * A_ATOM_BYTES;
                     mbar_wait(&bar_empty[s], (use & 1) ^ 1);
                     mbar_arrive_expect_tx(&bar_full[s], 2u * (uint32_t)b_atom_bytes);
@@ -525,20 +487,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                     bulk_g2s(b_hi + b_atom_bytes, src + b_atom_bytes, (uint32_t)b_atom_bytes, &bar_full[s]);
                 }
                 __syncwarp();
+                if (++s == (uint32_t)p.stages) { s = 0; ++use; }
             }
         }
     } else {
         // ------------------------------------------------------------------ producer warps
         double st_sum[2] = {0.0, 0.0}, st_sq[2] = {0.0, 0.0};
-        uint32_t it = 0, tile_cnt = 0;
+        uint32_t tile_cnt = 0, s = 0, use = 0;
         int64_t prev_tile0 = -1;
-        RawAtom cur, nxt;
+        RawAtom cur, nxt;                              // raw rows of the atom being stored / the next one
+        float4 dbacc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dbacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE != MODE_FWD_GATHER && (int64_t)blockIdx.x < n_tiles) load_raw<MODE>(p, (int64_t)blockIdx.x * TC_M, 0, warp, lane, cur);
+        int4 nb_epi = make_int4(-1, -1, -1, -1);
+        auto load_nb_epi = [&](int64_t t0) {           // the epilogue's row of the ELL table (1/cnt of d_agg)
+            if (MODE == MODE_BWD && p.nbr != nullptr) {
+                const int64_t t = t0 + (warp & 3) * 32 + lane;
+                if (t < p.n_tgt) nb_epi = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+            }
+        };
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
             const int64_t tile0 = tile * TC_M;
-            for (int a = 0; a < p.ka; ++a, ++it) {
-                const uint32_t s = it % (uint32_t)p.stages;
-                const uint32_t use = it / (uint32_t)p.stages;
+#ifndef DGNN_NO_NB_PREFETCH
+            if (prev_tile0 >= 0) load_nb_epi(prev_tile0);   // in flight while this tile is produced
+#endif
+            for (int a = 0; a < p.ka; ++a) {
                 uint8_t* a_hi = smem + (size_t)s * stage_bytes;
                 uint8_t* a_lo = a_hi + A_ATOM_BYTES;
                 if (MODE != MODE_FWD_GATHER) {
@@ -552,18 +526,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                     if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
                     else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
                 } else {
-                    store_raw<MODE>(p, a_hi, a_lo, tile0, a, warp, lane, cur, (MODE == MODE_BWD && p.db_partials) ? red_db : nullptr);
+                    store_raw<MODE>(p, a_hi, a_lo, tile0, a, warp, lane, cur, (MODE == MODE_BWD && p.db_partials) ? red_db : nullptr, dbacc);
                     cur = nxt;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_full[s]);
+                if (++s == (uint32_t)p.stages) { s = 0; ++use; }
             }
             if (prev_tile0 >= 0) {
                 const uint32_t pacc = (tile_cnt - 1) & 1;
                 mbar_wait(&bar_acc_full[pacc], ((tile_cnt - 1) >> 1) & 1);
                 tc_fence_after_sync();
-                epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq);
+#ifdef DGNN_NO_NB_PREFETCH
+                load_nb_epi(prev_tile0);
+#endif
+                epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq, nb_epi);
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_acc_free[pacc]);
@@ -572,9 +550,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
         }
         if (prev_tile0 >= 0) {
             const uint32_t pacc = (tile_cnt - 1) & 1;
+            load_nb_epi(prev_tile0);
             mbar_wait(&bar_acc_full[pacc], ((tile_cnt - 1) >> 1) & 1);
             tc_fence_after_sync();
-            epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq);
+            epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq, nb_epi);
+        }
+        if (MODE == MODE_BWD && p.db_partials != nullptr) {
+            const int c = (lane & 7) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float4 cs = dbacc[k];
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+                const int f = k * ATOM_K + c;
+                if (lane < 8 && f < p.f_out) {
+                    atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
+                    atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
+                }
+            }
         }
         if (MODE != MODE_BWD && p.stats != nullptr) {
             const int grp = warp >> 2;
