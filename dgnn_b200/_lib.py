@@ -32,6 +32,7 @@ SIGNATURES = {
     "dgnn_gather_rows": [P, P, L, I, P, P],
     "dgnn_scatter_rows": [P, P, L, I, P, P],
     "dgnn_edge_relayout": [P, P, P, P, L, I, P, P, P],
+    "dgnn_edge_relayout_idx": [P, P, P, P, P, L, I, P, P, P],
     "dgnn_layer_grid": [I, I],
     "dgnn_layer_fwd": [P, P, P, I, P, P, I, P, P, P, P, P, P, I, L, I, I, P, P, P, P],
     "dgnn_tc_supported": [I, I, I],

@@ -139,9 +139,11 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const int32_t
     }
 }
 
-__global__ void edge_relayout_kernel(const float* __restrict__ ea, const int32_t* __restrict__ nbr,
-                                     const uint8_t* __restrict__ rslot, const int32_t* __restrict__ perm, long long n,
-                                     int fe4, float* __restrict__ ea_in, float* __restrict__ ea_own) {
+// e_id (nullable): row r of the edge list is row e_id[r] of `ea` (data.all.edge_attr[e_id] without materialising it)
+__global__ void edge_relayout_kernel(const float* __restrict__ ea, const long long* __restrict__ e_id,
+                                     const int32_t* __restrict__ nbr, const uint8_t* __restrict__ rslot,
+                                     const int32_t* __restrict__ perm, long long n, int fe4,
+                                     float* __restrict__ ea_in, float* __restrict__ ea_own) {
     const long long total = n * 4 * fe4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long row = i / fe4;  // new*4 + k
@@ -149,11 +151,17 @@ __global__ void edge_relayout_kernel(const float* __restrict__ ea, const int32_t
         long long nw = row >> 2;
         int k = (int)(row & 3);
         long long old = perm ? perm[nw] : nw;
-        if (ea_own) reinterpret_cast<float4*>(ea_own)[i] = __ldg(reinterpret_cast<const float4*>(ea) + (old * 4 + k) * fe4 + c);
+        if (ea_own) {
+            long long r = old * 4 + k;
+            if (e_id) r = e_id[r];
+            reinterpret_cast<float4*>(ea_own)[i] = __ldg(reinterpret_cast<const float4*>(ea) + r * fe4 + c);
+        }
         if (ea_in) {
             long long s = nbr[old * 4 + k];
             int rs = rslot[old * 4 + k];
-            reinterpret_cast<float4*>(ea_in)[i] = __ldg(reinterpret_cast<const float4*>(ea) + (s * 4 + rs) * fe4 + c);
+            long long r = s * 4 + rs;
+            if (e_id) r = e_id[r];
+            reinterpret_cast<float4*>(ea_in)[i] = __ldg(reinterpret_cast<const float4*>(ea) + r * fe4 + c);
         }
     }
 }
@@ -232,6 +240,17 @@ extern "C" int dgnn_edge_relayout(const float* ea, const int32_t* nbr, const uin
     DGNN_REQUIRE(fe % 4 == 0, "edge feature width must be a multiple of 4");
     DGNN_REQUIRE(!ea_in || (nbr && rslot), "incoming order needs nbr and rslot");
     if (n <= 0) return 0;
-    edge_relayout_kernel<<<ggrid(n * fe), 256, 0, as_stream(stream)>>>(ea, nbr, rslot, perm, n, fe / 4, ea_in, ea_own);
+    edge_relayout_kernel<<<ggrid(n * fe), 256, 0, as_stream(stream)>>>(ea, nullptr, nbr, rslot, perm, n, fe / 4, ea_in, ea_own);
     return check_launch("dgnn_edge_relayout");
+}
+
+extern "C" int dgnn_edge_relayout_idx(const float* ea, const int64_t* e_id, const int32_t* nbr, const uint8_t* rslot,
+                                      const int32_t* perm, int64_t n, int fe, float* ea_in, float* ea_own,
+                                      void* stream) {
+    DGNN_REQUIRE(fe % 4 == 0, "edge feature width must be a multiple of 4");
+    DGNN_REQUIRE(!ea_in || (nbr && rslot), "incoming order needs nbr and rslot");
+    if (n <= 0) return 0;
+    edge_relayout_kernel<<<ggrid(n * fe), 256, 0, as_stream(stream)>>>(ea, (const long long*)e_id, nbr, rslot, perm, n,
+                                                                       fe / 4, ea_in, ea_own);
+    return check_launch("dgnn_edge_relayout_idx");
 }

@@ -110,16 +110,21 @@ def locality_order(edge_index_cpu: Optional[torch.Tensor], n: int, pos: Optional
 
 def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], n: int, device,
                      pos: Optional[torch.Tensor] = None, order: str = "auto",
-                     need_backward: bool = True) -> EllGraph:
+                     need_backward: bool = True, e_id: Optional[torch.Tensor] = None) -> EllGraph:
     """Whole-graph layout (inference, or training on whole graphs).
 
     ``order``: "auto" (Morton if ``pos`` else RCM), "morton", "rcm", "none".
+    ``e_id`` (int64[4n], optional): edge r of the graph carries row ``e_id[r]`` of ``edge_attr``; the selection
+    is fused into the re-layout kernel instead of materialising ``edge_attr[e_id]``.
     """
     dev = torch.device(device)
     _lib.check_device(dev.index or 0)
     fe = 0 if edge_attr is None else pad4(edge_attr.shape[1])
+    if e_id is not None and edge_attr is not None and (edge_attr.shape[1] % 4 or not edge_attr.is_contiguous()
+                                                       or edge_attr.dtype != torch.float32):
+        edge_attr, e_id = edge_attr.to(dev)[e_id.to(dev)], None      # odd widths: select first, pad below
     if not is_reference_layout(edge_index, n):
-        g = build_from_edges(edge_index.to(dev), None, edge_attr, n, n, dev, need_backward)
+        g = build_from_edges(edge_index.to(dev), e_id, edge_attr, n, n, dev, need_backward)
         return g
     st = _stream()
     adj = edge_index.t().to(torch.int32).contiguous().to(dev)  # [4n,2] == adjacencies.npz layout
@@ -129,7 +134,7 @@ def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor]
     call("dgnn_ell_from_adjacency", ptr(adj), n, ptr(nbr0), ptr(rslot), ptr(err), st)
     code = int(err.item())
     if code == 2:  # not symmetric: the generic edge-list builder handles it
-        return build_from_edges(edge_index.to(dev), None, edge_attr, n, n, dev, need_backward)
+        return build_from_edges(edge_index.to(dev), e_id, edge_attr, n, n, dev, need_backward)
     if code != 0:
         raise _lib.DgnnError("dgnn_ell_from_adjacency: malformed adjacency (code %d)" % code)
     perm = None
@@ -151,10 +156,16 @@ def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor]
     if edge_attr is not None:
         ea = pad_cols(edge_attr.to(dev, dtype=torch.float32), fe)
         ea_in = torch.empty((n, 4, fe), dtype=torch.float32, device=dev)
+        own_copy = need_backward and (perm is not None or e_id is not None)
         if need_backward:
-            ea_own = torch.empty((n, 4, fe), dtype=torch.float32, device=dev) if perm is not None else ea.view(n, 4, fe)
-        call("dgnn_edge_relayout", ptr(ea), ptr(nbr0), ptr(rslot), ptr(perm), n, fe, ptr(ea_in),
-             ptr(ea_own) if (need_backward and perm is not None) else None, st)
+            ea_own = torch.empty((n, 4, fe), dtype=torch.float32, device=dev) if own_copy else ea.view(n, 4, fe)
+        if e_id is not None:
+            eid = e_id.to(dev, dtype=torch.int64).contiguous()
+            call("dgnn_edge_relayout_idx", ptr(ea), ptr(eid), ptr(nbr0), ptr(rslot), ptr(perm), n, fe, ptr(ea_in),
+                 ptr(ea_own) if own_copy else None, st)
+        else:
+            call("dgnn_edge_relayout", ptr(ea), ptr(nbr0), ptr(rslot), ptr(perm), n, fe, ptr(ea_in),
+                 ptr(ea_own) if own_copy else None, st)
     return EllGraph(n_src=n, n_tgt=n, fe=fe, nbr=nbr, ea_in=ea_in, onbr=nbr if need_backward else None,
                     ea_own=ea_own, perm=perm, inv=inv)
 

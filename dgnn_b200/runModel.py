@@ -109,6 +109,56 @@ def interface_facets(labels_finite, nfacets):
     return flag
 
 
+class BatchPrefetcher:
+    """Host -> device staging of training batches on a copy stream, one batch ahead of the compute stream
+    (what ``DataLoader(pin_memory=True)`` + ``non_blocking`` copies give the reference trainer).
+
+        pf = BatchPrefetcher(device)
+        pf.put(host_batch)                      # async upload of the first batch
+        for nxt in batches[1:] + [None]:
+            cur = pf.get()                      # device-resident batch; the compute stream waits for its copy
+            if nxt is not None: pf.put(nxt)     # next upload overlaps this step
+            logits = model(cur); ...
+
+    Tensors shared inside a batch (the same ``edge_index`` in every ``batch_adjs`` entry) are uploaded once and
+    stay shared, so the whole-graph fast path of ``SurfaceNet.forward`` still recognises them."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pending = None
+
+    def _upload(self, obj, memo):
+        if torch.is_tensor(obj):
+            key = id(obj)
+            if key not in memo:
+                memo[key] = obj.to(self.device, non_blocking=True)
+            return memo[key]
+        if isinstance(obj, dict):
+            return type(obj)({k: self._upload(v, memo) for k, v in obj.items()})
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._upload(v, memo) for v in obj)
+        return obj
+
+    def put(self, host_batch):
+        with torch.cuda.stream(self.stream):
+            memo = {}
+            dev_batch = self._upload(host_batch, memo)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (dev_batch, ev, list(memo.values()))
+
+    def get(self):
+        dev_batch, ev, tensors = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in tensors:                       # allocated on the copy stream, consumed on the compute stream
+            if t.is_cuda:
+                t.record_stream(cur)
+        return dev_batch
+
+
 class Adam(torch.optim.Optimizer):
     """``torch.optim.Adam(params, lr)`` with the reference's defaults (``runModel.py:290``), all
     parameter tensors updated by ONE kernel launch (``dgnn_adam_multi``)."""

@@ -235,10 +235,10 @@ class SurfaceNet(nn.Module):
             def build():
                 if full:
                     ei, e_id, size = adjs[0]
-                    ea = ea_all.to(dev, non_blocking=True)[e_id.to(dev)] if ea_all is not None else None
+                    ea = ea_all.to(dev, non_blocking=True) if ea_all is not None else None
                     pos = getattr(data.all, "pos", None)
                     pos = pos[n_id.to(pos.device)] if pos is not None else None
-                    g = build_full_graph(ei, ea, size[0], dev, pos=pos, order="auto")
+                    g = build_full_graph(ei, ea, size[0], dev, pos=pos, order="auto", e_id=e_id)
                     return [g] * self.num_layers
                 return [build_from_edges(ei, e_id, ea_all, size[0], size[1], dev) for (ei, e_id, size) in adjs]
 

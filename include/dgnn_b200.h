@@ -74,6 +74,11 @@ int dgnn_scatter_rows(const float* src, const int32_t* idx, int64_t n_rows, int 
 int dgnn_edge_relayout(const float* ea, const int32_t* nbr, const uint8_t* rslot,
                        const int32_t* perm, int64_t n, int fe, float* ea_in, float* ea_own,
                        void* stream);
+/* Same with the batch's edge selection fused in: edge r of the batch is row e_id[r] of `ea`
+ * (data.all.edge_attr[e_id], Static:217; e_id int64[4n], NULL = identity). */
+int dgnn_edge_relayout_idx(const float* ea, const int64_t* e_id, const int32_t* nbr, const uint8_t* rslot,
+                           const int32_t* perm, int64_t n, int fe, float* ea_in, float* ea_own,
+                           void* stream);
 
 /* ---- one message-passing layer, forward (Static:66-96 + norm/ReLU of the producer) ------
  * For target row t < n_tgt (targets are the first n_tgt source rows):
