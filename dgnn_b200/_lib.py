@@ -59,6 +59,8 @@ SIGNATURES = {
     "dgnn_kl_loss_fwd": [P, P, I, P, I, I, L, P, P],
     "dgnn_kl_loss_finalize": [P, I, P, P],
     "dgnn_kl_loss_bwd": [P, P, I, P, I, I, L, P, P, P, P],
+    "dgnn_point_loss_fwd": [P, P, I, P, I, I, I, L, P, P],
+    "dgnn_point_loss_bwd": [P, P, I, P, I, I, I, L, P, P, P, P],
     "dgnn_edge_reg_fwd": [P, P, P, L, P, P],
     "dgnn_rowdot_bwd": [P, P, P, P, P, P, I, P, L, I, I, P, P, P],
     "dgnn_act_bwd": [P, P, P, P, P, P, I, L, I, P, P, P],

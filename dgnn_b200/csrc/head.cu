@@ -223,6 +223,43 @@ __global__ void __launch_bounds__(256) kl_loss_bwd_kernel(const float* __restric
     }
 }
 
+// ---- bce / mse on one logit per cell (runModel.py:181-188) ----------------------------------------
+//   kind 0 (bce): l_r = BCEWithLogits(z_r, y_r) = max(z,0) - z*y + log(1 + exp(-|z|)), weighted like kl
+//   kind 1 (mse): F.mse_loss(sigmoid(z), y) is already the mean over cells; the reference multiplies that scalar by
+//                 the weights and divides by their sum again, so the weights cancel: partials = (sum sq, count)
+__global__ void __launch_bounds__(256) point_loss_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                                                             int ys, const float* __restrict__ w, int ws, int mode,
+                                                             int kind, long long n, double* __restrict__ partials) {
+    double sl = 0.0, sw = 0.0;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const float zv = z[r], yv = y[r * ys];
+        if (kind == 0) {
+            const float l = fmaxf(zv, 0.f) - zv * yv + log1pf(expf(-fabsf(zv)));
+            const float wv = weight_of(w ? w[r * ws] : 1.f, w ? mode : 3);
+            sl += (double)(l * wv);
+            sw += (double)wv;
+        } else {
+            const float d = 1.f / (1.f + expf(-zv)) - yv;
+            sl += (double)(d * d);
+            sw += 1.0;
+        }
+    }
+    block_sum2(sl, sw, partials + 2 * blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) point_loss_bwd_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                                                             int ys, const float* __restrict__ w, int ws, int mode,
+                                                             int kind, long long n, const float* __restrict__ sums,
+                                                             const float* __restrict__ gout, float* __restrict__ dz) {
+    const float g = (gout ? gout[0] : 1.f) / sums[2];
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const float zv = z[r], yv = y[r * ys];
+        const float sg = 1.f / (1.f + expf(-zv));
+        if (kind == 0) dz[r] = g * weight_of(w ? w[r * ws] : 1.f, w ? mode : 3) * (sg - yv);
+        else dz[r] = g * 2.f * (sg - yv) * sg * (1.f - sg);
+    }
+}
+
 __global__ void __launch_bounds__(256) edge_reg_kernel(const float* __restrict__ z, const long long* __restrict__ src,
                                                        const long long* __restrict__ tgt, long long ne,
                                                        double* __restrict__ partials) {
@@ -471,6 +508,22 @@ extern "C" int dgnn_kl_loss_bwd(const float* logits, const float* y, int y_strid
     kl_loss_bwd_kernel<<<grid_for(n, 256, sm_count() * 8), 256, 0, as_stream(stream)>>>(
         logits, y, y_stride, w, w_stride, weight_mode, n, sums, grad_out, dlogits);
     return check_launch("dgnn_kl_loss_bwd");
+}
+extern "C" int dgnn_point_loss_fwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
+                                   int weight_mode, int kind, int64_t n, double* partials, void* stream) {
+    DGNN_REQUIRE(logits && y && partials, "null pointer");
+    DGNN_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (bce) or 1 (mse)");
+    point_loss_fwd_kernel<<<dgnn_small_grid(), 256, 0, as_stream(stream)>>>(logits, y, y_stride, w, w_stride, weight_mode,
+                                                                           kind, n, partials);
+    return check_launch("dgnn_point_loss_fwd");
+}
+extern "C" int dgnn_point_loss_bwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
+                                   int weight_mode, int kind, int64_t n, const float* sums, const float* grad_out,
+                                   float* dlogits, void* stream) {
+    if (n <= 0) return 0;
+    point_loss_bwd_kernel<<<grid_for(n, 256, sm_count() * 8), 256, 0, as_stream(stream)>>>(
+        logits, y, y_stride, w, w_stride, weight_mode, kind, n, sums, grad_out, dlogits);
+    return check_launch("dgnn_point_loss_bwd");
 }
 extern "C" int dgnn_edge_reg_fwd(const float* logits, const int64_t* src, const int64_t* tgt, int64_t n_edges,
                                  double* partials, void* stream) {

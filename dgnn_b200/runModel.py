@@ -60,14 +60,50 @@ class _KLCellLoss(torch.autograd.Function):
         return d, None, None, None, None, None
 
 
+class _PointCellLoss(torch.autograd.Function):
+    """bce / mse on one logit per cell (``runModel.py:181-188``)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, weight, mode, kind, group=None, distributed=False):
+        n = logits.shape[0]
+        dev = logits.device
+        z = logits.reshape(-1).contiguous()
+        grid = lib().dgnn_small_grid()
+        part = torch.empty((grid, 2), dtype=torch.float64, device=dev)
+        call("dgnn_point_loss_fwd", ptr(z), ptr(target), target.stride(0), ptr(weight) if weight is not None else None,
+             weight.stride(0) if weight is not None else 0, mode, kind, n, ptr(part), _stream())
+        if distributed:
+            import torch.distributed as dist
+            part = part.sum(dim=0, keepdim=True).contiguous()
+            dist.all_reduce(part, group=group)
+            grid = 1
+        sums = torch.empty(3, dtype=torch.float32, device=dev)
+        call("dgnn_kl_loss_finalize", ptr(part), grid, ptr(sums), _stream())
+        ctx.save_for_backward(z, target, sums)
+        ctx.weight, ctx.mode, ctx.kind, ctx.shape = weight, mode, kind, logits.shape
+        ctx.mark_non_differentiable(sums)
+        return sums[0].clone(), sums
+
+    @staticmethod
+    def backward(ctx, gout, _gs):
+        z, target, sums = ctx.saved_tensors
+        weight = ctx.weight
+        d = torch.empty_like(z)
+        gout = gout.contiguous().to(torch.float32)
+        call("dgnn_point_loss_bwd", ptr(z), ptr(target), target.stride(0), ptr(weight) if weight is not None else None,
+             weight.stride(0) if weight is not None else 0, ctx.mode, ctx.kind, z.shape[0], ptr(sums), ptr(gout), ptr(d),
+             _stream())
+        return d.view(ctx.shape), None, None, None, None, None, None
+
+
 def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False, group=None, distributed=False):
     """``Trainer.calcLossAndOA`` (kl): ``batch_gt[:, :2]`` targets, ``batch_x[:, 0]`` raw volume.
     ``batch_gt`` / ``batch_x`` may live on the host; they are moved to ``logits.device``.
     ``distributed``: the rows are one rank's share of a partitioned scene; the value returned is the loss over
     the cells of all ranks of ``group`` (numerator and normaliser all-reduced)."""
-    if clf.training.loss != "kl":
-        raise NotImplementedError("only the 'kl' loss of the shipped configs has a CUDA kernel (got %r)"
-                                  % clf.training.loss)
+    kind = clf.training.loss
+    if kind not in ("kl", "bce", "mse"):
+        raise ValueError("%r is not a valid loss. choose either kl, bce or mse" % (kind,))   # runModel.py:189-191
     dev = logits.device
     gt = batch_gt.to(dev, dtype=torch.float32)
     if gt.stride(1) != 1:
@@ -78,7 +114,11 @@ def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False, group=None, dis
         mode = _WEIGHT_MODE[clf.regularization.cell_norm]
     else:
         w, mode = None, 3
-    loss, sums = _KLCellLoss.apply(logits, gt, w, mode, group, distributed)
+    if kind == "kl":
+        loss, sums = _KLCellLoss.apply(logits, gt, w, mode, group, distributed)
+    else:      # bce supervises with the graph-cut label gt[:, 3], mse with the inside percentage gt[:, 0]
+        target = gt[:, 3] if kind == "bce" else gt[:, 0]
+        loss, sums = _PointCellLoss.apply(logits, target, w, mode, 0 if kind == "bce" else 1, group, distributed)
     return (loss, sums) if return_sums else loss
 
 

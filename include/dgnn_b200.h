@@ -214,6 +214,14 @@ int dgnn_kl_loss_finalize(const double* partials, int n_partials, float* out, vo
 int dgnn_kl_loss_bwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
                      int weight_mode, int64_t n, const float* sums, const float* grad_out,
                      float* dlogits, void* stream);
+/* runModel.py:181-188, one logit per cell: kind 0 = bce (BCEWithLogits against y, weighted like kl),
+ * kind 1 = mse (mean of (sigmoid(z) - y)^2; the reference's weights cancel).  partials double[dgnn_small_grid(), 2]
+ * = (numerator, normaliser), finalised by dgnn_kl_loss_finalize; y / w are strided columns. */
+int dgnn_point_loss_fwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
+                        int weight_mode, int kind, int64_t n, double* partials, void* stream);
+int dgnn_point_loss_bwd(const float* logits, const float* y, int y_stride, const float* w, int w_stride,
+                        int weight_mode, int kind, int64_t n, const float* sums, const float* grad_out,
+                        float* dlogits, void* stream);
 /* runModel.py:109-160: partial sums of |p0[src]-p0[tgt]| over an edge list (int64) */
 int dgnn_edge_reg_fwd(const float* logits, const int64_t* src, const int64_t* tgt, int64_t n_edges,
                       double* partials, void* stream);

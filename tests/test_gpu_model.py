@@ -75,7 +75,8 @@ def _train_compare(clf_kwargs, data, d, n_sup_rows, seed=0, loss_kwargs=None):
     zr = ref(data)
     gt = d.y[data.batch_n_id[:n_sup_rows]]
     bx = d.x[data.batch_n_id[:n_sup_rows]]
-    lr, _, _ = otr.cell_loss(zr, gt, bx[:, 0], "kl", clf.regularization.cell_norm, clf.regularization.cell_type)
+    lr, _, _ = otr.cell_loss(zr, gt, bx[:, 0], clf.training.loss, clf.regularization.cell_norm,
+                             clf.regularization.cell_type)
     lr.backward()
     z = net(data)
     assert z.requires_grad and z.shape == zr.shape
@@ -94,6 +95,17 @@ def _train_compare(clf_kwargs, data, d, n_sup_rows, seed=0, loss_kwargs=None):
         rb = dict(ref.named_buffers())[k]
         np.testing.assert_allclose(b.cpu().numpy(), rb.numpy(), rtol=2e-4, atol=1e-6, err_msg=k)
     return net, ref
+
+
+@pytest.mark.parametrize("loss", ["bce", "mse"])
+def test_train_single_logit_losses(loss):
+    """Row S: the bce / mse branches of calcLossAndOA (one logit per cell, runModel.py:181-188) through a whole
+    train step: logits, loss value and every gradient against the oracle."""
+    g = make_graph(500, seed=27)
+    d = data_all(g)
+    # batch_gt columns: inside %, outside %, (unused), graph-cut label
+    d.y = torch.cat([d.y, torch.zeros(d.y.shape[0], 1), (d.y[:, :1] > d.y[:, 1:2]).float()], dim=1)
+    _train_compare(dict(convs=(16, 32, 32, 32), loss=loss), full_batch(d), d, d.x.shape[0])
 
 
 def test_train_full_graph_kf96_widths():
