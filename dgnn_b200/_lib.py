@@ -31,6 +31,7 @@ SIGNATURES = {
     "dgnn_perm_apply_ell": [P, P, P, L, P, P],
     "dgnn_gather_rows": [P, P, L, I, P, P],
     "dgnn_scatter_rows": [P, P, L, I, P, P],
+    "dgnn_add_rows": [P, P, L, I, P, P],
     "dgnn_edge_relayout": [P, P, P, P, L, I, P, P, P],
     "dgnn_edge_relayout_idx": [P, P, P, P, P, L, I, P, P, P],
     "dgnn_layer_grid": [I, I],

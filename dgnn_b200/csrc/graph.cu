@@ -140,6 +140,21 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const int32_t
 }
 
 // e_id (nullable): row r of the edge list is row e_id[r] of `ea` (data.all.edge_attr[e_id] without materialising it)
+// dst[idx[r],:] += src[r,:]; the indices of one call must be distinct (one peer's boundary list)
+__global__ void add_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, long long n_rows,
+                                int row4, float* __restrict__ dst) {
+    const long long total = n_rows * row4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / row4;
+        int c = (int)(i % row4);
+        int d = idx[r];
+        if (d < 0) continue;
+        float4* o = reinterpret_cast<float4*>(dst) + (long long)d * row4 + c;
+        const float4 a = *o, b = __ldg(reinterpret_cast<const float4*>(src) + i);
+        *o = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
 __global__ void edge_relayout_kernel(const float* __restrict__ ea, const long long* __restrict__ e_id,
                                      const int32_t* __restrict__ nbr, const uint8_t* __restrict__ rslot,
                                      const int32_t* __restrict__ perm, long long n, int fe4,
@@ -233,6 +248,14 @@ extern "C" int dgnn_scatter_rows(const float* src, const int32_t* idx, int64_t n
     if (n_rows <= 0) return 0;
     scatter_rows_kernel<<<ggrid(n_rows * (row_floats / 4)), 256, 0, as_stream(stream)>>>(src, idx, n_rows, row_floats / 4, dst);
     return check_launch("dgnn_scatter_rows");
+}
+
+extern "C" int dgnn_add_rows(const float* src, const int32_t* idx, int64_t n_rows, int row_floats, float* dst,
+                             void* stream) {
+    DGNN_REQUIRE(row_floats % 4 == 0, "row length must be a multiple of 4 floats");
+    if (n_rows <= 0) return 0;
+    add_rows_kernel<<<ggrid(n_rows * (row_floats / 4)), 256, 0, as_stream(stream)>>>(src, idx, n_rows, row_floats / 4, dst);
+    return check_launch("dgnn_add_rows");
 }
 
 extern "C" int dgnn_edge_relayout(const float* ea, const int32_t* nbr, const uint8_t* rslot, const int32_t* perm,

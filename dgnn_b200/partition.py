@@ -101,6 +101,33 @@ class HaloComm:
             dist.all_reduce(t, group=self.group)
         return t
 
+    def reverse_add(self, d: torch.Tensor) -> None:
+        """The mirror of ``exchange`` for gradients that were accumulated on the SOURCE side: the halo rows
+        ``d[n_own:]`` hold this rank's contributions to cells owned by peers; they travel back to their owners and are
+        added to the owners' rows (one peer at a time, fixed order: deterministic, no atomics)."""
+        m = self.maps
+        if m.world == 1:
+            return
+        f = d.shape[1]
+        n_back = int(m.send_idx.numel())
+        back = torch.empty((n_back, f), dtype=d.dtype, device=d.device)
+        dist.all_to_all_single(back, d[m.n_own:].contiguous(), output_split_sizes=m.send_counts,
+                               input_split_sizes=m.recv_counts, group=self.group)
+        if d.is_cuda:
+            from ._lib import call, ptr
+            st = torch.cuda.current_stream().cuda_stream
+            o = 0
+            for q, c in enumerate(m.send_counts):
+                if c:
+                    call("dgnn_add_rows", ptr(back[o:o + c]), ptr(m.send_idx[o:o + c]), c, f, ptr(d), st)
+                o += c
+        else:  # host logic of the CPU tests (gloo)
+            o = 0
+            for c in m.send_counts:
+                if c:
+                    d.index_add_(0, m.send_idx[o:o + c].long(), back[o:o + c])
+                o += c
+
 
 def _local_plan(net, data_all, world, rank, need_backward):
     """Replicated graph build (Morton order), then this rank's [owned | halo] slice of it."""
@@ -179,6 +206,60 @@ class PartitionedTraining:
         for p in ps:
             p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
             o += p.numel()
+
+
+class PartitionedUpdatedTraining:
+    """BASELINE configs[3]: the Updated-edge-filter model trained on ONE scene sharded over the ranks.  The edge
+    state of an edge lives with its target cell, so it never crosses the partition; node activations are exchanged
+    forward (halo rows) and the gradients of halo sources travel back to their owners (``HaloComm.reverse_add``).
+
+        pt = PartitionedUpdatedTraining(model)          # dgnn_b200.surfaceNetUpdatedEdgeFilters.SurfaceNet
+        ids, out = pt.forward(data_all)                 # data_all: x, edge_index, edge_attr[, pos] of the whole scene
+        loss = ...(out, targets[ids]); loss.backward(); pt.allreduce_gradients(); optimizer.step()
+    """
+
+    def __init__(self, model, group=None):
+        self.model = model
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._plan = None
+
+    def prepare(self, data_all):
+        from .graph import build_full_graph
+        from .surfaceNetUpdatedEdgeFilters import AttrView
+        net = self.model
+        dev = torch.device(net.clf.temp.device)
+        n = data_all.x.shape[0]
+        pos = getattr(data_all, "pos", None)
+        full = build_full_graph(data_all.edge_index.to(torch.long), data_all.edge_attr, n, dev, pos=pos, order="auto",
+                                need_backward=False)
+        maps = build_halo_maps(full.nbr, partition_bounds(n, self.world), self.rank)
+        lo, hi, n_own, n_src = maps.lo, maps.hi, maps.n_own, maps.n_own + maps.n_halo
+        # local edge list: edge 4t+k runs from local_nbr[t,k] (in [owned | halo]) into owned target t
+        tgt = torch.arange(n_own, device=dev).repeat_interleave(4)
+        src = maps.local_nbr.reshape(-1).long()
+        ei = torch.stack([src, tgt])
+        e_loc = 4 * n_own
+        fe_raw = data_all.edge_attr.shape[1]
+        ea_loc = full.ea_in[lo:hi].reshape(e_loc, -1)[:, :fe_raw].contiguous()
+        rows = torch.cat([torch.arange(lo, hi, device=dev), maps.halo_gid.to(dev)])
+        x_dev = data_all.x.to(dev, dtype=torch.float32)
+        x_loc = (x_dev[full.perm.long()] if full.perm is not None else x_dev).index_select(0, rows).contiguous()
+        adj = (ei, torch.arange(e_loc, device=dev), (n_src, n_own))
+        local = AttrView(x=x_loc, n_id=torch.arange(n_src, device=dev), adjs=[adj] * net.num_layers, edge_attr=ea_loc)
+        ids = full.perm[lo:hi].long() if full.perm is not None else torch.arange(lo, hi, device=dev)
+        self._plan = (local, maps, ids, HaloComm(maps, n, self.group))
+        return self._plan
+
+    def forward(self, data_all):
+        if self._plan is None:
+            self.prepare(data_all)
+        local, maps, ids, comm = self._plan
+        return ids, self.model(local, comm=comm)
+
+    def allreduce_gradients(self):
+        PartitionedTraining.allreduce_gradients(self)
 
 
 class PartitionedInference:

@@ -48,10 +48,11 @@ class SAGEConv(nn.Module):
                                                                     self.edge_in_channels, self.in_channels, self.out_channels)
 
 
-def _dense(x_in, relu_in, w, bias, n, f_in, f_out, agg=None):
-    """z = [agg | relu?(x_in)] . w^T + bias on the device (tensor cores when the widths allow)."""
+def _dense(x_in, relu_in, w, bias, n, f_in, f_out, agg=None, out_rows=None):
+    """z = [agg | relu?(x_in)] . w^T + bias on the device (tensor cores when the widths allow).
+    ``out_rows`` > n leaves room behind the result for the halo rows of a partitioned scene."""
     dev = x_in.device
-    out = torch.empty((n, f_out), dtype=torch.float32, device=dev)
+    out = torch.empty((out_rows or n, f_out), dtype=torch.float32, device=dev)
     if engine.use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 0) and f_out % 4 == 0:
         bp = engine.pack_b(w, f_out, f_in, 2 if agg is not None else 1)
         call("dgnn_dense_fwd_tc", ptr(agg), ptr(x_in), None, None, int(relu_in), ptr(bp), ptr(bias), None, None, 0, n,
@@ -92,7 +93,9 @@ class SurfaceNet(nn.Module):
     def _has_head(self):
         return self.clf.training.model_name[-1] == "+"
 
-    def forward(self, data_all):
+    def forward(self, data_all, comm=None):
+        """``comm`` (``dgnn_b200.partition.HaloComm``, optional): ``data_all`` is one rank's [owned | halo] share of
+        a partitioned scene; activations cross the partition boundary forward and gradients backward."""
         dev = torch.device(self.clf.temp.device)
         if dev.type != "cuda":
             raise DgnnError("dgnn_b200 has no CPU path: clf.temp.device must be a CUDA (sm_100) device")
@@ -108,15 +111,22 @@ class SurfaceNet(nn.Module):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         with torch.cuda.device(dev):
             if not need_grad:
-                return _forward(self, data_all, dev, None)
-            return _UpdFn.apply(self, data_all, dev, *params)
+                return _forward(self, data_all, dev, None, comm)
+            return _UpdFn.apply(self, data_all, dev, comm, *params)
 
 
 class _Saved:
     pass
 
 
-def _forward(net, data_all, dev, sv):
+class AttrView:
+    """Minimal attribute container for a ``data_all`` built by this package (x, n_id, adjs, edge_attr)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _forward(net, data_all, dev, sv, comm=None):
     """Forward on the device; ``sv`` (a list) receives what the backward needs, one entry per layer."""
     f = net.clf.features
     cols = slice(1, None) if (f.normalization_feature and not f.keep_normalization_feature) else slice(None)
@@ -146,7 +156,11 @@ def _forward(net, data_all, dev, sv):
              _stream())
         w_cat = torch.cat([engine._pad2(conv.lin_l.weight.detach(), fo, fi),
                            engine._pad2(conv.lin_r.weight.detach(), fo, fi)], dim=1).contiguous()
-        out = _dense(x, relu_in, w_cat, conv.lin_l.bias.detach().contiguous(), n_tgt, fi, fo, agg=agg)
+        halo = comm is not None and i + 1 < len(net.convs)
+        out = _dense(x, relu_in, w_cat, conv.lin_l.bias.detach().contiguous(), n_tgt, fi, fo, agg=agg,
+                     out_rows=size[0] if halo else None)
+        if halo:
+            comm.exchange(out)                 # rows n_tgt.. = the owners' outputs of the halo cells
         if sv is not None:
             s = _Saved()
             s.g, s.eid_glob, s.ea, s.phi, s.agg, s.x_in, s.out = g, eid_glob, ea, e_new, agg, x, out
@@ -165,7 +179,7 @@ def _forward(net, data_all, dev, sv):
         call("dgnn_scatter_rows", ptr(e_new), ptr(eid_glob), n_tgt * 4, fi, ptr(e_state), _stream())
         relu_in = True                                                        # x, e <- relu (applied on load)
     if net._has_head():
-        n = x.shape[0]
+        n = data_all.adjs[len(net.convs) - 1][2][1]
         w1 = net.out_net[1].weight.detach().contiguous()
         h = _dense(x, True, w1, net.out_net[1].bias.detach().contiguous(), n, x.shape[1], 128)
         logits = torch.empty((n, 2), dtype=torch.float32, device=dev)
@@ -187,15 +201,15 @@ class _UpdFn(torch.autograd.Function):
     """Autograd bridge: parameters enter as inputs so that ``loss.backward()`` fills their ``.grad``."""
 
     @staticmethod
-    def forward(ctx, net, data_all, dev, *params):
+    def forward(ctx, net, data_all, dev, comm, *params):
         sv = []
-        out = _forward(net, data_all, dev, sv)
-        ctx.net, ctx.sv, ctx.dev = net, sv, dev
+        out = _forward(net, data_all, dev, sv, comm)
+        ctx.net, ctx.sv, ctx.dev, ctx.comm = net, sv, dev, comm
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        net, sv, dev = ctx.net, ctx.sv, ctx.dev
+        net, sv, dev, comm = ctx.net, ctx.sv, ctx.dev, ctx.comm
         st = _stream()
         grads = []
         with torch.cuda.device(dev):
@@ -235,6 +249,11 @@ class _UpdFn(torch.autograd.Function):
                     d_x = torch.empty((n_src, fi), dtype=torch.float32, device=dev)
                     call("dgnn_gather_phi_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(s.orow), ptr(s.phi),
                          ptr(s.x_in), int(s.relu_in), n_src, n_tgt, fi, ptr(d_x), st)
+                    if comm is not None:
+                        # the rows of halo sources hold this rank's share of their gradient: send them home, add
+                        # what the peers computed for our boundary cells, and keep the owned rows
+                        comm.reverse_add(d_x)
+                        d_x = d_x[:sv[i - 1].g.n_tgt]
                     d_out = d_x
                     de_next = torch.zeros((s.e_all, s.k_in), dtype=torch.float32, device=dev)
                     call("dgnn_scatter_rows", ptr(d_ea), ptr(s.eid_glob), n_tgt * 4, s.k_in, ptr(de_next), st)
@@ -242,7 +261,7 @@ class _UpdFn(torch.autograd.Function):
                 grads += lg
             grads += head_grads
         ctx.sv = None
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 def g_eid(g):

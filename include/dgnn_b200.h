@@ -64,6 +64,9 @@ int dgnn_perm_apply_ell(const int32_t* nbr, const int32_t* perm, const int32_t* 
 /* dst[r,:] = src[idx[r],:]  (row_floats multiple of 4; idx<0 -> zeros) */
 int dgnn_gather_rows(const float* src, const int32_t* idx, int64_t n_rows, int row_floats,
                      float* dst, void* stream);
+/* dst[idx[r],:] += src[r,:]; idx distinct within a call (gradient rows returned by one peer) */
+int dgnn_add_rows(const float* src, const int32_t* idx, int64_t n_rows, int row_floats,
+                  float* dst, void* stream);
 /* dst[idx[r],:] = src[r,:] */
 int dgnn_scatter_rows(const float* src, const int32_t* idx, int64_t n_rows, int row_floats,
                       float* dst, void* stream);

@@ -29,3 +29,8 @@ def test_partitioned_inference_matches_single_gpu():
 def test_partitioned_training_step_matches_single_gpu():
     out = _torchrun("check_partition_train.py", 29522, 8000)
     assert "PARTITIONED_TRAINING world=2" in out
+
+
+def test_partitioned_updated_training_step_matches_single_gpu():
+    out = _torchrun("check_partition_upd.py", 29523, 6000)
+    assert "PARTITIONED_UPDATED_TRAINING world=2" in out

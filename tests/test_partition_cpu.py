@@ -59,6 +59,14 @@ def _worker(rank, world, port, ok):
         # the local table resolves to the same rows the global table names
         rows = torch.cat([torch.arange(m.lo, m.hi), m.halo_gid])
         assert torch.equal(rows[m.local_nbr.long()], torch.from_numpy(nb[m.lo:m.hi]).long())
+        # reverse exchange (gradients accumulated on the source side): every rank scatters 1 per (target, slot) into
+        # its [owned | halo] rows; after reverse_add each owned cell holds its global in-degree as a source
+        from dgnn_b200.partition import HaloComm
+        d = torch.zeros((m.n_own + m.n_halo, 4))
+        d.index_add_(0, m.local_nbr.reshape(-1).long(), torch.ones((m.n_own * 4, 4)))
+        HaloComm(m, n).reverse_add(d)
+        deg = np.bincount(nb.reshape(-1), minlength=n).astype(np.float32)     # times a cell is named as a neighbour
+        assert np.array_equal(d[:m.n_own, 0].numpy(), deg[m.lo:m.hi])
         ok[rank] = 1
     finally:
         dist.destroy_process_group()
