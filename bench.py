@@ -215,7 +215,7 @@ class KernelProfile:
                 "kernel_ms_per_launch": round(r["ms"] / r["launches"], 4),
                 "kernel_share_of_step": round(r["ms"] / total, 4),
                 "algorithmic_bytes_per_launch": r["bytes"] // r["launches"]}
-        return roof, table[:12], total / n_steps
+        return roof, table[:int(os.environ.get("DGNN_BENCH_TABLE", "12"))], total / n_steps
 
 
 def peak_hbm():

@@ -23,6 +23,7 @@ constexpr int DW_NPW = 12;                         // producer warps: one per 32
 constexpr int DW_THREADS = (DW_NPW + 1) * 32;      // 13 warps: at most 4 per scheduler => 128 registers per thread
 constexpr int DW_CELLS = 32;                       // cells (K) per stage = 8 groups of 4 cells
 constexpr int DW_A_BYTES = 128 * 128;               // M = 128 channel rows x 32 cells (one K-atom): 16 KB
+constexpr int DW_MAX_STAGES = 4;                    // narrow layers have small stages: more of them in flight
 
 struct DwTcArgs {
     const float* dy;
@@ -75,14 +76,14 @@ __device__ __forceinline__ void put_split4(uint8_t* hi, uint8_t* lo, uint32_t of
 
 __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[2], bar_empty[2], bar_done;
+    __shared__ uint64_t bar_full[DW_MAX_STAGES], bar_empty[DW_MAX_STAGES], bar_done;
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b_bytes = p.np * 128;
     const int stage_bytes = 2 * DW_A_BYTES + 2 * b_bytes;
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&bar_full[s], p.active_warps); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < DW_MAX_STAGES; ++s) { mbar_init(&bar_full[s], p.active_warps); mbar_init(&bar_empty[s], 1); }
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
@@ -297,7 +298,11 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
     p.agg = agg; p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;
     p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out; p.k_total = k_total;
     p.np = ceil32i(k_total);
-    p.stages = 2;
+    {   // as many 32-cell stages as fit 200 KB (2 at 128 -> 128, 4 for the narrow layers)
+        const int stage_bytes = 2 * DW_A_BYTES + 2 * p.np * 128;
+        int st = (200 * 1024) / stage_bytes;
+        p.stages = st > DW_MAX_STAGES ? DW_MAX_STAGES : (st < 2 ? 2 : st);
+    }
     p.partials = partials;
     const int nb = (f_out + 31) / 32 + p.np / 32;      // operand blocks of 32 channels (<= 12)
     p.wpb = nb * 4 <= DW_NPW ? 4 : (nb * 2 <= DW_NPW ? 2 : 1);

@@ -18,7 +18,10 @@
 // so each thread scatters its strip of P (rounded to TF32) and of EA (hi / lo) transposed into K-major
 // shared-memory operands; the [F x 32] accumulator lives in TMEM for the whole kernel.
 //
-// Warp roles (one persistent CTA per SM): 16 compute warps, 1 MMA warp; no CTA-wide barrier in the loop.
+// One persistent CTA per SM with 16 compute warps (4 per scheduler => 128 registers per thread).  There is no
+// dedicated MMA warp: every warp counts itself in on a shared-memory counter after it has written its share of an
+// operand stage, and the warp that completes the count issues the stage's tcgen05.mma + commits (elect-by-arrival).
+// No CTA-wide barrier in the loop.
 #include "umma.cuh"
 #include "common.cuh"
 
@@ -27,7 +30,7 @@ namespace dgnn {
 using namespace umma;
 
 constexpr int G_NCW = 16;
-constexpr int G_THREADS = (G_NCW + 1) * 32;
+constexpr int G_THREADS = G_NCW * 32;                // no dedicated MMA warp: the last warp to finish a stage issues its MMAs
 constexpr int G_M = 128;
 constexpr int G_EA_STAGES = 2;                       // EA operand ring (hi | lo per stage)
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
@@ -112,9 +115,10 @@ __device__ __forceinline__ void act8(float4& a, float4& b, const float4& sa, con
 template <int CPT, int MODE>  // CPT: features per thread = fp / 4
 __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t ea_full[G_EA_STAGES], ea_empty[G_EA_STAGES];
+    __shared__ uint64_t ea_empty[G_EA_STAGES];
     __shared__ uint64_t phi_full[4], phi_free[4];
     __shared__ uint32_t tmem_slot;
+    __shared__ int ea_count[G_EA_STAGES];                // warps that have stored their share of the stage
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int FP = CPT * 4;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     float* aff_s = reinterpret_cast<float*>(x_base + (size_t)2 * G_NCW * WSTAGE);   // MODE 0: scale[FP] | shift[FP]
 
     if (tid == 0) {
-        for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_full[s], G_NCW); mbar_init(&ea_empty[s], 1); }
+        for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); ea_count[s] = 0; }
         for (int s = 0; s < 4; ++s) { mbar_init(&phi_full[s], 1); mbar_init(&phi_free[s], G_NCW); }
         fence_barrier_init();
     }
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         }
     }
     fence_proxy_async_smem();
-    if (warp == G_NCW) tmem_alloc(&tmem_slot, 512);
+    if (warp == 0) tmem_alloc(&tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -169,35 +173,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     const uint32_t n_my = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     const uint32_t n_phi = n_my * 4u;
 
-    if (warp == G_NCW) {
-        // ---------------------------------------------------------------- MMA warp
-        const uint32_t idesc = make_idesc_tf32(G_M, FP);
-        const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
-        const int ksteps = (p.fe + 1 + 7) >> 3;          // fe features + bias column, 8 per k-step (3 for fe = 20)
-        for (uint32_t n = 0; n < n_phi; ++n) {
-            if (lane == 0) {
-                const uint32_t s = n % G_EA_STAGES, su = n / G_EA_STAGES, b = n & 3u, bu = n >> 2;
-                mbar_wait(&ea_full[s], su & 1);
-                if (bu > 0) mbar_wait(&phi_free[b], (bu - 1) & 1);
-                tc_fence_after_sync();
-                const uint32_t ah = smem_u32(ea_base + (size_t)s * 2 * G_ATOM), al = ah + G_ATOM;
-                const uint32_t d = tmem_base + b * (uint32_t)FP;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const uint32_t ko = kk * 32;
-                    mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
-                    mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
-                    mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
-                }
-                mma_commit(&ea_empty[s]);
-                mma_commit(&phi_full[b]);
-            }
-            __syncwarp();
-        }
-    } else {
+    {
         // ---------------------------------------------------------------- compute warps
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;                      // first feature of this thread's strip
+        const uint32_t idesc = make_idesc_tf32(G_M, FP);
+        const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
+        const int ksteps = (p.fe + 1 + 7) >> 3;        // fe features + bias column, 8 per k-step (3 for fe = 20)
         const bool relu = (p.relu & 1) != 0;
         const bool affine = p.scale != nullptr;
         const bool al8 = (p.f & 7) == 0;
@@ -256,7 +239,28 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ea_full[s]);
+            if (lane == 0) {
+                __threadfence_block();
+                const int arrived = atomicAdd(&ea_count[s], 1);
+                if (arrived == G_NCW - 1) {            // last warp of the stage: issue PHI item n = EA . WE^T
+                    ea_count[s] = 0;                   // next use of the stage is ordered behind ea_empty
+                    __threadfence_block();
+                    const uint32_t b = n & 3u, bu = n >> 2;
+                    if (bu > 0) mbar_wait(&phi_free[b], (bu - 1) & 1);   // every warp is past item n - 4 by now
+                    tc_fence_after_sync();
+                    const uint32_t ah = smem_u32(e_hi), al = ah + G_ATOM;
+                    const uint32_t d = tmem_base + b * (uint32_t)FP;
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
+                        mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+                        mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
+                    }
+                    mma_commit(&ea_empty[s]);
+                    mma_commit(&phi_full[b]);
+                }
+            }
+            __syncwarp();
         };
         // ---- x ring: cp.async of item (tile count tc, slot k) into stage `st`
         auto x_issue = [&](uint32_t tc, int k, const int (&nbv)[4], uint32_t st) {
@@ -465,154 +469,211 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             my[p.f + c] = rs * (b2 - mu * a);          // sum(dh * xhat), xhat = (z - mean) * rstd
         }
     }
-    if (warp == G_NCW) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// dW_e / db_e.  Per slot and row quarter a double-buffered stage (P^T hi | EA^T hi | EA^T lo).
+// dW_e / db_e = P^T . EA over all edges, P[edge, f] = h(s)[f] * d_agg[onbr[s,k]][f].
+// Per row quarter q one operand stage (P^T hi [128 features x 32 cells] | EA^T hi | EA^T lo); the strips a warp
+// needs (its rows' z_prev strip, then the four gathered d_agg strips) arrive through the same warp-private
+// cp.async ring as in gather_tc_kernel, one item ahead, so no load is waited for in registers.
 template <int CPT>
 __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t p_full[4][2], p_empty[4][2], dwe_done;
+    __shared__ uint64_t p_empty[4];
     __shared__ uint32_t tmem_slot;
+    __shared__ int p_count[4];                           // warps of the quarter that have stored their rows of the stage
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int CH = CPT / 4, RPI = 32 / CH, PITCH = CPT * 4, WSTAGE = 32 * PITCH;
+    uint8_t* x_base = smem + (size_t)4 * G_P_BYTES;      // [2 stages][G_NCW warps][32 rows x PITCH]
     if (tid == 0) {
-        for (int qq = 0; qq < 4; ++qq)
-            for (int b = 0; b < 2; ++b) { mbar_init(&p_full[qq][b], 4); mbar_init(&p_empty[qq][b], 1); }
-        mbar_init(&dwe_done, 1);
+        for (int qq = 0; qq < 4; ++qq) { mbar_init(&p_empty[qq], 1); p_count[qq] = 0; }
         fence_barrier_init();
     }
-    for (int i = tid; i < 8 * G_P_BYTES / 16; i += G_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < 4 * G_P_BYTES / 16; i += G_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     // row fe of every EA^T operand is all ones: column fe of the accumulator collects db_e = sum dphi
-    for (int i = tid; i < 8 * 32; i += G_THREADS)
+    for (int i = tid; i < 4 * 32; i += G_THREADS)
         *reinterpret_cast<float*>(smem + (size_t)(i >> 5) * G_P_BYTES + G_ATOM + atom_off(p.fe, i & 31)) = 1.0f;
     fence_proxy_async_smem();
-    if (warp == G_NCW) tmem_alloc(&tmem_slot, 32);
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);        // one [128 x 32] accumulator per row quarter
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
     const int64_t n_tiles = (p.n_rows + G_M - 1) / G_M;
+    const uint32_t n_my = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
 
-    if (warp == G_NCW) {
+    {
         const uint32_t idesc = make_idesc_tf32(G_M, 32);
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int k = 0; k < 4; ++k, ++it) {
-                if (lane == 0) {
-                    const uint32_t b = it & 1, bu = it >> 1;
-#pragma unroll 1
-                    for (int qq = 0; qq < 4; ++qq) {
-                        mbar_wait(&p_full[qq][b], bu & 1);
-                        tc_fence_after_sync();
-                        const uint32_t ph = smem_u32(smem + (size_t)(qq * 2 + b) * G_P_BYTES), eh = ph + G_ATOM, el = eh + 32 * 128;
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint32_t ko = kk * 32;
-                            mma_tf32(tmem_base, make_desc(ph + ko), make_desc(eh + ko), idesc, (it > 0 || qq > 0 || kk > 0) ? 1u : 0u);
-                            mma_tf32(tmem_base, make_desc(ph + ko), make_desc(el + ko), idesc, 1u);
-                        }
-                        mma_commit(&p_empty[qq][b]);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        if (lane == 0 && it > 0) mma_commit(&dwe_done);
-        __syncwarp();
-    } else {
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t t = tile * G_M + row;
-            const bool tv = t < p.n_rows;
-            int4 nb4 = make_int4(-1, -1, -1, -1);
-            if (tv) nb4 = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
-            const int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-            // h strip of this row
-            float h[CPT];
-#pragma unroll
-            for (int j = 0; j < CPT; j += 4) {
-                const int f0 = c0 + j;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tv && f0 < p.f) {
-                    v = ldg4(p.z_prev + (size_t)t * p.f + f0);
-                    if (p.p_scale != nullptr) {
-                        float4 sc = ldg4(p.p_scale + f0), sh = ldg4(p.p_shift + f0);
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                    if (p.p_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                }
-                h[j] = v.x; h[j + 1] = v.y; h[j + 2] = v.z; h[j + 3] = v.w;
+        uint8_t* xw = x_base + (size_t)warp * WSTAGE;
+        const uint32_t swz_l = ((uint32_t)lane / (8 / CH)) & (CH - 1);
+        const int c_row = lane / CH, c_ch = lane % CH;
+        uint8_t* pq = smem + (size_t)q * G_P_BYTES;
+        uint8_t* eh = pq + G_ATOM;
+        uint8_t* el = eh + 32 * 128;
+        auto tile_of = [&](uint32_t tc) { return (int64_t)blockIdx.x + (int64_t)tc * gridDim.x; };
+        auto load_nbr = [&](uint32_t tc) {
+            int4 nb = make_int4(-1, -1, -1, -1);
+            if (tc < n_my) {
+                const int64_t t = tile_of(tc) * G_M + row;
+                if (t < p.n_rows) nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
             }
-            for (int k = 0; k < 4; ++k, ++it) {
-                const uint32_t b = it & 1, bu = it >> 1;
-                uint8_t* pq = smem + (size_t)(q * 2 + b) * G_P_BYTES;
-                uint8_t* eh = pq + G_ATOM;
-                uint8_t* el = eh + 32 * 128;
-                const int s_row = nbv[k];
-                // gathered d_agg strip (all loads first), and this warp's share of the EA row
-                float4 da[CPT / 4];
+            return nb;
+        };
+        // item m of a tile: m = 0 the rows' own z_prev strip, m = 1..4 the d_agg strip of neighbour m-1
+        auto x_issue = [&](uint32_t tc, int m, const int (&nbv)[4], uint32_t st) {
+            if (tc < n_my) {
+                uint8_t* dst = xw + (size_t)st * G_NCW * WSTAGE;
+                const int64_t t0 = tile_of(tc) * G_M + q * 32;
+                const int fcol = c0 + c_ch * 4;
+                const int mine = m > 0 ? nbv[m > 0 ? m - 1 : 0] : 0;
 #pragma unroll
-                for (int j = 0; j < CPT; j += 8) {
-                    da[j >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    da[(j >> 2) + 1] = da[j >> 2];
-                    if ((p.f & 7) == 0) {
-                        if (s_row >= 0 && c0 + j < p.f) ldg8(p.x + (size_t)s_row * p.f + c0 + j, da[j >> 2], da[(j >> 2) + 1]);
+                for (int i = 0; i < CH; ++i) {
+                    const int r = i * RPI + c_row;
+                    int64_t sr = -1;
+                    const float* base = p.x;
+                    if (m > 0) {
+                        sr = __shfl_sync(0xffffffffu, mine, r);
                     } else {
-                        if (s_row >= 0 && c0 + j < p.f) da[j >> 2] = ldg4(p.x + (size_t)s_row * p.f + c0 + j);
-                        if (s_row >= 0 && c0 + j + 4 < p.f) da[(j >> 2) + 1] = ldg4(p.x + (size_t)s_row * p.f + c0 + j + 4);
+                        base = p.z_prev;
+                        if (t0 + r < p.n_rows) sr = t0 + r;
+                    }
+                    if (sr >= 0 && fcol < p.f) {
+                        const uint32_t sw = ((uint32_t)r / (8 / CH)) & (CH - 1);
+                        cp_async16(dst + r * PITCH + (((uint32_t)c_ch ^ sw) << 4), base + (size_t)sr * p.f + fcol);
                     }
                 }
-                float4 ev[2];
+            }
+            cp_async_commit();
+        };
+        int4 nb4 = load_nbr(0);
+        int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
+        uint32_t xi = 0, it = 0;
+        x_issue(0, 0, nbv, 0);
+        for (uint32_t tc = 0; tc < n_my; ++tc) {
+            const int64_t t = tile_of(tc) * G_M + row;
+            const bool tv = t < p.n_rows;
+            const int4 nbn4 = load_nbr(tc + 1);
+            const int nbn[4] = {nbn4.x, nbn4.y, nbn4.z, nbn4.w};
+            float h[CPT];
+            float4 ev[2];
+            auto load_ev = [&](int k) {                // this warp's share of the EA row of slot k (global, one item ahead)
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int e0 = grp * 8 + h2 * 4;
                     ev[h2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e0 < p.fe && tv && s_row >= 0) ev[h2] = ldg4(p.ea + ((size_t)t * 4 + k) * p.fe + e0);
+                    if (e0 < p.fe && tv && nbv[k] >= 0) ev[h2] = ldg4(p.ea + ((size_t)t * 4 + k) * p.fe + e0);
                 }
-                mbar_wait(&p_empty[q][b], (bu & 1) ^ 1);
+            };
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int e0 = grp * 8 + h2 * 4;
-                    if (e0 >= p.fe) continue;
-                    const float vv[4] = {ev[h2].x, ev[h2].y, ev[h2].z, ev[h2].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float hi, lo;
-                        split_tf32(vv[i], hi, lo);
-                        const uint32_t off = atom_off(e0 + i, lane);
-                        *reinterpret_cast<float*>(eh + off) = hi;
-                        *reinterpret_cast<float*>(el + off) = lo;
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < CPT; j += 4) {
-                    const float dp[4] = {h[j] * da[j >> 2].x, h[j + 1] * da[j >> 2].y, h[j + 2] * da[j >> 2].z, h[j + 3] * da[j >> 2].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        // row = c0 + j + i, column = lane; c0 is a multiple of 8: row & 7 = (j & 4) + i
-                        const uint32_t r8 = (uint32_t)((j & 4) + i);
-                        const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ r8) << 4) + (((uint32_t)lane & 3u) << 2);
-                        *reinterpret_cast<float*>(pq + off) = tf32_rna(dp[i]);
-                    }
-                }
-                fence_proxy_async_smem();
+            for (int m = 0; m < 5; ++m, ++xi) {
+                if (m + 1 < 5) x_issue(tc, m + 1, nbv, (xi + 1) & 1);
+                else x_issue(tc + 1, 0, nbn, (xi + 1) & 1);
+                cp_async_wait<1>();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[q][b]);
+                const uint8_t* xs = xw + (size_t)(xi & 1) * G_NCW * WSTAGE + lane * PITCH;
+                if (m == 0) {
+                    load_ev(0);
+#pragma unroll
+                    for (int j = 0; j < CPT; j += 4) {
+                        const int f0 = c0 + j;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tv && f0 < p.f) {
+                            v = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                            if (p.p_scale != nullptr) {
+                                float4 sc = ldg4(p.p_scale + f0), sh = ldg4(p.p_shift + f0);
+                                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                            }
+                            if (p.p_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        }
+                        h[j] = v.x; h[j + 1] = v.y; h[j + 2] = v.z; h[j + 3] = v.w;
+                    }
+                } else {
+                    const int k = m - 1;
+                    const bool valid = tv && nbv[k] >= 0;
+                    mbar_wait(&p_empty[q], (it & 1) ^ 1);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int e0 = grp * 8 + h2 * 4;
+                        if (e0 >= p.fe) continue;
+                        const float vv[4] = {ev[h2].x, ev[h2].y, ev[h2].z, ev[h2].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float hi, lo;
+                            split_tf32(vv[i], hi, lo);
+                            const uint32_t off = atom_off(e0 + i, lane);
+                            *reinterpret_cast<float*>(eh + off) = hi;
+                            *reinterpret_cast<float*>(el + off) = lo;
+                        }
+                    }
+                    if (k < 3) load_ev(k + 1);
+#pragma unroll
+                    for (int j = 0; j < CPT; j += 4) {
+                        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid && c0 + j < p.f) d = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                        const float dp[4] = {h[j] * d.x, h[j + 1] * d.y, h[j + 2] * d.z, h[j + 3] * d.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            // row = c0 + j + i, column = lane; c0 is a multiple of 8: row & 7 = (j & 4) + i
+                            const uint32_t r8 = (uint32_t)((j & 4) + i);
+                            const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ r8) << 4) + (((uint32_t)lane & 3u) << 2);
+                            *reinterpret_cast<float*>(pq + off) = tf32_rna(dp[i]);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence_block();
+                        const int arrived = atomicAdd(&p_count[q], 1);
+                        if (arrived == 3) {            // last warp of the quarter: accumulate P^T . EA of this stage
+                            p_count[q] = 0;
+                            __threadfence_block();
+                            tc_fence_after_sync();
+                            // every quarter accumulates into its own TMEM columns, its stages in order: the sum over
+                            // cells is evaluated in a fixed order whatever the timing of the warps
+                            const uint32_t ph = smem_u32(pq), ehh = ph + G_ATOM, ell = ehh + 32 * 128;
+                            const uint32_t dq = tmem_base + (uint32_t)(q * 32);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint32_t ko = kk * 32;
+                                mma_tf32(dq, make_desc(ph + ko), make_desc(ehh + ko), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                                mma_tf32(dq, make_desc(ph + ko), make_desc(ell + ko), idesc, 1u);
+                            }
+                            mma_commit(&p_empty[q]);
+                        }
+                    }
+                    __syncwarp();
+                    ++it;
+                }
+                __syncwarp();
             }
+            nbv[0] = nbn[0]; nbv[1] = nbn[1]; nbv[2] = nbn[2]; nbv[3] = nbn[3];
         }
+        cp_async_wait<0>();
+        // The quarters run independently; only after every warp has issued its last stage is each p_empty barrier at
+        // most one phase behind, which makes the parity wait below unambiguous.
+        __syncthreads();
         if (grp == 0) {
             float* outp = p.dwe_partials + (size_t)blockIdx.x * p.f * 32;
             float v[32];
             if (it > 0) {
-                mbar_wait(&dwe_done, 0);
+                // every stage's MMAs were issued and committed by some thread of its quarter; the last stage of each
+                // quarter is the only one nobody has waited for yet
+                for (int qq = 0; qq < 4; ++qq) mbar_wait(&p_empty[qq], (it - 1) & 1);
                 tc_fence_after_sync();
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);          // quarter 0, then + 1, 2, 3 in order
+#pragma unroll 1
+                for (int qq = 1; qq < 4; ++qq) {
+                    float w[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(qq * 32), w);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += w[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -626,7 +687,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == G_NCW) tmem_dealloc(tmem_base, 32);
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 }  // namespace dgnn
@@ -666,13 +727,13 @@ static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* 
 
 static int launch_dwe_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
-    size_t smem = (size_t)8 * G_P_BYTES + 1024;
+    size_t smem = (size_t)4 * G_P_BYTES + (size_t)2 * G_NCW * 32 * p.fp + 1024;
 #define LAUNCH_D(CPT)                                                                                          \
     do {                                                                                                       \
         static bool configured = false;                                                                        \
         if (!configured) {                                                                                     \
             cudaError_t e = cudaFuncSetAttribute(dwe_tc_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 210 * 1024);                                                  \
+                                                 226 * 1024);                                                  \
             if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                    \
             configured = true;                                                                                 \
         }                                                                                                      \

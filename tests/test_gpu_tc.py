@@ -198,3 +198,43 @@ def test_gather_tc_forward_and_backward_match_generic_kernels(f_in, fe, ragged):
     call("dgnn_edge_filter_bwd", ptr(d_agg), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x), ptr(sc), ptr(sh),
          1, n, n, f_in, ptr(part3), st)
     assert _rel(part3.sum(0)[:f_in * (fe + 1)], dwe_ref) < 1e-6
+
+
+def test_gather_tc_kernels_are_bitwise_reproducible():
+    """The elect-by-arrival MMA issue must not leak timing into the results: forward aggregate, backward dy / (S1, S2)
+    partials and the dW_e partials of repeated launches on a graph that spans many tiles are bit-identical."""
+    from dgnn_b200._lib import call, lib, ptr
+    from dgnn_b200.graph import build_full_graph
+    g = make_graph(9000, seed=9)
+    n, f_in, fe = g["n"], 128, 20
+    ei = torch.from_numpy(g["adj"].T.astype(np.int64)).contiguous()
+    torch.manual_seed(6)
+    eg = build_full_graph(ei, torch.randn(4 * n, fe), n, DEV, order="rcm")
+    x = torch.randn(n, f_in, device=DEV)
+    w_e = torch.randn(f_in, fe, device=DEV) * 0.3
+    b_e = torch.randn(f_in, device=DEV)
+    sc = torch.rand(f_in, device=DEV) + 0.5
+    sh = torch.randn(f_in, device=DEV) * 0.3
+    mean = torch.randn(f_in, device=DEV) * 0.1
+    rstd = torch.rand(f_in, device=DEV) + 0.5
+    d_agg = torch.randn(n, f_in, device=DEV)
+    d_self = torch.randn(n, f_in, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    tcg = lib().dgnn_tc_grid()
+
+    def once():
+        agg = torch.empty(n, f_in, device=DEV)
+        dy = torch.empty(n, f_in, device=DEV)
+        part = torch.empty(tcg, 2 * f_in, dtype=torch.float64, device=DEV)
+        dwe = torch.empty(tcg, f_in, 32, device=DEV)
+        call("dgnn_gather_tc_fwd", ptr(x), ptr(sc), ptr(sh), 1, ptr(eg.nbr), ptr(eg.ea_in), fe, ptr(w_e), ptr(b_e), n, f_in,
+             ptr(agg), st)
+        call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x),
+             ptr(sc), ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f_in, ptr(dy), ptr(part), ptr(dwe), st)
+        torch.cuda.synchronize()
+        return agg, dy, part, dwe
+
+    ref = once()
+    for _ in range(8):
+        for a, b in zip(once(), ref):
+            assert torch.equal(a, b)

@@ -1,5 +1,5 @@
 """Multi-GPU check (run under torchrun): partitioned inference vs the single-GPU forward, and its throughput.
-    torchrun --nproc-per-node N --master-addr 127.0.0.1 tools/check_partition.py [n_points]"""
+    torchrun --nproc-per-node N --master-addr 127.0.0.1 tools/check_partition.py [n_points | nx lattice]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
@@ -12,8 +12,11 @@ torch.cuda.set_device(lr); dev = "cuda:%d" % lr
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(dev))
 npts = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
-pts = syn.random_points(npts, seed=0)
-adj, infinite, cen, _ = syn.delaunay_graph(pts)
+if len(sys.argv) > 2 and sys.argv[2] == "lattice":      # analytic 4-regular scene with 2 * npts^3 cells (no qhull)
+    adj, infinite, cen = syn.lattice_graph(npts, npts, npts)
+else:
+    pts = syn.random_points(npts, seed=0)
+    adj, infinite, cen, _ = syn.delaunay_graph(pts)
 n = infinite.shape[0]
 x, ea, y = syn.synthetic_features(n, infinite, seed=1)
 d = syn.to_attr(dict(x=torch.from_numpy(x), edge_attr=torch.from_numpy(ea), edge_index=torch.from_numpy(adj.T.astype(np.int64)).contiguous(),
