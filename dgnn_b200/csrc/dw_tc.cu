@@ -70,8 +70,8 @@ __device__ __forceinline__ void put_split4(uint8_t* hi, uint8_t* lo, uint32_t of
     split_tf32(v.y, h.y, l.y);
     split_tf32(v.z, h.z, l.z);
     split_tf32(v.w, h.w, l.w);
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
+    sts128(smem_u32(hi) + off, h);
+    sts128(smem_u32(lo) + off, l);
 }
 
 __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) {

@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                     float4 h, l;
                     split_tf32(ev[u].x, h.x, l.x); split_tf32(ev[u].y, h.y, l.y);
                     split_tf32(ev[u].z, h.z, l.z); split_tf32(ev[u].w, h.w, l.w);
-                    *reinterpret_cast<float4*>(e_hi + e_off[u]) = h;
-                    *reinterpret_cast<float4*>(e_lo + e_off[u]) = l;
+                    sts128(smem_u32(e_hi) + e_off[u], h);
+                    sts128(smem_u32(e_lo) + e_off[u], l);
                 }
             }
             fence_proxy_async_smem();
@@ -333,13 +333,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                         const int f0 = c0 + j;
                         uint32_t ph[8];
                         tmem_ld8(trow + (uint32_t)j, ph);
-                        float4 xa = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
-                        float4 xb = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4));
+                        float4 xa = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                        float4 xb = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4));
                         if (MODE == 0 && affine) {               // warp-uniform addresses: shared-memory broadcasts
-                            const float4 sa = *reinterpret_cast<const float4*>(aff_s + f0);
-                            const float4 sb = *reinterpret_cast<const float4*>(aff_s + f0 + 4);
-                            const float4 ha = *reinterpret_cast<const float4*>(aff_s + FP + f0);
-                            const float4 hb = *reinterpret_cast<const float4*>(aff_s + FP + f0 + 4);
+                            const uint32_t as = smem_u32(aff_s) + (uint32_t)f0 * 4u;
+                            const float4 sa = lds128(as), sb = lds128(as + 16u);
+                            const float4 ha = lds128(as + FP * 4u), hb = lds128(as + FP * 4u + 16u);
                             act8(xa, xb, sa, sb, ha, hb, true, relu);
                         } else if (MODE == 0) {
                             act8(xa, xb, xa, xa, xa, xa, false, relu);
@@ -381,7 +380,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
 #pragma unroll
                         for (int j = 0; j < CPT; j += 4) {
                             if (c0 + j < p.f) {
-                                const float4 a = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                                const float4 a = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
                                 acc[j] += a.x; acc[j + 1] += a.y; acc[j + 2] += a.z; acc[j + 3] += a.w;
                             }
                         }
@@ -399,8 +398,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
 #pragma unroll
                             for (int i = 0; i < 8; ++i) a8[i] = (i < 4 || fvalid_b) ? acc[j + i] : 0.f;
                             if (p.z_prev != nullptr) {
-                                const float4 za = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
-                                const float4 zb = fvalid_b ? *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4)) : zero4;
+                                const float4 za = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                                const float4 zb = fvalid_b ? lds128(smem_u32(xs) + ((((uint32_t)(j >> 2) + 1u) ^ swz_l) << 4)) : zero4;
                                 const float zv[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
                                 // ReLU mask of the producer layer; S2 is accumulated as sum(dh * z) and turned into
                                 // sum(dh * xhat) = rstd * (sum(dh * z) - mean * S1) when the CTA partial is written
@@ -584,7 +583,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                         const int f0 = c0 + j;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (tv && f0 < p.f) {
-                            v = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                            v = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
                             if (p.p_scale != nullptr) {
                                 float4 sc = ldg4(p.p_scale + f0), sh = ldg4(p.p_shift + f0);
                                 v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
@@ -607,22 +606,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                             float hi, lo;
                             split_tf32(vv[i], hi, lo);
                             const uint32_t off = atom_off(e0 + i, lane);
-                            *reinterpret_cast<float*>(eh + off) = hi;
-                            *reinterpret_cast<float*>(el + off) = lo;
+                            sts32(smem_u32(eh) + off, hi);
+                            sts32(smem_u32(el) + off, lo);
                         }
                     }
                     if (k < 3) load_ev(k + 1);
 #pragma unroll
                     for (int j = 0; j < CPT; j += 4) {
                         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid && c0 + j < p.f) d = *reinterpret_cast<const float4*>(xs + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                        if (valid && c0 + j < p.f) d = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
                         const float dp[4] = {h[j] * d.x, h[j + 1] * d.y, h[j + 2] * d.z, h[j + 3] * d.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             // row = c0 + j + i, column = lane; c0 is a multiple of 8: row & 7 = (j & 4) + i
                             const uint32_t r8 = (uint32_t)((j & 4) + i);
                             const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ r8) << 4) + (((uint32_t)lane & 3u) << 2);
-                            *reinterpret_cast<float*>(pq + off) = tf32_rna(dp[i]);
+                            sts32(smem_u32(pq) + off, tf32_rna(dp[i]));
                         }
                     }
                     fence_proxy_async_smem();

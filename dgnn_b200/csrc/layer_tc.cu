@@ -81,8 +81,8 @@ __device__ __forceinline__ void store_split2(uint8_t* a_hi, uint8_t* a_lo, int r
     split_tf32(v0, h0, l0);
     split_tf32(v1, h1, l1);
     uint32_t off = atom_off(r, k);
-    *reinterpret_cast<float2*>(a_hi + off) = make_float2(h0, h1);
-    *reinterpret_cast<float2*>(a_lo + off) = make_float2(l0, l1);
+    sts64(smem_u32(a_hi) + off, make_float2(h0, h1));
+    sts64(smem_u32(a_lo) + off, make_float2(l0, l1));
 }
 __device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, int r, int k, float4 v) {
     float4 h, l;
@@ -91,8 +91,8 @@ __device__ __forceinline__ void store_split4(uint8_t* a_hi, uint8_t* a_lo, int r
     split_tf32(v.z, h.z, l.z);
     split_tf32(v.w, h.w, l.w);
     uint32_t off = atom_off(r, k);
-    *reinterpret_cast<float4*>(a_hi + off) = h;
-    *reinterpret_cast<float4*>(a_lo + off) = l;
+    sts128(smem_u32(a_hi) + off, h);
+    sts128(smem_u32(a_lo) + off, l);
 }
 
 // warp `w` fills its 8 rows of the atom with h(x_in[row, f0 .. f0+32))

@@ -7,8 +7,8 @@
 // inside an atom advances the descriptor start address by 32 B.
 //
 // FP32 fidelity: every product is evaluated as hi*hi + lo*hi + hi*lo with
-// hi = rna_tf32(x), lo = rna_tf32(x - hi) (3xTF32, fp32 accumulation in TMEM); the dropped lo*lo
-// term and the rounding of lo are ~2^-22 relative (indistinguishable from fp32).
+// hi = rna_tf32(x), lo = x - hi truncated to TF32 by the tensor core (3xTF32, fp32 accumulation in TMEM); the
+// dropped lo*lo term and the truncation of lo are ~2^-21 relative (indistinguishable from fp32).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,14 +28,34 @@ __device__ __forceinline__ uint32_t atom_off(int r, int k) {
     return (uint32_t)r * 128u + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)k & 3u) << 2);
 }
 
+// Round to TF32 (10 mantissa bits), nearest with ties away from zero, for finite inputs: add half an ulp of the
+// TF32 grid to the bit pattern and clear the 13 low bits.  (cvt.rna.tf32.f32 compiles to the same two operations plus
+// an Inf/NaN guard of three more instructions on sm_100a; an Inf/NaN input is garbage for the product anyway.)
 __device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+// 3xTF32 split: hi = rna_tf32(x); lo = x - hi is exact in fp32 and is handed to the tensor core as is (kind::tf32
+// reads the 19 high bits of an operand, i.e. truncates lo to TF32: |x - hi - trunc(lo)| <= 2^-21 |x|).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    lo = x - hi;
+}
+
+// shared-memory accesses through 32-bit shared-space addresses (generic pointers derived from the aligned dynamic
+// shared base compile to 64-bit generic LD / ST)
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const float2& v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // ---- mbarrier -------------------------------------------------------------------------------
