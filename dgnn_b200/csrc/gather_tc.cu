@@ -116,7 +116,7 @@ template <int CPT, int MODE>  // CPT: features per thread = fp / 4
 __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ea_empty[G_EA_STAGES];
-    __shared__ uint64_t phi_full[4], phi_free[4];
+    __shared__ uint64_t phi_full[4];
     __shared__ uint32_t tmem_slot;
     __shared__ int ea_count[G_EA_STAGES];                // warps that have stored their share of the stage
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
 
     if (tid == 0) {
         for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); ea_count[s] = 0; }
-        for (int s = 0; s < 4; ++s) { mbar_init(&phi_full[s], 1); mbar_init(&phi_free[s], G_NCW); }
+        for (int s = 0; s < 4; ++s) mbar_init(&phi_full[s], 1);
         fence_barrier_init();
     }
     // zero the operands (K padding stays zero), then WE[n][e] = w_e[n][e] (e < fe), WE[n][fe] = b_e[n]
@@ -245,8 +245,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                 if (arrived == G_NCW - 1) {            // last warp of the stage: issue PHI item n = EA . WE^T
                     ea_count[s] = 0;                   // next use of the stage is ordered behind ea_empty
                     __threadfence_block();
-                    const uint32_t b = n & 3u, bu = n >> 2;
-                    if (bu > 0) mbar_wait(&phi_free[b], (bu - 1) & 1);   // every warp is past item n - 4 by now
+                    // PHI buffer n & 3 was last read for item n - 4.  Every warp stores item n at its position n - 2, i.e.
+                    // after it has finished consuming item n - 3 and everything before: once the count is complete no
+                    // warp can still be reading the buffer, so no further barrier is needed before overwriting it.
+                    const uint32_t b = n & 3u;
                     tc_fence_after_sync();
                     const uint32_t ah = smem_u32(e_hi), al = ah + G_ATOM;
                     const uint32_t d = tmem_base + b * (uint32_t)FP;
@@ -355,9 +357,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                             acc[j + 7] = fmaf(xb.w, __uint_as_float(ph[7]), acc[j + 7]);
                         }
                     }
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&phi_free[b]);
+                    tc_fence_before_sync();             // orders these TMEM reads before the warp's next ea_count arrival
                     ++pn;
                     if (MODE == 0 && k == 3) {
 #pragma unroll
