@@ -210,8 +210,19 @@ class KernelProfile:
         ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
         table = sorted(((k[0] + ":" + k[1], round(v["ms"] / n_steps, 4), v["launches"] // n_steps) for k, v in agg.items()),
                        key=lambda t: -t[1])
+        # DRAM bytes per cell (dram__bytes_read.sum + dram__bytes_write.sum) of the F = 128 kernels from the committed
+        # `ncu --set full` capture (profiles/r01_ncu_full_final_kernels.csv, 604 913 cells), scaled to this launch
+        traffic_per_cell = {"dgnn_gather_tc_bwd:f128": 3720, "dgnn_gather_tc_fwd:f128": 1304,
+                            "dgnn_dense_fwd_tc:f128->128": 1480, "dgnn_dense_bwd_tc:f128->128": 2007,
+                            "dgnn_dw_bwd_tc:f128->128": 2055}
+        algo_per_cell = {"dgnn_gather_tc_bwd:f128": 2384, "dgnn_gather_tc_fwd:f128": 1360,
+                         "dgnn_dense_fwd_tc:f128->128": 1536, "dgnn_dense_bwd_tc:f128->128": 2064,
+                         "dgnn_dw_bwd_tc:f128->128": 2048}
+        tpc = traffic_per_cell.get(top[0] + ":" + top[1])
+        cells = (r["bytes"] // r["launches"]) // algo_per_cell[top[0] + ":" + top[1]] if tpc else 0
         roof = {"bound": "hbm", "kernel": top[0] + ":" + top[1], "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
-                "frac": round(ach / peak_gbs, 4), "peak_source": peak_src, "traffic": None,
+                "frac": round(ach / peak_gbs, 4), "peak_source": peak_src,
+                "traffic": int(tpc * cells) if tpc and cells else None,
                 "kernel_ms_per_launch": round(r["ms"] / r["launches"], 4),
                 "kernel_share_of_step": round(r["ms"] / total, 4),
                 "algorithmic_bytes_per_launch": r["bytes"] // r["launches"]}
