@@ -10,13 +10,13 @@
 // Evaluating phi with FMAs costs 80 FMA per feature and cell and made the gather issue-bound
 // (profiles/r01_*).  Here PHI_k for a tile of 128 cells is one small tcgen05 product
 //     PHI_k[128 cells x F] = EA_k[128 x 32] . WE[F x 32]^T      (K = fe features + a bias column, 3xTF32)
-// that lands in TMEM (4 slots x F <= 512 columns).  Each thread then owns one cell row and a strip of
-// F/4 features; per 8 features it issues the 8 neighbour-row loads of all four slots (128-bit, the norm
-// affine + ReLU of the producer layer applied on load), reads the matching PHI strips from TMEM
-// (tcgen05.ld) and accumulates h * phi in registers.
+// that lands in TMEM (4 slots x F <= 512 columns).  Each thread owns one cell row and a strip of F/4 features;
+// slot by slot it reads the neighbour row's strip (staged through a warp-private cp.async ring; the norm affine +
+// ReLU of the producer layer applied on the way), the matching PHI strip from TMEM (tcgen05.ld) and accumulates
+// h * phi in registers.
 // dW_e is the product P^T . EA with P = dphi [edges x F]: both operands need the edge index contiguous,
 // so each thread scatters its strip of P (rounded to TF32) and of EA (hi / lo) transposed into K-major
-// shared-memory operands; the [F x 32] accumulator lives in TMEM for the whole kernel.
+// shared-memory operands; one [F x 32] accumulator per row quarter lives in TMEM for the whole kernel.
 //
 // One persistent CTA per SM with 16 compute warps (4 per scheduler => 128 registers per thread).  There is no
 // dedicated MMA warp: every warp counts itself in on a shared-memory counter after it has written its share of an
@@ -110,8 +110,10 @@ __device__ __forceinline__ void act8(float4& a, float4& b, const float4& sa, con
 //             in flight while item n is consumed, with no registers held.  MODE 1 appends two plain items per
 //             tile: the rows' own d_self (k = 4) and z_prev (k = 5) strips.
 //   EA ring   2 stages of (hi | lo) K-major operands; the global loads of item n+3 are issued, and the
-//             registers of item n+2 stored, while item n is consumed.
-//   PHI ring  4 TMEM buffers of FP columns; the MMA warp runs up to 4 items ahead of the consumers.
+//             registers of item n+2 stored, while item n is consumed.  The warp that completes a stage's arrival
+//             count issues the 9 MMAs of PHI item n+2 (elect-by-arrival, see the file header).
+//   PHI ring  4 TMEM buffers of FP columns (item n in buffer n & 3), ready two items before they are consumed;
+//             no "free" barrier: the arrival count of item n already orders the overwrite of item n-4's buffer.
 template <int CPT, int MODE>  // CPT: features per thread = fp / 4
 __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
