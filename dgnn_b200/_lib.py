@@ -50,7 +50,7 @@ SIGNATURES = {
     "dgnn_dw_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P, P],
     "dgnn_debug_umma": [P, I, P, I, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, I, P, P],
     "dgnn_gather_phi_fwd": [P, P, P, I, P, P, L, I, P, P],
-    "dgnn_upd_edge_bwd": [P, I, P, P, P, P, P, L, I, P, P],
+    "dgnn_upd_edge_bwd": [P, P, P, I, P, P, P, P, P, L, I, P, P],
     "dgnn_gather_phi_bwd": [P, P, P, P, P, P, I, L, L, I, P, P],
     "dgnn_relu_mask": [P, P, L, P, P],
     "dgnn_norm_finalize": [P, I, L, I, P, P, F, F, I, P, P, P, P, P, P, P],

@@ -9,7 +9,8 @@ namespace dgnn {
 //   first term : d(agg)/d(e') with d_agg already divided by max(cnt,1)
 //   second term: gradient that reaches e' through relu(edge state) read by the NEXT layer (de_next indexed by
 //                global edge id, NULL for the last layer)
-__global__ void __launch_bounds__(256) upd_edge_bwd_kernel(const float* __restrict__ x, int relu,
+__global__ void __launch_bounds__(256) upd_edge_bwd_kernel(const float* __restrict__ x, const float* __restrict__ sc,
+                                                           const float* __restrict__ sh, int relu,
                                                            const int32_t* __restrict__ nbr,
                                                            const float* __restrict__ d_agg,
                                                            const float* __restrict__ phi,
@@ -26,6 +27,10 @@ __global__ void __launch_bounds__(256) upd_edge_bwd_kernel(const float* __restri
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s >= 0) {
             float4 v = ldg4(x + (size_t)s * f + c);
+            if (sc) {                                  // norm affine of the producer layer applied on load
+                const float4 a = ldg4(sc + c), b = ldg4(sh + c);
+                v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+            }
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
             const float4 g = ldg4(d_agg + (size_t)t * f + c);
             o = make_float4(v.x * g.x, v.y * g.y, v.z * g.z, v.w * g.w);
@@ -98,14 +103,15 @@ static inline int grid_for(long long total) {
 
 using namespace dgnn;
 
-extern "C" int dgnn_upd_edge_bwd(const float* x_in, int relu_in, const int32_t* nbr, const float* d_agg,
+extern "C" int dgnn_upd_edge_bwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                                 const int32_t* nbr, const float* d_agg,
                                  const float* phi, const float* de_next, const int32_t* eid, int64_t n_tgt, int f,
                                  float* dphi, void* stream) {
     DGNN_REQUIRE(f > 0 && f % 4 == 0, "f must be a positive multiple of 4");
     DGNN_REQUIRE(x_in && nbr && d_agg && dphi, "null pointer");
     DGNN_REQUIRE(!de_next || (phi && eid), "de_next needs phi and eid");
     if (n_tgt <= 0) return 0;
-    upd_edge_bwd_kernel<<<grid_for((long long)n_tgt * f), 256, 0, as_stream(stream)>>>(x_in, relu_in, nbr, d_agg, phi,
+    upd_edge_bwd_kernel<<<grid_for((long long)n_tgt * f), 256, 0, as_stream(stream)>>>(x_in, in_scale, in_shift, relu_in, nbr, d_agg, phi,
                                                                                       de_next, eid, n_tgt, f, dphi);
     return check_launch("dgnn_upd_edge_bwd");
 }

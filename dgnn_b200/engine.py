@@ -14,7 +14,7 @@ from typing import List, Optional
 
 import torch
 
-from ._lib import call, lib, ptr
+from ._lib import DgnnError, call, lib, ptr
 from .graph import EllGraph, pad4
 
 
@@ -51,15 +51,26 @@ class NormSpec:
 
 
 @dataclass
+class EdgeMlpSpec:
+    """``edge_convs == 2`` (Static:131-136): Linear(Fe -> 2Fe) -> norm over the layer's edges -> ReLU -> Linear(2Fe -> F_in)."""
+    w0: torch.Tensor             # [2Fe, Fe]
+    b0: torch.Tensor
+    norm: NormSpec
+    w3: torch.Tensor             # [f_in, 2Fe]
+    b3: torch.Tensor
+
+
+@dataclass
 class ConvSpec:
     f_in: int                    # unpadded
     f_out: int
     w_i: torch.Tensor            # [f_out, f_in]
     w_j: torch.Tensor
     b_j: torch.Tensor
-    w_e: Optional[torch.Tensor]  # [f_in, fe] or None (edge_convs == 0)
+    w_e: Optional[torch.Tensor]  # [f_in, fe] or None (edge_convs == 0 or 2)
     b_e: Optional[torch.Tensor]
     norm: Optional[NormSpec]
+    edge_mlp: Optional[EdgeMlpSpec] = None
 
 
 @dataclass
@@ -170,6 +181,7 @@ class Saved:
     z_d: Optional[torch.Tensor] = None
     aff_d: Optional[Affine] = None
     graphs: List[EllGraph] = field(default_factory=list)
+    edge: List[Optional[tuple]] = field(default_factory=list)   # edge_convs == 2: (e1, aff_e, phi_in, w0p, w3p) per layer
 
 
 def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGraph], pk_wt, pk_bias, w_e, b_e, fe,
@@ -201,12 +213,60 @@ def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_a
     sh = ptr(in_aff.shift) if in_aff else None
     call("dgnn_gather_tc_fwd", ptr(x_in), sc, sh, int(relu_in), ptr(g.nbr), ptr(g.ea_in), pk.fe, ptr(pk.w_e),
          ptr(pk.b_e), n_tgt, pk.f_in, ptr(agg), _stream())
+    return _dense_from_agg(agg, x_in, in_aff, relu_in, n_tgt, pk, out_aff, relu_out, want_stats, out_rows)
+
+
+def _dense_from_agg(agg, x_in, in_aff, relu_in, n_tgt, pk: PackedConv, out_aff, relu_out, want_stats, out_rows=None):
+    """z = [agg | h(x_in)] . [W_j | W_i]^T (dgnn_dense_fwd_tc)."""
+    dev = x_in.device
+    sc = ptr(in_aff.scale) if in_aff else None
+    sh = ptr(in_aff.shift) if in_aff else None
     out = torch.empty((out_rows or n_tgt, pk.f_out), dtype=torch.float32, device=dev)
     stats = torch.empty((lib().dgnn_tc_grid(), 2, pk.f_out), dtype=torch.float64, device=dev) if want_stats else None
     call("dgnn_dense_fwd_tc", ptr(agg), ptr(x_in), sc, sh, int(relu_in), ptr(pk.b_fwd), ptr(pk.bias),
          ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None, int(relu_out), n_tgt,
          pk.f_in, pk.f_out, ptr(out), ptr(stats), _stream())
     return out, agg, stats
+
+
+def _edge_mlp_fwd(em: EdgeMlpSpec, g: EllGraph, f_in_p: int, batch_stats: bool, training: bool):
+    """phi for every (target, slot) from the two-layer edge MLP, evaluated over the layer's edges in edge-list order so
+    that the norm statistics are taken over exactly the rows the reference normalises (``edge_attr[e_id]``).
+    Returns (e1 pre-norm [E, 2Fe], its norm affine, phi [n_tgt*4, f_in] in incoming order, padded weights)."""
+    if g.ea_edges is None or g._eid_in is None:
+        raise DgnnError("edge_convs == 2 needs the edge-list layout (graph.build_from_edges)")
+    ea = g.ea_edges
+    dev = ea.device
+    n_e, fe_p = ea.shape
+    h1 = em.w0.shape[0]
+    if h1 % 4:
+        raise NotImplementedError("edge MLP hidden width must be a multiple of 4")
+    w0p = _pad2(em.w0.detach(), h1, fe_p).contiguous()
+    w3p = _pad2(em.w3.detach(), f_in_p, h1).contiguous()
+    b3p = _pad1(em.b3.detach(), f_in_p).contiguous()
+    if batch_stats or em.norm.mode == 1:
+        e1, _, stats = _layer_fwd(ea, None, False, None, w0p.t().contiguous(), em.b0.detach().contiguous(), None, None, 0,
+                                  None, False, n_e, fe_p, h1, False, True)
+        aff_e = batch_affine(em.norm, stats, n_e, h1, dev, update_running=training)
+    else:
+        e1, _, _ = _layer_fwd(ea, None, False, None, w0p.t().contiguous(), em.b0.detach().contiguous(), None, None, 0,
+                              None, False, n_e, fe_p, h1, False, False)
+        aff_e = eval_affine(em.norm, h1, dev)
+    phi_e, _, _ = _layer_fwd(e1, aff_e, True, None, w3p.t().contiguous(), b3p, None, None, 0, None, False, n_e, h1,
+                             f_in_p, False, False)
+    phi_in = torch.empty((g.n_tgt * 4, f_in_p), dtype=torch.float32, device=dev)
+    call("dgnn_gather_rows", ptr(phi_e), ptr(g._eid_in), g.n_tgt * 4, f_in_p, ptr(phi_in), _stream())
+    return e1, aff_e, phi_in, w0p, w3p
+
+
+def _layer_fwd_edge_mlp(h, in_aff, relu_in, g, pk, phi_in, out_aff, relu_out, want_stats, out_rows=None):
+    """One conv layer whose edge filter is a materialised matrix: aggregation (dgnn_gather_phi_fwd), then the dense part."""
+    if pk.b_fwd is None:
+        raise NotImplementedError("edge_convs == 2 needs widths the tensor-core dense kernel supports")
+    agg = torch.empty((g.n_tgt, pk.f_in), dtype=torch.float32, device=h.device)
+    call("dgnn_gather_phi_fwd", ptr(h), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
+         int(relu_in), ptr(g.nbr), ptr(phi_in), g.n_tgt, pk.f_in, ptr(agg), _stream())
+    return _dense_from_agg(agg, h, in_aff, relu_in, g.n_tgt, pk, out_aff, relu_out, want_stats, out_rows)
 
 
 def _global_stats(stats, n_rows, comm):
@@ -248,8 +308,17 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             raise NotImplementedError("normalization must be 'b' or 'l' (the reference crashes otherwise, Static:218)")
         split = pk.b_fwd is not None and pk.fe > 0 and lib().dgnn_gather_tc_supported(pk.f_in, pk.fe)
         out_rows = g.n_src if (comm is not None and l + 1 < L) else g.n_tgt
+        edge = None
+        if c.edge_mlp is not None:
+            if comm is not None:
+                raise NotImplementedError("edge_convs == 2 on a partitioned scene")
+            edge = _edge_mlp_fwd(c.edge_mlp, g, pk.f_in, batch_stats, training)
+        if save:
+            sv.edge.append(edge)
         if batch_stats:
-            if split:
+            if edge is not None:
+                z, agg, stats = _layer_fwd_edge_mlp(h, in_aff, relu_in, g, pk, edge[2], None, False, True, out_rows)
+            elif split:
                 z, agg, stats = _gather_then_dense(h, in_aff, relu_in, g, pk, None, False, True, out_rows=out_rows)
             else:
                 z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None,
@@ -264,7 +333,9 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             h, in_aff, relu_in = z, aff, True
         else:
             aff = eval_affine(c.norm, pk.f_out, dev)
-            if split:
+            if edge is not None:
+                h, _, _ = _layer_fwd_edge_mlp(h, in_aff, relu_in, g, pk, edge[2], aff, True, False, out_rows)
+            elif split:
                 h, _, _ = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False, out_rows=out_rows)
             else:
                 h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
@@ -466,7 +537,46 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor, comm=None):
         grads["convs.%d.w_i" % l] = dw[:, pk.f_in:pk.f_in + c.f_in]
         need_prev = l > 0
         tc_gather = use_tensor_cores() and pk.fe > 0 and lib().dgnn_gather_tc_supported(pk.f_in, pk.fe)
-        if tc_gather:
+        if c.edge_mlp is not None:
+            em = c.edge_mlp
+            e1, aff_e, phi_in, w0p, w3p = sv.edge[l]
+            n_e, h1 = e1.shape
+            sc_in = ptr(in_aff.scale) if in_aff else None
+            sh_in = ptr(in_aff.shift) if in_aff else None
+            # d phi for every (target, slot), then back to edge-list order
+            dphi_in = torch.empty((g.n_tgt * 4, pk.f_in), dtype=torch.float32, device=dev)
+            call("dgnn_upd_edge_bwd", ptr(x_in), sc_in, sh_in, int(relu_in), ptr(g.nbr), ptr(d_agg), None, None, None,
+                 g.n_tgt, pk.f_in, ptr(dphi_in), st)
+            dphi_e = torch.zeros((n_e, pk.f_in), dtype=torch.float32, device=dev)
+            call("dgnn_scatter_rows", ptr(dphi_in), ptr(g._eid_in), g.n_tgt * 4, pk.f_in, ptr(dphi_e), st)
+            noaff, nocoef = Affine(None, None, None, None), (None, None, None)
+            _, d_h1, db3, dw3 = _dense_and_dw(dphi_e, phi_in, nocoef, noaff, w3p, None, None, e1, aff_e, True, n_e, h1,
+                                              pk.f_in)
+            grads["convs.%d.e3_w" % l] = dw3[:c.f_in]
+            grads["convs.%d.e3_b" % l] = db3[:c.f_in]
+            part = torch.empty((small, 2 * h1), dtype=torch.float64, device=dev)
+            dy1 = torch.empty_like(d_h1)
+            call("dgnn_act_bwd", ptr(d_h1), ptr(e1), ptr(aff_e.scale), ptr(aff_e.shift), ptr(aff_e.mean), ptr(aff_e.rstd),
+                 1, n_e, h1, ptr(dy1), ptr(part), st)
+            r = _reduce(part)
+            s1e, s2e = r[:h1], r[h1:]
+            grads["convs.%d.e_norm_w" % l], grads["convs.%d.e_norm_b" % l] = s2e, s1e
+            coeffs_e = _norm_coeffs(em.norm, aff_e, s1e, s2e, n_e, h1)
+            _, _, db0, dw0 = _dense_and_dw(dy1, e1, coeffs_e, aff_e, w0p, None, None, g.ea_edges, None, False, n_e,
+                                           g.ea_edges.shape[1], h1)
+            grads["convs.%d.e0_w" % l] = dw0[:, :em.w0.shape[1]]
+            grads["convs.%d.e0_b" % l] = db0
+            if need_prev:
+                dh = torch.empty((g.n_src, pk.f_in), dtype=torch.float32, device=dev)
+                call("dgnn_gather_phi_bwd", ptr(d_agg), ptr(d_self), ptr(g.onbr), ptr(g.orow()), ptr(phi_in), None, 0,
+                     g.n_src, g.n_tgt, pk.f_in, ptr(dh), st)
+                part = torch.empty((small, 2 * pk.f_in), dtype=torch.float64, device=dev)
+                call("dgnn_act_bwd", ptr(dh), ptr(x_in), sc_in, sh_in, ptr(in_aff.mean) if in_aff else None,
+                     ptr(in_aff.rstd) if in_aff else None, int(relu_in), g.n_src, pk.f_in, ptr(dh), ptr(part), st)
+                r = _reduce(part)
+                s1, s2 = r[:pk.f_in], r[pk.f_in:]
+                dy = dh
+        elif tc_gather:
             # dh / dy_prev / (S1,S2) and dW_e / db_e with the edge filter on tensor cores
             tcg = lib().dgnn_tc_grid()
             part = torch.empty((tcg, 2 * pk.f_in), dtype=torch.float64, device=dev) if need_prev else None

@@ -58,6 +58,21 @@ class EllGraph:
     inv: Optional[torch.Tensor] = None       # int32[n]: old -> new
     _eid_in: Optional[torch.Tensor] = None   # int32[n_tgt,4]: local edge id of every (target, slot), -1 = none
     _eid_out: Optional[torch.Tensor] = None  # int32[n_src,4]: local edge id of every (source, out-slot), -1 = none
+    ea_edges: Optional[torch.Tensor] = None  # float32[E, fe]: edge attributes in edge-list order (edge_convs == 2)
+    _orow: Optional[torch.Tensor] = None     # int32[n_src,4]: row 4t+k (incoming order) of every out-edge, -1 = none
+
+    def orow(self) -> torch.Tensor:
+        """Row of the incoming-order edge matrix [n_tgt*4, .] that holds the out-edge (s, j): inverts _eid_in."""
+        if self._orow is None:
+            dev = self._eid_in.device
+            flat = self._eid_in.reshape(-1)
+            ok = flat >= 0
+            n_edges = int(flat.max().item()) + 1 if flat.numel() else 0
+            row_of_edge = torch.full((max(n_edges, 1),), -1, dtype=torch.int32, device=dev)
+            row_of_edge[flat[ok].long()] = torch.arange(flat.numel(), dtype=torch.int32, device=dev)[ok]
+            eo = self._eid_out
+            self._orow = torch.where(eo >= 0, row_of_edge[eo.clamp(min=0).long()], torch.full_like(eo, -1)).contiguous()
+        return self._orow
 
     def permute_rows(self, x: torch.Tensor) -> torch.Tensor:
         """Rows of ``x`` (caller order, width multiple of 4) in internal order."""
@@ -200,7 +215,7 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
                              "(self-loops / cliques are not supported by the ELL-4 layout)")
     if code != 0:
         raise _lib.DgnnError("dgnn_ell_build: edge endpoint out of range (code %d)" % code)
-    ea_in = ea_own = None
+    ea_in = ea_own = ea = None
     if edge_attr is not None:
         if e_id is None:
             rows = edge_attr
@@ -215,4 +230,4 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
             ea_own = torch.empty((n_src, 4, fe), dtype=torch.float32, device=dev)
             call("dgnn_gather_rows", ptr(ea), ptr(eid_out), n_src * 4, fe, ptr(ea_own), st)
     return EllGraph(n_src=n_src, n_tgt=n_tgt, fe=fe, nbr=nbr, ea_in=ea_in, onbr=onbr, ea_own=ea_own, _eid_in=eid_in,
-                    _eid_out=eid_out)
+                    _eid_out=eid_out, ea_edges=ea)

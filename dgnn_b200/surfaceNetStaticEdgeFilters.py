@@ -19,7 +19,7 @@ from torch.nn import Linear
 
 from . import engine
 from ._lib import DgnnError, check_device
-from .engine import ConvSpec, NetSpec, NormSpec
+from .engine import ConvSpec, EdgeMlpSpec, NetSpec, NormSpec
 from .graph import EllGraph, build_from_edges, build_full_graph, pad4, pad_cols
 
 
@@ -146,14 +146,16 @@ class SurfaceNet(nn.Module):
 
     # ------------------------------------------------------------------ parameter views
     def _spec(self) -> NetSpec:
-        if self.clf.model.edge_convs == 2:
-            raise NotImplementedError("edge_convs == 2 (two-layer edge MLP with a norm over edges) has no CUDA "
-                                      "kernel yet; no shipped config uses it")
         convs = []
         for blk in self.convs:
             c = blk.conv
             le = c.lin_e
             norm = blk.norm.spec() if blk.norm is not None else None
+            if isinstance(le, nn.Sequential):        # edge_convs == 2 (Static:131-136)
+                em = EdgeMlpSpec(le[0].weight, le[0].bias, le[1].spec(), le[3].weight, le[3].bias)
+                convs.append(ConvSpec(c.lin_i.in_features, c.lin_i.out_features, c.lin_i.weight, c.lin_j.weight,
+                                      c.lin_j.bias, None, None, norm, edge_mlp=em))
+                continue
             convs.append(ConvSpec(c.lin_i.in_features, c.lin_i.out_features, c.lin_i.weight, c.lin_j.weight,
                                   c.lin_j.bias, le.weight if le is not None else None,
                                   le.bias if le is not None else None, norm))
@@ -174,7 +176,12 @@ class SurfaceNet(nn.Module):
             c = blk.conv
             names += ["convs.%d.w_i" % l, "convs.%d.w_j" % l, "convs.%d.b_j" % l]
             params += [c.lin_i.weight, c.lin_j.weight, c.lin_j.bias]
-            if c.lin_e is not None:
+            if isinstance(c.lin_e, nn.Sequential):
+                en = c.lin_e[1].spec()
+                names += ["convs.%d.e0_w" % l, "convs.%d.e0_b" % l, "convs.%d.e_norm_w" % l, "convs.%d.e_norm_b" % l,
+                          "convs.%d.e3_w" % l, "convs.%d.e3_b" % l]
+                params += [c.lin_e[0].weight, c.lin_e[0].bias, en.weight, en.bias, c.lin_e[3].weight, c.lin_e[3].bias]
+            elif c.lin_e is not None:
                 names += ["convs.%d.w_e" % l, "convs.%d.b_e" % l]
                 params += [c.lin_e.weight, c.lin_e.bias]
             if blk.norm is not None:
@@ -229,7 +236,7 @@ class SurfaceNet(nn.Module):
                 raise ValueError("need one adjacency per layer (%d), got %d" % (self.num_layers, len(adjs)))
             ea_all = data.all.edge_attr if self.clf.model.edge_convs else None
             full = all(a[2][0] == a[2][1] == n_id.numel() for a in adjs) and \
-                all(a[0].data_ptr() == adjs[0][0].data_ptr() for a in adjs)
+                all(a[0].data_ptr() == adjs[0][0].data_ptr() for a in adjs) and self.clf.model.edge_convs != 2
             key = ("train", n_id.data_ptr(), tuple(a[0].data_ptr() for a in adjs), n_id.numel())
 
             def build():
@@ -267,6 +274,8 @@ class SurfaceNet(nn.Module):
                 if self.clf.model.edge_convs:
                     ea = data_all.edge_attr[:, 1:] if self.clf.regularization.edge_type else data_all.edge_attr
                 pos = getattr(data_all, "pos", None)
+                if self.clf.model.edge_convs == 2:   # the edge MLP is evaluated over the edge list
+                    return build_from_edges(data_all.edge_index.to(torch.long), None, ea, n, n, dev, need_backward=False)
                 return build_full_graph(data_all.edge_index.to(torch.long), ea, n, dev, pos=pos, order="auto",
                                         need_backward=False)
 

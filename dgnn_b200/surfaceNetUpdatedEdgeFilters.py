@@ -238,7 +238,7 @@ class _UpdFn(torch.autograd.Function):
                 d_agg, d_self, db_l, dw_cat = engine._dense_and_dw(d_out, s.out, _NOCOEF, _NOAFF, s.w_cat, g, s.agg,
                                                                    s.x_in, None, s.relu_in, n_tgt, fi, fo)
                 dphi = torch.empty((n_tgt * 4, fi), dtype=torch.float32, device=dev)
-                call("dgnn_upd_edge_bwd", ptr(s.x_in), int(s.relu_in), ptr(g.nbr), ptr(d_agg), ptr(s.phi),
+                call("dgnn_upd_edge_bwd", ptr(s.x_in), None, None, int(s.relu_in), ptr(g.nbr), ptr(d_agg), ptr(s.phi),
                      ptr(de_next), ptr(s.eid_glob), n_tgt, fi, ptr(dphi), st)
                 _, d_ea, db_e, dw_e = engine._dense_and_dw(dphi, s.phi, _NOCOEF, _NOAFF, s.w_e, None, None, s.ea, None,
                                                            s.relu_in, n_tgt * 4, s.k_in, fi)

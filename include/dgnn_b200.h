@@ -169,9 +169,11 @@ int dgnn_gather_phi_fwd(const float* x_in, const float* in_scale, const float* i
                         const int32_t* nbr, const float* phi, int64_t n_tgt, int f, float* agg, void* stream);
 /* Backward of that aggregation (autograd of Updated:157-176, :236-241 in the reference).
  *   dphi[t,k,:] = h(x_in[nbr[t,k]]) (*) d_agg[t]  +  (phi[t,k,:] > 0) * de_next[eid[t,k],:]
+ *   h(s) = relu?(x_in[s]*in_scale + in_shift)  (in_scale NULL: no affine)
  * d_agg already divided by max(cnt,1) (dgnn_dense_bwd); de_next float32[E_all,f] indexed by the global
  * edge id eid int32[n_tgt,4] = gradient arriving through relu(edge state) from the next layer (NULL: none). */
-int dgnn_upd_edge_bwd(const float* x_in, int relu_in, const int32_t* nbr, const float* d_agg,
+int dgnn_upd_edge_bwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
+                      const int32_t* nbr, const float* d_agg,
                       const float* phi, const float* de_next, const int32_t* eid, int64_t n_tgt, int f,
                       float* dphi, void* stream);
 /*   dx[s] = relu'(x_in[s]) * ( d_self[s] (s < n_tgt) + sum_j phi[orow[s,j],:] (*) d_agg[onbr[s,j]] )

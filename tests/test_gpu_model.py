@@ -140,27 +140,30 @@ def test_train_sampled_closure_matches_oracle(golden, kw):
     _train_compare(kw, data, d, n_sup)
 
 
-def test_golden_train_step_a(golden):
-    """The reference's own train step (golden case 'a'): logits, loss and every gradient."""
+@pytest.mark.parametrize("tag,kw", [("a", dict(convs=(16, 32, 32, 32))),
+                                    ("c", dict(convs=(16, 32, 32, 32), edge_convs=2, decoder=2, normalization="l"))])
+def test_golden_train_step(golden, tag, kw):
+    """The reference's own train step on a sampled closure (golden cases 'a': shipped options, 'c': two-layer edge
+    MLP + graph LayerNorm): logits, loss and every gradient."""
     from dgnn_b200 import runModel as rm
     d = golden_data(golden)
-    state = {k[len("train_a_init."):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith("train_a_init.")}
-    kw = dict(convs=(16, 32, 32, 32))
+    pre = "train_%s_" % tag
+    state = {k[len(pre + "init."):]: torch.from_numpy(v) for k, v in golden.items() if k.startswith(pre + "init.")}
     net = cuda_net(kw, state).train()
-    n_id = torch.from_numpy(golden["train_a_n_id"])
-    adjs = [(torch.from_numpy(golden["train_a_adj%d_ei" % i]), torch.from_numpy(golden["train_a_adj%d_eid" % i]),
-             tuple(int(v) for v in golden["train_a_adj%d_size" % i])) for i in range(5)]
+    n_id = torch.from_numpy(golden[pre + "n_id"])
+    adjs = [(torch.from_numpy(golden[pre + "adj%d_ei" % i]), torch.from_numpy(golden[pre + "adj%d_eid" % i]),
+             tuple(int(v) for v in golden[pre + "adj%d_size" % i])) for i in range(5)]
     data = to_attr(dict(all=d, batch_n_id=n_id, batch_adjs=adjs))
     z = net(data)
     n_sup = adjs[3][2][1]
     clf = make_clf(device=DEV, **kw)
     loss = rm.cell_loss(z, d.y[n_id[:n_sup]], d.x[n_id[:n_sup]], clf)
     loss.backward()
-    err, ok = logits_close(z.detach().cpu().numpy(), golden["train_a_logits"])
+    err, ok = logits_close(z.detach().cpu().numpy(), golden[pre + "logits"])
     assert ok, err
-    assert abs(loss.item() - float(golden["train_a_loss"])) <= 2e-5
+    assert abs(loss.item() - float(golden[pre + "loss"])) <= 2e-5
     for k, p in net.named_parameters():
-        e, tol = grad_close(p.grad, torch.from_numpy(golden["train_a_grad." + k]))
+        e, tol = grad_close(p.grad, torch.from_numpy(golden[pre + "grad." + k]))
         assert e <= tol, (k, e, tol)
 
 
@@ -207,9 +210,25 @@ def test_training_reduces_loss_and_matches_oracle_trajectory():
 def test_unsupported_options_fail_loudly():
     from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
     g = make_graph(60, seed=1)
-    net = SurfaceNet(make_clf(device=DEV, edge_convs=2)).to(DEV).eval()
+    net = SurfaceNet(make_clf(device=DEV, convs=(18, 32, 32, 32))).to(DEV).eval()   # hidden width not a multiple of 4
     with pytest.raises(NotImplementedError):
         net.inference_layer(data_all(g))
+
+
+@pytest.mark.parametrize("norm", ["b", "l"])
+def test_train_two_layer_edge_mlp(norm):
+    """Row C with ``edge_convs == 2`` (Linear -> norm over the edges -> ReLU -> Linear as the edge filter): a whole
+    train step (logits, loss, every gradient, running statistics) against the oracle, and eval-mode inference."""
+    g = make_graph(500, seed=31)
+    d = data_all(g)
+    kw = dict(convs=(16, 32, 32, 32), edge_convs=2, normalization=norm)
+    net, ref = _train_compare(kw, full_batch(d), d, d.x.shape[0])
+    if norm == "b":
+        net.eval(); ref.eval()
+        with torch.no_grad():
+            z, zr = net.inference_layer(d), ref.inference_layer(d)
+        err, ok = logits_close(z.cpu().numpy(), zr.numpy())
+        assert ok, err
 
 
 def test_updated_edge_filters_forward_matches_reference_golden(golden):
