@@ -30,6 +30,7 @@ constexpr int NPW = 16;                        // producer warps
 constexpr int TC_THREADS = (NPW + 2) * 32;     // + 1 MMA warp + 1 TMA (weight slice) warp
 constexpr int A_ATOM_BYTES = TC_M * ATOM_ROW_BYTES;  // 16 KB
 constexpr int MAX_STAGES = 4;
+constexpr int RAW_DEPTH = 4;                   // dense forward: raw input atoms staged by cp.async this many atoms ahead
 
 enum { MODE_FWD_DENSE = 0, MODE_FWD_GATHER = 1, MODE_BWD = 2 };
 
@@ -150,6 +151,30 @@ __device__ __forceinline__ void load_raw(const TcArgs& p, int64_t tile0, int a, 
             if (f < p.f_in) r.v[it] = ldg4((raw_agg ? p.agg_in : p.x_in) + (size_t)t * p.f_in + f);
         }
     }
+}
+
+// dense forward: the thread's two 16-byte pieces of raw atom `a` go global -> shared by cp.async into the slot the same
+// thread reads back later (thread-private: no cross-thread synchronisation, no registers held while in flight)
+__device__ __forceinline__ void issue_raw_fwd(const TcArgs& p, uint32_t slot, int64_t tile0, int a, int warp, int lane) {
+    const int c = (lane & 7) * 4;
+    const bool raw_agg = a < p.ka_agg;
+    const int f = (raw_agg ? a : a - p.ka_agg) * ATOM_K + c;
+    const float* src = raw_agg ? p.agg_in : p.x_in;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int row = warp * 8 + (lane >> 3) + it * 4;
+        const int64_t t = tile0 + row;
+        if (t < p.n_tgt && f < p.f_in) {
+            const uint32_t dst = slot + atom_off(row, c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + (size_t)t * p.f_in + f));
+        }
+    }
+    cp_async_commit();
+}
+__device__ __forceinline__ void read_raw_fwd(uint32_t slot, int warp, int lane, RawAtom& r) {
+    const int c = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) r.v[it] = lds128(slot + atom_off(warp * 8 + (lane >> 3) + it * 4, c));
 }
 
 template <int MODE>
@@ -499,7 +524,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
         float4 dbacc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) dbacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE != MODE_FWD_GATHER && (int64_t)blockIdx.x < n_tiles) load_raw<MODE>(p, (int64_t)blockIdx.x * TC_M, 0, warp, lane, cur);
+        if (MODE == MODE_BWD && (int64_t)blockIdx.x < n_tiles) load_raw<MODE>(p, (int64_t)blockIdx.x * TC_M, 0, warp, lane, cur);
+        // dense forward: cp.async ring of raw atoms behind the operand stages, RAW_DEPTH - 1 atoms ahead of the stores
+        const uint32_t raw_base = smem_u32(smem) + (uint32_t)p.stages * (uint32_t)stage_bytes;
+        int64_t ld_tile = blockIdx.x;
+        int ld_a = 0;
+        uint32_t ld_i = 0, st_i = 0;
+        auto issue_next = [&]() {
+            if (ld_tile < n_tiles) issue_raw_fwd(p, raw_base + (ld_i % RAW_DEPTH) * (uint32_t)A_ATOM_BYTES, ld_tile * TC_M, ld_a, warp, lane);
+            else cp_async_commit();
+            ++ld_i;
+            if (++ld_a == p.ka) { ld_a = 0; ld_tile += gridDim.x; }
+        };
+        if (MODE == MODE_FWD_DENSE)
+            for (int i = 0; i < RAW_DEPTH - 1; ++i) issue_next();
         int4 nb_epi = make_int4(-1, -1, -1, -1);
         auto load_nb_epi = [&](int64_t t0) {           // the epilogue's row of the ELL table (1/cnt of d_agg)
             if (MODE == MODE_BWD && p.nbr != nullptr) {
@@ -515,7 +553,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
             for (int a = 0; a < p.ka; ++a) {
                 uint8_t* a_hi = smem + (size_t)s * stage_bytes;
                 uint8_t* a_lo = a_hi + A_ATOM_BYTES;
-                if (MODE != MODE_FWD_GATHER) {
+                if (MODE == MODE_FWD_DENSE) {
+                    issue_next();
+                    cp_async_wait<RAW_DEPTH - 1>();
+                    read_raw_fwd(raw_base + (st_i % RAW_DEPTH) * (uint32_t)A_ATOM_BYTES, warp, lane, cur);
+                    ++st_i;
+                }
+                if (MODE == MODE_BWD) {
                     // loads of the next atom (possibly of the next tile) go in flight before this one is processed
                     const bool last = a + 1 == p.ka;
                     const int64_t ntile = last ? tile + gridDim.x : tile;
@@ -527,7 +571,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                     else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
                 } else {
                     store_raw<MODE>(p, a_hi, a_lo, tile0, a, warp, lane, cur, (MODE == MODE_BWD && p.db_partials) ? red_db : nullptr, dbacc);
-                    cur = nxt;
+                    if (MODE == MODE_BWD) cur = nxt;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -644,14 +688,15 @@ extern "C" int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len,
 
 // ring depth: the gather mode keeps >= 90 KB of the SM's 228 KB as L1 for the neighbour rows; the streaming
 // (dense / backward) modes use all the shared memory they can get for a deeper ring
-static int tc_stage_config(int np, bool gather, int* stages, size_t* smem) {
+// raw_ring: bytes reserved behind the operand stages (dense forward: RAW_DEPTH raw atoms)
+static int tc_stage_config(int np, bool gather, int* stages, size_t* smem, int raw_ring = 0) {
     int stage_bytes = 2 * A_ATOM_BYTES + 2 * np * ATOM_ROW_BYTES;
-    int s = ((gather ? 132 : 200) * 1024) / stage_bytes;
+    int s = ((gather ? 132 : 200) * 1024 - raw_ring) / stage_bytes;
     if (s > MAX_STAGES) s = MAX_STAGES;
     if (s < 2) s = 2;
-    if ((size_t)s * stage_bytes + 1024 > 200 * 1024) return 1;
+    if ((size_t)s * stage_bytes + raw_ring + 1024 > 200 * 1024) return 1;
     *stages = s;
-    *smem = (size_t)s * stage_bytes + 1024;
+    *smem = (size_t)s * stage_bytes + raw_ring + 1024;
     return 0;
 }
 
@@ -698,7 +743,8 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.agg_save = agg_save; p.stats = stats;
     size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, nbr != nullptr, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    DGNN_REQUIRE(tc_stage_config(p.np, nbr != nullptr, &p.stages, &smem, nbr == nullptr ? RAW_DEPTH * A_ATOM_BYTES : 0) == 0,
+                 "tile does not fit shared memory");
     cudaStream_t st = as_stream(stream);
     if (nbr == nullptr) return launch_tc<MODE_FWD_DENSE, 0>(p, smem, st, "dgnn_layer_fwd_tc");
     switch (fe) {
@@ -735,7 +781,7 @@ extern "C" int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const floa
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.stats = stats;
     size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem) == 0, "tile does not fit shared memory");
+    DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem, RAW_DEPTH * A_ATOM_BYTES) == 0, "tile does not fit shared memory");
     return launch_tc<MODE_FWD_DENSE, 0>(p, smem, as_stream(stream), "dgnn_dense_fwd_tc");
 }
 
