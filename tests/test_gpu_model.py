@@ -311,3 +311,18 @@ def test_updated_edge_filters_full_graph_training_matches_oracle(name):
     with torch.no_grad():
         y2 = m(to_attr(batch))
     assert torch.equal(y2, y.detach())
+
+
+@pytest.mark.parametrize("n_points", [5, 6, 9])
+def test_tiny_graphs(n_points):
+    """Smallest tetrahedralisations (one to a handful of tetrahedra plus their infinite cells; far fewer rows than one
+    128-cell tile): inference and a train step still match the oracle."""
+    g = make_graph(n_points, seed=40 + n_points, scan_like=False)
+    d = data_all(g)
+    kw = dict(convs=(16, 32, 32, 32))
+    net, ref = _train_compare(kw, full_batch(d), d, d.x.shape[0])
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        z, zr = net.inference_layer(d), ref.inference_layer(d)
+    err, ok = logits_close(z.cpu().numpy(), zr.numpy())
+    assert ok, err
