@@ -32,6 +32,8 @@ SIGNATURES = {
     "dgnn_gather_rows": [P, P, L, I, P, P],
     "dgnn_scatter_rows": [P, P, L, I, P, P],
     "dgnn_add_rows": [P, P, L, I, P, P],
+    "dgnn_column_moments": [P, L, I, I, I, P, P, I, P],
+    "dgnn_column_affine": [P, L, I, I, I, P, P, I, P, P],
     "dgnn_edge_relayout": [P, P, P, P, L, I, P, P, P],
     "dgnn_edge_relayout_idx": [P, P, P, P, P, L, I, P, P, P],
     "dgnn_layer_grid": [I, I],

@@ -277,3 +277,63 @@ extern "C" int dgnn_edge_relayout_idx(const float* ea, const int64_t* e_id, cons
                                                                        fe / 4, ea_in, ea_own);
     return check_launch("dgnn_edge_relayout_idx");
 }
+
+// ---- per-graph feature standardisation (processing/data.py:467-506: sklearn StandardScaler per graph) --------------
+// columns col0 .. col0+c-1 of x float32[n, ld]:  partials[block][0][j] = sum (x - m_j), partials[block][1][j] = sum (x - m_j)^2
+// (m = NULL: zeros).  One thread per row chunk, double accumulation, per-block partials (deterministic).
+namespace dgnn {
+constexpr int STD_MAXC = 64;
+__global__ void __launch_bounds__(256) column_moments_kernel(const float* __restrict__ x, long long n, int ld, int col0,
+                                                             int c, const double* __restrict__ m,
+                                                             double* __restrict__ partials) {
+    __shared__ double red[2][256];
+    // thread = (row lane rsub, column): rows_per_pass = blockDim.x / c
+    const int col = threadIdx.x % c, rsub = threadIdx.x / c, rpp = blockDim.x / c;
+    double s1 = 0.0, s2 = 0.0;
+    if (rsub < rpp) {
+        const double mj = m ? m[col] : 0.0;
+        for (long long r = (long long)blockIdx.x * rpp + rsub; r < n; r += (long long)gridDim.x * rpp) {
+            const double d = (double)x[r * ld + col0 + col] - mj;
+            s1 += d; s2 += d * d;
+        }
+    }
+    red[0][threadIdx.x] = s1; red[1][threadIdx.x] = s2;
+    __syncthreads();
+    if (threadIdx.x < c) {                              // fixed summation order over the row lanes
+        double a = 0.0, b = 0.0;
+        for (int q = 0; q < rpp; ++q) { a += red[0][q * c + threadIdx.x]; b += red[1][q * c + threadIdx.x]; }
+        partials[(size_t)blockIdx.x * 2 * c + threadIdx.x] = a;
+        partials[(size_t)blockIdx.x * 2 * c + c + threadIdx.x] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) column_affine_kernel(const float* __restrict__ x, long long n, int ld, int col0,
+                                                            int c, const double* __restrict__ shift,
+                                                            const double* __restrict__ inv_scale, int ld_out,
+                                                            float* __restrict__ out) {
+    const long long total = n * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / c;
+        const int j = (int)(i % c);
+        out[r * ld_out + col0 + j] = (float)(((double)x[r * ld + col0 + j] - shift[j]) * inv_scale[j]);
+    }
+}
+}  // namespace dgnn
+
+extern "C" int dgnn_column_moments(const float* x, int64_t n, int ld, int col0, int c, const double* center,
+                                   double* partials, int n_blocks, void* stream) {
+    DGNN_REQUIRE(x && partials, "null pointer");
+    DGNN_REQUIRE(c > 0 && c <= dgnn::STD_MAXC && col0 >= 0 && col0 + c <= ld, "column range");
+    DGNN_REQUIRE(n_blocks > 0, "n_blocks");
+    dgnn::column_moments_kernel<<<n_blocks, 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, center, partials);
+    return check_launch("dgnn_column_moments");
+}
+
+extern "C" int dgnn_column_affine(const float* x, int64_t n, int ld, int col0, int c, const double* shift,
+                                  const double* inv_scale, int ld_out, float* out, void* stream) {
+    DGNN_REQUIRE(x && shift && inv_scale && out, "null pointer");
+    DGNN_REQUIRE(c > 0 && col0 >= 0 && col0 + c <= ld && col0 + c <= ld_out, "column range");
+    if (n <= 0) return 0;
+    dgnn::column_affine_kernel<<<ggrid(n * c), 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, shift, inv_scale, ld_out, out);
+    return check_launch("dgnn_column_affine");
+}

@@ -83,6 +83,16 @@ int dgnn_edge_relayout_idx(const float* ea, const int64_t* e_id, const int32_t* 
                            const int32_t* perm, int64_t n, int fe, float* ea_in, float* ea_own,
                            void* stream);
 
+/* ---- loader: per-graph feature standardisation (processing/data.py:467-506, sklearn StandardScaler) -----------
+ * Columns col0 .. col0+c-1 (c <= 64) of x float32[n, ld].  dgnn_column_moments writes per-block partial sums
+ * double[n_blocks, 2, c] of (x - center_j) and (x - center_j)^2 (center NULL = 0): a first pass gives the means, a
+ * second pass centred on them the variances (the numerically stable two-pass form sklearn uses).
+ * dgnn_column_affine writes out[r, col0+j] = float((x[r, col0+j] - shift[j]) * inv_scale[j]); out may alias x. */
+int dgnn_column_moments(const float* x, int64_t n, int ld, int col0, int c, const double* center,
+                        double* partials, int n_blocks, void* stream);
+int dgnn_column_affine(const float* x, int64_t n, int ld, int col0, int c, const double* shift,
+                       const double* inv_scale, int ld_out, float* out, void* stream);
+
 /* ---- one message-passing layer, forward (Static:66-96 + norm/ReLU of the producer) ------
  * For target row t < n_tgt (targets are the first n_tgt source rows):
  *   h(s)   = in_scale ? relu?(x_in[s]*in_scale + in_shift) : relu?(x_in[s])   (relu iff relu_in)
