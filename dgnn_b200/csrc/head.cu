@@ -29,11 +29,21 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int n_par
     __shared__ double red_s[32], red_q[32];
     double tot_s = 0.0, tot_q = 0.0;
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int p = 0; p < n_partials; ++p) {
-            s += stats[(size_t)p * 2 * c + ch];
-            q += stats[(size_t)p * 2 * c + c + ch];
+        // four independent accumulators per sum (loads in flight together), combined in a fixed order
+        double s4[4] = {0.0, 0.0, 0.0, 0.0}, q4[4] = {0.0, 0.0, 0.0, 0.0};
+        int p = 0;
+        for (; p + 4 <= n_partials; p += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s4[u] += stats[(size_t)(p + u) * 2 * c + ch];
+                q4[u] += stats[(size_t)(p + u) * 2 * c + c + ch];
+            }
         }
+        for (; p < n_partials; ++p) {
+            s4[0] += stats[(size_t)p * 2 * c + ch];
+            q4[0] += stats[(size_t)p * 2 * c + c + ch];
+        }
+        const double s = (s4[0] + s4[1]) + (s4[2] + s4[3]), q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
         if (mode == 0) {
             double n = (double)n_rows;
             double m = s / n;
@@ -274,19 +284,25 @@ __global__ void __launch_bounds__(256) edge_reg_kernel(const float* __restrict__
 }
 
 // ---- generic partial reductions ---------------------------------------------------------------
-__global__ void reduce_partials_kernel(const double* __restrict__ p, int np, int len, float* __restrict__ out) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= len) return;
+// out[j] = sum_i p[i, j] in double.  256 threads = 32 columns x 8 lanes; lane q adds the partials i = q, q+8, ..., the
+// eight lane sums are added in lane order: a fixed summation tree, so the result is reproducible run to run.
+template <typename T>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const T* __restrict__ p, int np, long long len,
+                                                              float* __restrict__ out) {
+    __shared__ double red[8][32];
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const long long j = (long long)blockIdx.x * 32 + lane;
     double s = 0.0;
-    for (int i = 0; i < np; ++i) s += p[(size_t)i * len + j];
-    out[j] = (float)s;
-}
-__global__ void reduce_partials_f32_kernel(const float* __restrict__ p, int np, long long len, float* __restrict__ out) {
-    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= len) return;
-    double s = 0.0;
-    for (int i = 0; i < np; ++i) s += (double)p[(size_t)i * len + j];
-    out[j] = (float)s;
+    if (j < len)
+        for (int i = q; i < np; i += 8) s += (double)p[(size_t)i * len + j];
+    red[q][lane] = s;
+    __syncthreads();
+    if (q == 0 && j < len) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][lane];
+        out[j] = (float)t;
+    }
 }
 
 __global__ void norm_bwd_coeffs_kernel(const float* s1, const float* s2, long long n_rows, int c, const float* weight,
@@ -534,12 +550,12 @@ extern "C" int dgnn_edge_reg_fwd(const float* logits, const int64_t* src, const 
 
 extern "C" int dgnn_reduce_partials(const double* partials, int n_partials, int len, float* out, void* stream) {
     if (len <= 0) return 0;
-    reduce_partials_kernel<<<(len + 127) / 128, 128, 0, as_stream(stream)>>>(partials, n_partials, len, out);
+    reduce_partials_kernel<double><<<(len + 31) / 32, 256, 0, as_stream(stream)>>>(partials, n_partials, len, out);
     return check_launch("dgnn_reduce_partials");
 }
 extern "C" int dgnn_reduce_partials_f32(const float* partials, int n_partials, int64_t len, float* out, void* stream) {
     if (len <= 0) return 0;
-    reduce_partials_f32_kernel<<<(int)((len + 127) / 128), 128, 0, as_stream(stream)>>>(partials, n_partials, len, out);
+    reduce_partials_kernel<float><<<(int)((len + 31) / 32), 256, 0, as_stream(stream)>>>(partials, n_partials, len, out);
     return check_launch("dgnn_reduce_partials_f32");
 }
 extern "C" int dgnn_norm_bwd_coeffs(const float* s1, const float* s2, int64_t n_rows, int c, const float* weight,
