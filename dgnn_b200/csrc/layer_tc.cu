@@ -420,16 +420,30 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                 st_sq[j] += (double)warp_colsum32(sq);
             }
         } else if (tv) {
+            // columns [0, f_in) of the tile are d_agg (x 1/cnt), [f_in, 2 f_in) d_self.  A 32-column chunk lies entirely in one
+            // of them at the 32-multiple widths; its row pointer is formed once (not re-read from the constant bank per store)
+            const bool has_agg = p.nbr != nullptr;
+            const bool all_agg = has_agg && c0 + 32 <= p.f_in;
+            const bool all_self = !has_agg || c0 >= p.f_in;
+            if ((all_agg || all_self) && c0 + 32 <= n_real && (p.f_in & 7) == 0) {
+                float* dst = (all_agg ? p.d_agg : p.d_self) + (size_t)t * p.f_in + (all_agg ? c0 : (has_agg ? c0 - p.f_in : c0));
+                const float s = all_agg ? icnt : 1.f;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const int n = c0 + i;
-                if (n >= n_real) continue;
-                const bool is_agg = p.nbr != nullptr && n < p.f_in;
-                float s = is_agg ? icnt : 1.f;
-                float* dst = is_agg ? p.d_agg : p.d_self;
-                int col = is_agg ? n : (p.nbr ? n - p.f_in : n);
-                *reinterpret_cast<float4*>(dst + (size_t)t * p.f_in + col) =
-                    make_float4(v[i] * s, v[i + 1] * s, v[i + 2] * s, v[i + 3] * s);
+                for (int i = 0; i < 32; i += 8)
+                    stg8(dst + i, make_float4(v[i] * s, v[i + 1] * s, v[i + 2] * s, v[i + 3] * s),
+                         make_float4(v[i + 4] * s, v[i + 5] * s, v[i + 6] * s, v[i + 7] * s));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int n = c0 + i;
+                    if (n >= n_real) continue;
+                    const bool is_agg = has_agg && n < p.f_in;
+                    float s = is_agg ? icnt : 1.f;
+                    float* dst = is_agg ? p.d_agg : p.d_self;
+                    int col = is_agg ? n : (has_agg ? n - p.f_in : n);
+                    *reinterpret_cast<float4*>(dst + (size_t)t * p.f_in + col) =
+                        make_float4(v[i] * s, v[i + 1] * s, v[i + 2] * s, v[i + 3] * s);
+                }
             }
         }
     }
