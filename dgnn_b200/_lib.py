@@ -49,7 +49,7 @@ SIGNATURES = {
     "dgnn_gather_tc_bwd": [P, P, P, P, I, P, P, P, P, P, P, P, I, L, L, I, P, P, P, P],
     "dgnn_dense_fwd_tc": [P, P, P, P, I, P, P, P, P, I, L, I, I, P, P, P],
     "dgnn_dw_tc_supported": [I, I],
-    "dgnn_dw_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P, P],
+    "dgnn_dw_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P, P, P],
     "dgnn_debug_umma": [P, I, P, I, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, I, P, P],
     "dgnn_gather_phi_fwd": [P, P, P, I, P, P, L, I, P, P],
     "dgnn_upd_edge_bwd": [P, P, P, I, P, P, P, P, P, L, I, P, P],

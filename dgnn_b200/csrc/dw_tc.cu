@@ -42,6 +42,7 @@ struct DwTcArgs {
     int f_in, f_out, k_total, np, stages;
     int wpb, active_warps;   // producer warps per 32-channel block; warps that produce (the rest idle)
     float* partials;  // [grid][f_out][k_total]
+    double* db_partials;  // [grid][f_out] column sums of dz (bias gradient), may be NULL
 };
 
 // 4x4 transpose across the 4 lanes 4q..4q+3: in: lane j holds (c0..c3) of cell j; out: lane j holds
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[DW_MAX_STAGES], bar_empty[DW_MAX_STAGES], bar_done;
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float red_db[DW_NPW][32];                 // per producer warp: column sums of its 32-channel dz block
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b_bytes = p.np * 128;
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             }
         };
         uint32_t s = 0, ph = 0;
+        float4 dbv = make_float4(0.f, 0.f, 0.f, 0.f);  // running sum of this thread's dz values (its 4 channels): db
         Batch cur, nxt;
         const bool on = kind >= 0;
         load_batch(cell_first, on && n_batches > 0, cur);
@@ -217,12 +220,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                         v.y = tv ? fmaf(k0.y, v.y, -fmaf(zv.y, k2.y, k1.y)) : 0.f;
                         v.z = tv ? fmaf(k0.z, v.z, -fmaf(zv.z, k2.z, k1.z)) : 0.f;
                         v.w = tv ? fmaf(k0.w, v.w, -fmaf(zv.w, k2.w, k1.w)) : 0.f;
+                        dbv.x += v.x; dbv.y += v.y; dbv.z += v.z; dbv.w += v.w;
                     } else if (affine) {
                         const bool tv = tb + u * ustep < n_tgt32;
                         v.x = tv ? act(v.x, k0.x, k1.x, relu) : 0.f; v.y = tv ? act(v.y, k0.y, k1.y, relu) : 0.f;
                         v.z = tv ? act(v.z, k0.z, k1.z, relu) : 0.f; v.w = tv ? act(v.w, k0.w, k1.w, relu) : 0.f;
                     } else if (kind == 2 && relu) {
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    } else if (kind == 0) {                 // dz = dy (no normalisation): padding rows are zero already
+                        dbv.x += v.x; dbv.y += v.y; dbv.z += v.z; dbv.w += v.w;
                     }
                     v = transpose4(v, j);                   // now: channel `row`, cells 4g .. 4g+3
                     const uint32_t off = dst0 + ((((uint32_t)g) ^ rsw) << 4);
@@ -239,6 +245,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             }
             cur = nxt;
         }
+        // db: sum over the 4 cells of a lane group, then one float4 per (warp, chunk); warps of a block are added below
+        dbv.x += __shfl_xor_sync(0xffffffffu, dbv.x, 1); dbv.y += __shfl_xor_sync(0xffffffffu, dbv.y, 1);
+        dbv.z += __shfl_xor_sync(0xffffffffu, dbv.z, 1); dbv.w += __shfl_xor_sync(0xffffffffu, dbv.w, 1);
+        dbv.x += __shfl_xor_sync(0xffffffffu, dbv.x, 2); dbv.y += __shfl_xor_sync(0xffffffffu, dbv.y, 2);
+        dbv.z += __shfl_xor_sync(0xffffffffu, dbv.z, 2); dbv.w += __shfl_xor_sync(0xffffffffu, dbv.w, 2);
+        if (j == 0) *reinterpret_cast<float4*>(&red_db[warp][c * 4]) = is_a ? dbv : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (warp < DW_NPW) {
+        if (lane < 8) *reinterpret_cast<float4*>(&red_db[warp][lane * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp < DW_NPW) {
         // read this CTA's partial out of TMEM
@@ -272,6 +286,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (p.db_partials != nullptr) {                      // channel ch lives in block ch / 32, produced by wpb warps
+        for (int ch = tid; ch < p.f_out; ch += DW_THREADS) {
+            double a = 0.0;
+            for (int w = 0; w < p.wpb; ++w) a += (double)red_db[(ch >> 5) * p.wpb + w][ch & 31];
+            p.db_partials[(size_t)blockIdx.x * p.f_out + ch] = a;
+        }
+    }
     if (warp == DW_NPW) tmem_dealloc(tmem_base, 256);
 }
 
@@ -288,7 +309,7 @@ extern "C" int dgnn_dw_tc_supported(int f_out, int k_total) {
 extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
                               const float* mean, const float* rstd, const float* agg, const float* x_in,
                               const float* in_scale, const float* in_shift, int relu_in, int64_t n_tgt, int f_in,
-                              int f_out, int k_total, float* partials, void* stream) {
+                              int f_out, int k_total, float* partials, double* db_partials, void* stream) {
     DGNN_REQUIRE(dgnn_dw_tc_supported(f_out, k_total), "widths not supported by the tensor-core dW kernel");
     DGNN_REQUIRE(k_total == (agg ? 2 * f_in : f_in), "k_total mismatch");
     DGNN_REQUIRE(dy && x_in && partials, "null pointer");
@@ -304,6 +325,7 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
         p.stages = st > DW_MAX_STAGES ? DW_MAX_STAGES : (st < 2 ? 2 : st);
     }
     p.partials = partials;
+    p.db_partials = db_partials;
     const int nb = (f_out + 31) / 32 + p.np / 32;      // operand blocks of 32 channels (<= 12)
     p.wpb = nb * 4 <= DW_NPW ? 4 : (nb * 2 <= DW_NPW ? 2 : 1);
     p.active_warps = nb * p.wpb;

@@ -179,7 +179,7 @@ __device__ __forceinline__ void read_raw_fwd(uint32_t slot, int warp, int lane, 
 
 template <int MODE>
 __device__ __forceinline__ void store_raw(const TcArgs& p, uint8_t* a_hi, uint8_t* a_lo, int64_t tile0, int a, int warp,
-                                          int lane, const RawAtom& r, float* red_db, float4 (&dbacc)[4]) {
+                                          int lane, const RawAtom& r, float* red_db) {
     const int c = (lane & 7) * 4;
     if (MODE == MODE_BWD) {
         const int f = a * ATOM_K + c;
@@ -207,21 +207,14 @@ __device__ __forceinline__ void store_raw(const TcArgs& p, uint8_t* a_hi, uint8_
             store_split4(a_hi, a_lo, row, c, v);
         }
         if (red_db != nullptr) {
-            if (a < 4) {
-                // column sums of dz (-> db) stay in registers for the first 4 atoms (f_out <= 128): one running
-                // float4 per atom and thread, reduced over rows / warps once at the end of the kernel
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (a == k) { dbacc[k].x += cs.x; dbacc[k].y += cs.y; dbacc[k].z += cs.z; dbacc[k].w += cs.w; }
-            } else {
-                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-                if (lane < 8 && f < p.f_out) {
-                    atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
-                    atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
-                }
+            // column sums of dz (-> db).  Only used when the dW kernel (which owns db at f_out <= 128, dw_tc.cu) is not.
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+            if (lane < 8 && f < p.f_out) {
+                atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
+                atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
             }
         }
     } else {
@@ -535,9 +528,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
         uint32_t tile_cnt = 0, s = 0, use = 0;
         int64_t prev_tile0 = -1;
         RawAtom cur, nxt;                              // raw rows of the atom being stored / the next one
-        float4 dbacc[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dbacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODE == MODE_BWD && (int64_t)blockIdx.x < n_tiles) load_raw<MODE>(p, (int64_t)blockIdx.x * TC_M, 0, warp, lane, cur);
         // dense forward: cp.async ring of raw atoms behind the operand stages, RAW_DEPTH - 1 atoms ahead of the stores
         const uint32_t raw_base = smem_u32(smem) + (uint32_t)p.stages * (uint32_t)stage_bytes;
@@ -584,7 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                     if (a < p.ka_agg) produce_agg<FE>(p, a_hi, a_lo, tile0, a * ATOM_K, warp, lane);
                     else produce_rows(p, a_hi, a_lo, tile0, (a - p.ka_agg) * ATOM_K, warp, lane);
                 } else {
-                    store_raw<MODE>(p, a_hi, a_lo, tile0, a, warp, lane, cur, (MODE == MODE_BWD && p.db_partials) ? red_db : nullptr, dbacc);
+                    store_raw<MODE>(p, a_hi, a_lo, tile0, a, warp, lane, cur, (MODE == MODE_BWD && p.db_partials) ? red_db : nullptr);
                     if (MODE == MODE_BWD) cur = nxt;
                 }
                 fence_proxy_async_smem();
@@ -612,22 +602,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
             mbar_wait(&bar_acc_full[pacc], ((tile_cnt - 1) >> 1) & 1);
             tc_fence_after_sync();
             epilogue<MODE>(p, tmem_base + pacc * (uint32_t)p.np, prev_tile0, warp, lane, st_sum, st_sq, nb_epi);
-        }
-        if (MODE == MODE_BWD && p.db_partials != nullptr) {
-            const int c = (lane & 7) * 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float4 cs = dbacc[k];
-                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-                cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-                cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-                const int f = k * ATOM_K + c;
-                if (lane < 8 && f < p.f_out) {
-                    atomicAdd(&red_db[f], cs.x); atomicAdd(&red_db[f + 1], cs.y);
-                    atomicAdd(&red_db[f + 2], cs.z); atomicAdd(&red_db[f + 3], cs.w);
-                }
-            }
         }
         if (MODE != MODE_BWD && p.stats != nullptr) {
             const int grp = warp >> 2;

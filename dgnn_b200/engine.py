@@ -421,25 +421,32 @@ def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, i
     gq, aq, bq = coeffs
     d_self = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev)
     d_agg = torch.empty((agg_rows or n_tgt, f_in), dtype=torch.float32, device=dev) if g is not None else None
-    if use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 1 if g is not None else 0) and f_out <= 256:
+    tc_dw = use_tensor_cores() and lib().dgnn_dw_tc_supported(f_out, k_total)
+    tc_dense = use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 1 if g is not None else 0) and f_out <= 256
+    db_from_dw = tc_dw and tc_dense          # the dW kernel forms dz anyway and sums its columns (db) on the way
+    if tc_dense:
         # operand B of the backward: [W_j | W_i]^T, i.e. rows = columns of d[agg|self], K = f_out
         b_bwd = pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
         db_p = torch.empty((lib().dgnn_tc_grid(), f_out), dtype=torch.float64, device=dev)
         call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(b_bwd),
-             ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, ptr(d_agg), ptr(d_self), ptr(db_p), _stream())
+             ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, ptr(d_agg), ptr(d_self),
+             None if db_from_dw else ptr(db_p), _stream())
     else:
         grid = lib().dgnn_layer_grid(f_in, f_out)
         db_p = torch.empty((grid, f_out), dtype=torch.float64, device=dev)
         call("dgnn_dense_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(w_cat),
              ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, k_total, ptr(d_agg), ptr(d_self), ptr(db_p),
              _stream())
-    db = _reduce(db_p)
-    tc_dw = use_tensor_cores() and lib().dgnn_dw_tc_supported(f_out, k_total)
     splits = lib().dgnn_tc_grid() if tc_dw else lib().dgnn_dw_splits(f_out, k_total)
     dw_p = torch.empty((splits, f_out, k_total), dtype=torch.float32, device=dev)
-    call("dgnn_dw_bwd_tc" if tc_dw else "dgnn_dw_bwd", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(agg), ptr(x_in),
-         ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None, int(relu_in), n_tgt, f_in,
-         f_out, k_total, ptr(dw_p), _stream())
+    args = (ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(agg), ptr(x_in),
+            ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None, int(relu_in), n_tgt, f_in,
+            f_out, k_total, ptr(dw_p))
+    if tc_dw:
+        call("dgnn_dw_bwd_tc", *args, ptr(db_p) if db_from_dw else None, _stream())
+    else:
+        call("dgnn_dw_bwd", *args, _stream())
+    db = _reduce(db_p)
     dw = torch.empty((f_out, k_total), dtype=torch.float32, device=dev)
     call("dgnn_reduce_partials_f32", ptr(dw_p), splits, f_out * k_total, ptr(dw), _stream())
     return d_agg, d_self, db, dw

@@ -162,12 +162,15 @@ int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const float* in_scale
                       double* stats, void* stream);
 
 /* dW on tensor cores with a TMEM-resident accumulator (f_out <= 128, k_total <= 256);
- * partials float[dgnn_tc_grid(), f_out, k_total], summed by dgnn_reduce_partials_f32. */
+ * partials float[dgnn_tc_grid(), f_out, k_total], summed by dgnn_reduce_partials_f32.
+ * db_partials (nullable) double[dgnn_tc_grid(), f_out]: column sums of dz = the bias gradient (then
+ * dgnn_dense_bwd_tc may be called with db_partials == NULL). */
 int dgnn_dw_tc_supported(int f_out, int k_total);
 int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
                    const float* mean, const float* rstd,
                    const float* agg, const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
-                   int64_t n_tgt, int f_in, int f_out, int k_total, float* partials, void* stream);
+                   int64_t n_tgt, int f_in, int f_out, int k_total, float* partials, double* db_partials,
+                   void* stream);
 
 /* development probe (tools/probe_umma.py): one tcgen05.mma on caller-provided smem images */
 int dgnn_debug_umma(const uint8_t* a_img, int a_bytes, const uint8_t* b_img, int b_bytes, uint64_t a_desc,

@@ -126,14 +126,16 @@ def test_dw_tc_matches_fp64(n, f_in, f_out, gather):
     assert lib().dgnn_dw_tc_supported(f_out, k_total)
     part = torch.empty(lib().dgnn_tc_grid(), f_out, k_total, device=DEV)
     st = torch.cuda.current_stream().cuda_stream
+    db_p = torch.empty(lib().dgnn_tc_grid(), f_out, dtype=torch.float64, device=DEV)
     call("dgnn_dw_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(mean), ptr(rstd), ptr(agg), ptr(x), ptr(sc),
-         ptr(sh), 1, n, f_in, f_out, k_total, ptr(part), st)
+         ptr(sh), 1, n, f_in, f_out, k_total, ptr(part), ptr(db_p), st)
     dw = part.double().sum(0)
     dz = gq.double() * dy.double() - (aq.double() + (z.double() - mean.double()) * rstd.double() * bq.double())
     h = torch.relu(x.double() * sc.double() + sh.double())
     A = torch.cat([agg.double(), h], 1) if gather else h
     ref = dz.t() @ A
     assert _rel(dw, ref) < 5e-6
+    np.testing.assert_allclose(db_p.sum(0).cpu().numpy(), dz.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)   # bias gradient
 
 
 @pytest.mark.parametrize("f_in,fe,ragged", [(28, 20, False), (64, 20, True), (128, 20, False), (128, 4, True)])

@@ -32,8 +32,8 @@ dwe = torch.empty((tcg, f, 32), device=DEV)
 steps = [
     ("gather_fwd", lambda: call("dgnn_gather_tc_fwd", ptr(x), ptr(sc), ptr(sh), 1, ptr(eg.nbr), ptr(eg.ea_in), fe, ptr(w_e), ptr(b_e), n, f, ptr(agg), st)),
     ("dense_fwd", lambda: call("dgnn_dense_fwd_tc", ptr(agg), ptr(x), ptr(sc), ptr(sh), 1, ptr(b_fwd), ptr(bias), None, None, 0, n, f, f, ptr(z), ptr(stats), st)),
-    ("dense_bwd", lambda: call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(g3[0]), ptr(g3[1]), ptr(g3[2]), ptr(mean), ptr(rstd), ptr(b_bwd), ptr(eg.nbr), n, f, f, ptr(d_agg), ptr(d_self), ptr(db_p), st)),
-    ("dw_bwd", lambda: call("dgnn_dw_bwd_tc", ptr(dy), ptr(z), ptr(g3[0]), ptr(g3[1]), ptr(g3[2]), ptr(mean), ptr(rstd), ptr(agg), ptr(x), ptr(sc), ptr(sh), 1, n, f, f, 2 * f, ptr(dw_p), st)),
+    ("dense_bwd", lambda: call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(g3[0]), ptr(g3[1]), ptr(g3[2]), ptr(mean), ptr(rstd), ptr(b_bwd), ptr(eg.nbr), n, f, f, ptr(d_agg), ptr(d_self), None, st)),
+    ("dw_bwd", lambda: call("dgnn_dw_bwd_tc", ptr(dy), ptr(z), ptr(g3[0]), ptr(g3[1]), ptr(g3[2]), ptr(mean), ptr(rstd), ptr(agg), ptr(x), ptr(sc), ptr(sh), 1, n, f, f, 2 * f, ptr(dw_p), ptr(db_p), st)),
     ("gather_bwd", lambda: call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x), ptr(sc), ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f, ptr(dyp), ptr(part), None, st)),
     ("dwe_bwd", lambda: call("dgnn_gather_tc_bwd", ptr(d_agg), ptr(d_self), ptr(eg.onbr), ptr(eg.ea_own), fe, ptr(w_e), ptr(b_e), ptr(x), ptr(sc), ptr(sh), ptr(mean), ptr(rstd), 1, n, n, f, None, None, ptr(dwe), st)),
 ]
