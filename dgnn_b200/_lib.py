@@ -32,6 +32,11 @@ SIGNATURES = {
     "dgnn_gather_rows": [P, P, L, I, P, P],
     "dgnn_scatter_rows": [P, P, L, I, P, P],
     "dgnn_add_rows": [P, P, L, I, P, P],
+    "dgnn_sampler_degree": [P, L, P, P, P],
+    "dgnn_sampler_expand": [P, L, P, P, P, P, P, P, P],
+    "dgnn_sampler_set_loc": [P, L, I, P, P],
+    "dgnn_sampler_mark": [P, L, P, P, P, P],
+    "dgnn_sampler_assign": [P, L, P, P, L, P, P, P, P, P],
     "dgnn_column_moments": [P, L, I, I, I, P, P, I, P],
     "dgnn_column_affine": [P, L, I, I, I, P, P, I, P, P],
     "dgnn_edge_relayout": [P, P, P, P, L, I, P, P, P],

@@ -1,0 +1,103 @@
+"""Full-neighbourhood closure sampler on the device.
+
+The reference trains on seed batches: ``NeighborSampler(edge_index, node_idx, sizes=[-1] * hops, batch_size, shuffle,
+return_e_id)`` (``run.py:59-74``) yields ``(batch_size, n_id, adjs)`` — for every hop all in-edges of the current node
+list, the node list extended by the newly reached sources in order of first appearance, ``adjs`` outermost hop first,
+each ``(edge_index in local ids, e_id, (n_src, n_tgt))`` — which ``SurfaceNet.forward`` consumes as
+``data.batch_n_id / data.batch_adjs``.  PyG builds this on the host; here the k frontier expansions run on the GPU over
+the in-edge ELL-4 table (``dgnn_sampler_*``), bit-exact against the oracle's restatement of the PyG sampler
+(``tests/test_gpu_sampler.py``).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import DgnnError, call, check_device, ptr
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class NeighborSampler:
+    """Drop-in for the way the reference uses PyG's ``NeighborSampler`` (all neighbours, ``return_e_id=True``).
+
+    ``edge_index`` int64[2, E] (``[0]`` = source, ``[1]`` = target; at most 4 in-edges per node, as in a cell graph);
+    ``sizes`` must be all -1; ``node_idx`` = the seed nodes (default: all); ``shuffle`` draws a new seed permutation
+    every epoch with ``torch.randperm`` on the device.  Iterating yields ``(batch_size, n_id, adjs)`` with all tensors on
+    ``device``."""
+
+    def __init__(self, edge_index: torch.Tensor, sizes, batch_size: int, node_idx: Optional[torch.Tensor] = None,
+                 num_nodes: Optional[int] = None, shuffle: bool = False, device="cuda:0"):
+        if any(s != -1 for s in sizes):
+            raise NotImplementedError("only full neighbourhoods (sizes = [-1] * hops), as in every reference config")
+        self.device = torch.device(device)
+        check_device(self.device.index or 0)
+        self.sizes = list(sizes)
+        self.batch_size = int(batch_size)
+        self.shuffle = shuffle
+        ei = edge_index.to(self.device, dtype=torch.int64).contiguous()
+        n = int(ei.max().item()) + 1 if num_nodes is None else int(num_nodes)
+        self.num_nodes = n
+        e = ei.shape[1]
+        with torch.cuda.device(self.device):
+            self.in_src = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+            self.in_eid = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+            cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
+            err = torch.zeros(1, dtype=torch.int32, device=self.device)
+            call("dgnn_ell_build", ptr(ei[0]), ptr(ei[1]), e, n, ptr(self.in_src), ptr(self.in_eid), ptr(cnt), ptr(err),
+                 _stream())
+            code = int(err.item())
+        if code == 3:
+            raise DgnnError("a node has more than 4 in-edges: not a Delaunay cell graph")
+        if code:
+            raise DgnnError("dgnn_ell_build: edge endpoint out of range (code %d)" % code)
+        self.node_idx = (torch.arange(n, device=self.device) if node_idx is None
+                         else node_idx.to(self.device, dtype=torch.int64).contiguous())
+        # scratch shared by all batches: local id of a node in the current n_id (-1 = absent), first-appearance position
+        self._loc = torch.full((n,), -1, dtype=torch.int32, device=self.device)
+        self._first = torch.full((n,), 0x7fffffff, dtype=torch.int32, device=self.device)
+
+    def __len__(self):
+        return (self.node_idx.numel() + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        idx = self.node_idx
+        if self.shuffle:
+            idx = idx[torch.randperm(idx.numel(), device=self.device)]
+        for s in range(0, idx.numel(), self.batch_size):
+            yield self.sample(idx[s:s + self.batch_size])
+
+    def sample(self, batch: torch.Tensor):
+        dev = self.device
+        with torch.cuda.device(dev):
+            st = _stream()
+            n_id = batch.to(dev, dtype=torch.int64).contiguous()
+            call("dgnn_sampler_set_loc", ptr(n_id), n_id.numel(), 0, ptr(self._loc), st)
+            adjs = []
+            for _ in self.sizes:
+                n_tgt = n_id.numel()
+                deg = torch.empty(n_tgt, dtype=torch.int64, device=dev)
+                call("dgnn_sampler_degree", ptr(n_id), n_tgt, ptr(self.in_src), ptr(deg), st)
+                incl = torch.cumsum(deg, 0)
+                offs = (incl - deg).contiguous()
+                n_e = int(incl[-1].item()) if n_tgt else 0
+                e_id = torch.empty(n_e, dtype=torch.int64, device=dev)
+                src_g = torch.empty(n_e, dtype=torch.int64, device=dev)
+                edge_local = torch.empty((2, n_e), dtype=torch.int64, device=dev)
+                call("dgnn_sampler_expand", ptr(n_id), n_tgt, ptr(self.in_src), ptr(self.in_eid), ptr(offs), ptr(e_id),
+                     ptr(src_g), ptr(edge_local[1]), st)
+                flag = torch.empty(n_e, dtype=torch.int64, device=dev)
+                call("dgnn_sampler_mark", ptr(src_g), n_e, ptr(self._loc), ptr(self._first), ptr(flag), st)
+                rank = torch.cumsum(flag, 0)
+                n_new = int(rank[-1].item()) if n_e else 0
+                new_ids = torch.empty(n_new, dtype=torch.int64, device=dev)
+                call("dgnn_sampler_assign", ptr(src_g), n_e, ptr(flag), ptr(rank), n_tgt, ptr(self._loc), ptr(self._first),
+                     ptr(new_ids), ptr(edge_local[0]), st)
+                n_id = torch.cat([n_id, new_ids]) if n_new else n_id
+                adjs.append((edge_local, e_id, (n_id.numel(), n_tgt)))
+            call("dgnn_sampler_set_loc", ptr(n_id), n_id.numel(), -1, ptr(self._loc), st)   # scratch back to "absent"
+        adjs = adjs[0] if len(adjs) == 1 else adjs[::-1]
+        return batch.numel(), n_id, adjs

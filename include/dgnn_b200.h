@@ -83,6 +83,25 @@ int dgnn_edge_relayout_idx(const float* ea, const int64_t* e_id, const int32_t* 
                            const int32_t* perm, int64_t n, int fe, float* ea_in, float* ea_own,
                            void* stream);
 
+/* ---- neighbour-closure sampler on the device (run.py:59-74: NeighborSampler(sizes=[-1]*hops)) -----------------
+ * in_src / in_eid int32[N,4]: the in-edge table of dgnn_ell_build (sources and edge ids, ascending edge id, -1 pad).
+ * One hop over the node list n_id int64[n_tgt] (targets = all of it), every step a grid-stride kernel:
+ *   dgnn_sampler_degree  deg[t] = in-degree of n_id[t]                       (caller: offsets = exclusive prefix sum)
+ *   dgnn_sampler_expand  edges in (target, ascending edge id) order: e_id, global source, local target
+ *   dgnn_sampler_set_loc loc[ids[i]] = base + i  (base < 0: reset to -1); loc int32[N] is -1 for nodes not in n_id
+ *   dgnn_sampler_mark    first[s] = min edge position whose source s is new (first int32[N], INT_MAX when idle);
+ *                        flag[p] = 1 iff position p is that first appearance          (caller: rank = inclusive prefix sum)
+ *   dgnn_sampler_assign  new_ids[rank-1] = source, loc[source] = n_tgt + rank - 1, first reset; src_local[p] = loc[src] */
+int dgnn_sampler_degree(const int64_t* n_id, int64_t n_tgt, const int32_t* in_src, int64_t* deg, void* stream);
+int dgnn_sampler_expand(const int64_t* n_id, int64_t n_tgt, const int32_t* in_src, const int32_t* in_eid,
+                        const int64_t* offsets, int64_t* e_id, int64_t* src_global, int64_t* tgt_local, void* stream);
+int dgnn_sampler_set_loc(const int64_t* ids, int64_t n, int base, int32_t* loc, void* stream);
+int dgnn_sampler_mark(const int64_t* src_global, int64_t n_edges, const int32_t* loc, int32_t* first,
+                      int64_t* flag, void* stream);
+int dgnn_sampler_assign(const int64_t* src_global, int64_t n_edges, const int64_t* flag, const int64_t* rank,
+                        int64_t n_tgt, int32_t* loc, int32_t* first, int64_t* new_ids, int64_t* src_local,
+                        void* stream);
+
 /* ---- loader: per-graph feature standardisation (processing/data.py:467-506, sklearn StandardScaler) -----------
  * Columns col0 .. col0+c-1 (c <= 64) of x float32[n, ld].  dgnn_column_moments writes per-block partial sums
  * double[n_blocks, 2, c] of (x - center_j) and (x - center_j)^2 (center NULL = 0): a first pass gives the means, a
