@@ -84,6 +84,7 @@ SIGNATURES = {
     "dgnn_adam_step": [P, P, P, P, L, F, F, F, F, I, P],
     "dgnn_adam_multi": [P, I, L, F, F, F, F, I, P],
     "dgnn_argmax_labels": [P, L, I, P, P],
+    "dgnn_scores": [P, L, I, P, P, P],
     "dgnn_interface_facets": [P, L, P, L, P, P],
 }
 _RET = {"dgnn_last_error": c_char_p}

@@ -421,6 +421,23 @@ __global__ void argmax_labels_kernel(const float* __restrict__ z, long long n, i
         else lab[r] = z[r] > 0.f ? 1 : 0;
     }
 }
+// exportScore (processing/data.py:521-535): sigmoid and softmax of the logits, one pass
+__global__ void scores_kernel(const float* __restrict__ z, long long n, int od, float* __restrict__ sig,
+                              float* __restrict__ soft) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        if (od == 2) {
+            const float a = z[r * 2], b = z[r * 2 + 1];
+            sig[r * 2] = 1.f / (1.f + expf(-a));
+            sig[r * 2 + 1] = 1.f / (1.f + expf(-b));
+            const float m = fmaxf(a, b), ea = expf(a - m), eb = expf(b - m), inv = 1.f / (ea + eb);
+            soft[r * 2] = ea * inv;
+            soft[r * 2 + 1] = eb * inv;
+        } else {
+            sig[r] = 1.f / (1.f + expf(-z[r]));
+            soft[r] = 1.f;                             // softmax over a single column
+        }
+    }
+}
 __global__ void interface_facets_kernel(const uint8_t* __restrict__ lab, long long nf, const int* __restrict__ nfac,
                                         long long n_facets, uint8_t* __restrict__ flag) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_facets; i += (long long)gridDim.x * blockDim.x) {
@@ -600,6 +617,13 @@ extern "C" int dgnn_argmax_labels(const float* logits, int64_t n, int od, uint8_
     if (n <= 0) return 0;
     argmax_labels_kernel<<<grid_for(n, 256, sm_count() * 8), 256, 0, as_stream(stream)>>>(logits, n, od, labels);
     return check_launch("dgnn_argmax_labels");
+}
+extern "C" int dgnn_scores(const float* logits, int64_t n, int od, float* sigmoid, float* softmax, void* stream) {
+    DGNN_REQUIRE(od == 1 || od == 2, "od must be 1 or 2");
+    DGNN_REQUIRE(logits && sigmoid && softmax, "null pointer");
+    if (n <= 0) return 0;
+    scores_kernel<<<grid_for(n, 256, sm_count() * 8), 256, 0, as_stream(stream)>>>(logits, n, od, sigmoid, softmax);
+    return check_launch("dgnn_scores");
 }
 extern "C" int dgnn_interface_facets(const uint8_t* labels_finite, int64_t n_finite, const int32_t* nfacets,
                                      int64_t n_facets, uint8_t* flag, void* stream) {

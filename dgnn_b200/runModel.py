@@ -140,6 +140,18 @@ def labels(logits):
     return out
 
 
+def export_scores(logits):
+    """``dataLoader.exportScore`` (``processing/data.py:521-535``): the arrays the reference writes next to the logits,
+    ``dict(number_of_cells, sigmoid, logits, softmax)`` as host NumPy arrays (computed in one pass on the device)."""
+    z = logits.detach().contiguous().float()
+    if z.dim() == 1:
+        z = z[:, None]
+    sig, soft = torch.empty_like(z), torch.empty_like(z)
+    call("dgnn_scores", ptr(z), z.shape[0], z.shape[1], ptr(sig), ptr(soft), _stream())
+    return dict(number_of_cells=int(z.shape[0]), sigmoid=sig.cpu().numpy(), logits=z.cpu().numpy(),
+                softmax=soft.cpu().numpy())
+
+
 def interface_facets(labels_finite, nfacets):
     """``processing/generate_mesh.py:94-105``: mask of facets whose two cells' labels differ
     (the infinite cell, -1, forced outside)."""

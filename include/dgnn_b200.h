@@ -326,6 +326,8 @@ int dgnn_adam_multi(const int64_t* table, int n_tensors, int64_t max_n, float lr
 
 /* ---- labels / facets (generate_mesh.py:75, 94-105) --------------------------------------- */
 int dgnn_argmax_labels(const float* logits, int64_t n, int od, uint8_t* labels, void* stream);
+/* dataLoader.exportScore (processing/data.py:521-535): sigmoid(logits) and softmax(logits, dim=-1), float32[n, od] each */
+int dgnn_scores(const float* logits, int64_t n, int od, float* sigmoid, float* softmax, void* stream);
 /* nfacets int32[f,2] in finite-cell numbering (-1 = infinite -> outside); flag[f] = 1 if the two
  * cells' labels differ */
 int dgnn_interface_facets(const uint8_t* labels_finite, int64_t n_finite, const int32_t* nfacets,

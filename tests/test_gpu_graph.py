@@ -103,3 +103,16 @@ def test_labels_and_interface_facets_match_oracle(g):
     nf = rng.integers(-1, nfin, size=(5000, 2)).astype(np.int32)
     flag = rm.interface_facets(lab[:nfin].contiguous(), torch.from_numpy(nf))
     assert np.array_equal(np.nonzero(flag.cpu().numpy())[0], og.interface_facets(og.labels_from_logits(z)[:nfin], nf))
+
+
+@pytest.mark.parametrize("od", [1, 2])
+def test_export_scores_match_torch(od):
+    """Row P, ``dataLoader.exportScore``: sigmoid / softmax of the logits as the reference writes them."""
+    from dgnn_b200 import runModel as rm
+    torch.manual_seed(0)
+    z = torch.randn(5000, od) * 6
+    out = rm.export_scores(z.to("cuda:0"))
+    assert out["number_of_cells"] == 5000
+    np.testing.assert_allclose(out["sigmoid"], z.sigmoid().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(out["softmax"], z.softmax(dim=-1).numpy(), rtol=2e-6, atol=1e-7)
+    assert np.array_equal(out["logits"], z.numpy())
