@@ -26,7 +26,7 @@ SIGNATURES = {
     "dgnn_sm_count": [],
     "dgnn_small_grid": [],
     "dgnn_ell_from_adjacency": [P, L, P, P, P, P],
-    "dgnn_ell_build": [P, P, L, L, P, P, P, P, P],
+    "dgnn_ell_build": [P, P, L, L, L, I, P, P, P, P, P],
     "dgnn_morton_codes": [P, L, P, P, I, P, P],
     "dgnn_perm_apply_ell": [P, P, P, L, P, P],
     "dgnn_gather_rows": [P, P, L, I, P, P],
@@ -55,7 +55,6 @@ SIGNATURES = {
     "dgnn_dense_fwd_tc": [P, P, P, P, I, P, P, P, P, I, L, I, I, P, P, P],
     "dgnn_dw_tc_supported": [I, I],
     "dgnn_dw_bwd_tc": [P, P, P, P, P, P, P, P, P, P, P, I, L, I, I, I, P, P, P],
-    "dgnn_debug_umma": [P, I, P, I, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, I, P, P],
     "dgnn_gather_phi_fwd": [P, P, P, I, P, P, L, I, P, P],
     "dgnn_upd_edge_bwd": [P, P, P, I, P, P, P, P, P, L, I, P, P],
     "dgnn_gather_phi_bwd": [P, P, P, P, P, P, I, L, L, I, P, P],
@@ -70,6 +69,7 @@ SIGNATURES = {
     "dgnn_point_loss_fwd": [P, P, I, P, I, I, I, L, P, P],
     "dgnn_point_loss_bwd": [P, P, I, P, I, I, I, L, P, P, P, P],
     "dgnn_edge_reg_fwd": [P, P, P, L, P, P],
+    "dgnn_edge_reg_bwd": [P, P, P, L, L, F, P, P, P, P],
     "dgnn_rowdot_bwd": [P, P, P, P, P, P, I, P, L, I, I, P, P, P],
     "dgnn_act_bwd": [P, P, P, P, P, P, I, L, I, P, P, P],
     "dgnn_reduce_partials": [P, I, I, P, P],

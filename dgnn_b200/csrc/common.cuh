@@ -27,7 +27,10 @@ inline int check_launch(const char* what) {
         if (!(cond)) return ::dgnn::fail(__func__, what);          \
     } while (0)
 
-int sm_count();
+int sm_count();          // SMs of the CURRENT device (cached per device)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: done once per (kernel, device)
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

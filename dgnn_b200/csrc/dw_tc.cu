@@ -8,9 +8,11 @@
 // hardware transpose is not an option.)  The producer warps transpose in registers: 4 lanes hold
 // 4 channels x 1 cell each, two shuffle rounds turn that into 1 channel x 4 cells, i.e. one
 // 16-byte chunk of the K-major (K = cell) swizzled operand row of that channel.
-// The [128 x N] fp32 accumulator (N = k_total <= 256 TMEM columns) stays in TMEM for the whole
+// The [128 x N] fp32 accumulator (N <= 256 TMEM columns) stays in TMEM for the whole
 // lifetime of the persistent CTA; it is read out once at the end as this CTA's partial, and the
 // partials of the 148 CTAs are summed by dgnn_reduce_partials_f32 (deterministic, no atomics).
+// One launch covers a [128 rows of dW] x [256 columns] block; wider layers (f_out > 128 or k_total > 256:
+// modelnet.yaml's 512 / 1024) are run block by block by the launch wrapper.
 // 3xTF32 split as in layer_tc.cu.
 #include "umma.cuh"
 #include "common.cuh"
@@ -39,7 +41,12 @@ struct DwTcArgs {
     const float* in_shift;
     int relu_in;
     int64_t n_tgt;
-    int f_in, f_out, k_total, np, stages;
+    int f_in, f_out, k_total, np, stages;   // f_out / k_total: rows / columns of THIS launch's dW block; f_in: full input width
+    int dz_ld;        // row stride of dy / z (the layer's full f_out; dy, z and the norm coefficients are pre-offset)
+    int k_off;        // first column of the block inside [agg | h]
+    int out_ld;       // row stride of the partials (the layer's full k_total; `partials` is pre-offset to the block)
+    int64_t part_stride;   // floats between the partials of consecutive CTAs (full f_out * full k_total)
+    int db_stride;    // doubles between the db partials of consecutive CTAs (full f_out)
     int wpb, active_warps;   // producer warps per 32-channel block; warps that produce (the rest idle)
     float* partials;  // [grid][f_out][k_total]
     double* db_partials;  // [grid][f_out] column sums of dz (bias gradient), may be NULL
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
         float4 k0 = make_float4(1.f, 1.f, 1.f, 1.f), k1 = make_float4(0.f, 0.f, 0.f, 0.f), k2 = k1, k3 = k1, k4 = k0;
         if (is_a) {
             if (ch < p.f_out) {
-                kind = 0; stride = p.f_out; src = p.dy + ch;
+                kind = 0; stride = p.dz_ld; src = p.dy + ch;
                 if (p.ng != nullptr) {
                     src2 = p.z + ch;
                     k0 = ldg4(p.ng + ch); k1 = ldg4(p.na + ch); k2 = ldg4(p.nb + ch); k3 = ldg4(p.nmean + ch); k4 = ldg4(p.nrstd + ch);
@@ -156,9 +163,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             }
         } else if (ch < p.k_total) {
             stride = p.f_in;
-            if (p.agg != nullptr && ch < p.f_in) { kind = 1; src = p.agg + ch; }
+            const int cha = p.k_off + ch;             // column inside [agg | h]
+            if (p.agg != nullptr && cha < p.f_in) { kind = 1; src = p.agg + cha; }
             else {
-                const int col = p.agg != nullptr ? ch - p.f_in : ch;
+                const int col = p.agg != nullptr ? cha - p.f_in : cha;
                 kind = 2; src = p.x_in + col;
                 if (p.in_scale != nullptr) { k0 = ldg4(p.in_scale + col); k1 = ldg4(p.in_shift + col); }
             }
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
     }
     if (warp < DW_NPW) {
         // read this CTA's partial out of TMEM
-        float* out = p.partials + (size_t)blockIdx.x * p.f_out * p.k_total;
+        float* out = p.partials + (size_t)blockIdx.x * p.part_stride;
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         if (my_groups > 0) {
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
                 for (int i = 0; i < 32; i += 4) {
                     const int n = c0 + i;
                     if (n >= p.k_total) continue;
-                    *reinterpret_cast<float4*>(out + (size_t)row * p.k_total + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    *reinterpret_cast<float4*>(out + (size_t)row * p.out_ld + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }
             }
         }
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
         for (int ch = tid; ch < p.f_out; ch += DW_THREADS) {
             double a = 0.0;
             for (int w = 0; w < p.wpb; ++w) a += (double)red_db[(ch >> 5) * p.wpb + w][ch & 31];
-            p.db_partials[(size_t)blockIdx.x * p.f_out + ch] = a;
+            p.db_partials[(size_t)blockIdx.x * p.db_stride + ch] = a;
         }
     }
     if (warp == DW_NPW) tmem_dealloc(tmem_base, 256);
@@ -303,7 +311,7 @@ using namespace dgnn;
 static inline int ceil32i(int x) { return (x + 31) / 32 * 32; }
 
 extern "C" int dgnn_dw_tc_supported(int f_out, int k_total) {
-    return (f_out % 4 == 0 && k_total % 4 == 0 && f_out <= 128 && ceil32i(k_total) <= 256) ? 1 : 0;
+    return (f_out % 4 == 0 && k_total % 4 == 0 && f_out > 0 && k_total > 0) ? 1 : 0;   // any width: [128 x 256] blocks
 }
 
 extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
@@ -314,28 +322,36 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
     DGNN_REQUIRE(k_total == (agg ? 2 * f_in : f_in), "k_total mismatch");
     DGNN_REQUIRE(dy && x_in && partials, "null pointer");
     DGNN_REQUIRE(n_tgt < (int64_t)1 << 31, "more than 2^31 cells on one GPU");
+    if (int rc_ = ensure_dyn_smem((const void*)dw_tc_kernel, 210 * 1024, "dgnn_dw_bwd_tc")) return rc_;
     DwTcArgs p;
-    p.dy = dy; p.z = z; p.ng = g; p.na = a; p.nb = b; p.nmean = mean; p.nrstd = rstd;
+    memset(&p, 0, sizeof(p));
     p.agg = agg; p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;
-    p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out; p.k_total = k_total;
-    p.np = ceil32i(k_total);
-    {   // as many 32-cell stages as fit 200 KB (2 at 128 -> 128, 4 for the narrow layers)
-        const int stage_bytes = 2 * DW_A_BYTES + 2 * p.np * 128;
-        int st = (200 * 1024) / stage_bytes;
-        p.stages = st > DW_MAX_STAGES ? DW_MAX_STAGES : (st < 2 ? 2 : st);
+    p.n_tgt = n_tgt; p.f_in = f_in;
+    p.dz_ld = f_out; p.out_ld = k_total; p.part_stride = (int64_t)f_out * k_total; p.db_stride = f_out;
+    for (int m0 = 0; m0 < f_out; m0 += 128) {
+        const int mw = f_out - m0 < 128 ? f_out - m0 : 128;
+        p.f_out = mw;
+        p.dy = dy + m0; p.z = z ? z + m0 : nullptr;
+        p.ng = g ? g + m0 : nullptr; p.na = a ? a + m0 : nullptr; p.nb = b ? b + m0 : nullptr;
+        p.nmean = mean ? mean + m0 : nullptr; p.nrstd = rstd ? rstd + m0 : nullptr;
+        for (int n0 = 0; n0 < k_total; n0 += 256) {
+            const int nw = k_total - n0 < 256 ? k_total - n0 : 256;
+            p.k_total = nw; p.k_off = n0;
+            p.np = ceil32i(nw);
+            {   // as many 32-cell stages as fit 200 KB (2 at 128 -> 128, 4 for the narrow layers)
+                const int stage_bytes = 2 * DW_A_BYTES + 2 * p.np * 128;
+                int st = (200 * 1024) / stage_bytes;
+                p.stages = st > DW_MAX_STAGES ? DW_MAX_STAGES : (st < 2 ? 2 : st);
+            }
+            p.partials = partials + (size_t)m0 * k_total + n0;
+            p.db_partials = (db_partials && n0 == 0) ? db_partials + m0 : nullptr;
+            const int nb = (mw + 31) / 32 + p.np / 32;      // operand blocks of 32 channels (<= 12)
+            p.wpb = nb * 4 <= DW_NPW ? 4 : (nb * 2 <= DW_NPW ? 2 : 1);
+            p.active_warps = nb * p.wpb;
+            size_t smem = (size_t)p.stages * (2 * DW_A_BYTES + 2 * p.np * 128) + 1024;
+            dw_tc_kernel<<<sm_count(), DW_THREADS, smem, as_stream(stream)>>>(p);
+            if (int rc = check_launch("dgnn_dw_bwd_tc")) return rc;
+        }
     }
-    p.partials = partials;
-    p.db_partials = db_partials;
-    const int nb = (f_out + 31) / 32 + p.np / 32;      // operand blocks of 32 channels (<= 12)
-    p.wpb = nb * 4 <= DW_NPW ? 4 : (nb * 2 <= DW_NPW ? 2 : 1);
-    p.active_warps = nb * p.wpb;
-    size_t smem = (size_t)p.stages * (2 * DW_A_BYTES + 2 * p.np * 128) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
-        if (e != cudaSuccess) return fail("dgnn_dw_bwd_tc", cudaGetErrorString(e));
-        configured = true;
-    }
-    dw_tc_kernel<<<sm_count(), DW_THREADS, smem, as_stream(stream)>>>(p);
-    return check_launch("dgnn_dw_bwd_tc");
+    return 0;
 }

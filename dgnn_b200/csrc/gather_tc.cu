@@ -47,8 +47,10 @@ struct GatherTcArgs {
     const float* b_e;      // [f]
     int fe;
     int64_t n_rows;
-    int f;                 // feature width (multiple of 4, <= 128)
+    int f;                 // feature width of this launch's slice (multiple of 4, <= 128)
     int fp;                // 32, 64 or 128
+    int ld;                // row stride of x / out / addend / z_prev (the layer's full width; pointers are pre-offset)
+    int s_ld;              // full width: stride of the (S1 | S2) blocks and rows of the dW_e partials per CTA
     float* out;            // fwd: agg [n_rows,f];  bwd: dy_prev [n_rows,f] (may be NULL)
     // backward extras
     const float* addend;   // d_self [n_add_rows, f] (rows >= n_add_rows add nothing), may be NULL
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         const int ksteps = (p.fe + 1 + 7) >> 3;        // fe features + bias column, 8 per k-step (3 for fe = 20)
         const bool relu = (p.relu & 1) != 0;
         const bool affine = p.scale != nullptr;
-        const bool al8 = (p.f & 7) == 0;
+        const bool al8 = ((p.f | p.ld) & 7) == 0;
         const int fe4 = p.fe >> 2;
         uint8_t* xw = x_base + (size_t)warp * WSTAGE;                  // + stage * G_NCW * WSTAGE
         const uint32_t swz_l = ((uint32_t)lane / (8 / CH)) & (CH - 1); // chunk swizzle of this thread's row
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                     }
                     if (sr >= 0 && fcol < p.f) {
                         const uint32_t sw = ((uint32_t)r / (8 / CH)) & (CH - 1);
-                        cp_async16(dst + r * PITCH + (((uint32_t)c_ch ^ sw) << 4), base + (size_t)sr * p.f + fcol);
+                        cp_async16(dst + r * PITCH + (((uint32_t)c_ch ^ sw) << 4), base + (size_t)sr * p.ld + fcol);
                     }
                 }
             }
@@ -369,10 +371,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                                 const float4 oa = make_float4(acc[j] * rcnt, acc[j + 1] * rcnt, acc[j + 2] * rcnt, acc[j + 3] * rcnt);
                                 const float4 ob = make_float4(acc[j + 4] * rcnt, acc[j + 5] * rcnt, acc[j + 6] * rcnt, acc[j + 7] * rcnt);
                                 if (al8) {
-                                    stg8(p.out + (size_t)t * p.f + f0, oa, ob);      // one full 32-byte sector per thread
+                                    stg8(p.out + (size_t)t * p.ld + f0, oa, ob);      // one full 32-byte sector per thread
                                 } else {
-                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = oa;
-                                    if (f0 + 4 < p.f) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = ob;
+                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.ld + f0) = oa;
+                                    if (f0 + 4 < p.f) *reinterpret_cast<float4*>(p.out + (size_t)t * p.ld + f0 + 4) = ob;
                                 }
                             }
                         }
@@ -421,12 +423,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
                             }
                             if (p.out != nullptr) {
                                 if (al8) {
-                                    stg8(p.out + (size_t)t * p.f + f0, make_float4(a8[0], a8[1], a8[2], a8[3]),
+                                    stg8(p.out + (size_t)t * p.ld + f0, make_float4(a8[0], a8[1], a8[2], a8[3]),
                                          make_float4(a8[4], a8[5], a8[6], a8[7]));
                                 } else {
-                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0) = make_float4(a8[0], a8[1], a8[2], a8[3]);
+                                    *reinterpret_cast<float4*>(p.out + (size_t)t * p.ld + f0) = make_float4(a8[0], a8[1], a8[2], a8[3]);
                                     if (fvalid_b)
-                                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.f + f0 + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+                                        *reinterpret_cast<float4*>(p.out + (size_t)t * p.ld + f0 + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
                                 }
                             }
                         }
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     tc_fence_before_sync();
     __syncthreads();
     if (MODE == 1 && p.s_partials != nullptr) {
-        double* my = p.s_partials + (size_t)blockIdx.x * 2 * p.f;
+        double* my = p.s_partials + (size_t)blockIdx.x * 2 * p.s_ld;
         for (int c = tid; c < p.f; c += G_THREADS) {
             const int g = c / CPT, cl = c % CPT;
             double a = 0.0, b2 = 0.0;
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             my[c] = a;
             const double mu = p.p_mean != nullptr ? (double)__ldg(p.p_mean + c) : 0.0;
             const double rs = p.p_rstd != nullptr ? (double)__ldg(p.p_rstd + c) : 1.0;
-            my[p.f + c] = rs * (b2 - mu * a);          // sum(dh * xhat), xhat = (z - mean) * rstd
+            my[p.s_ld + c] = rs * (b2 - mu * a);          // sum(dh * xhat), xhat = (z - mean) * rstd
         }
     }
     if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                     }
                     if (sr >= 0 && fcol < p.f) {
                         const uint32_t sw = ((uint32_t)r / (8 / CH)) & (CH - 1);
-                        cp_async16(dst + r * PITCH + (((uint32_t)c_ch ^ sw) << 4), base + (size_t)sr * p.f + fcol);
+                        cp_async16(dst + r * PITCH + (((uint32_t)c_ch ^ sw) << 4), base + (size_t)sr * p.ld + fcol);
                     }
                 }
             }
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
         // most one phase behind, which makes the parity wait below unambiguous.
         __syncthreads();
         if (grp == 0) {
-            float* outp = p.dwe_partials + (size_t)blockIdx.x * p.f * 32;
+            float* outp = p.dwe_partials + (size_t)blockIdx.x * p.s_ld * 32;
             float v[32];
             if (it > 0) {
                 // every stage's MMAs were issued and committed by some thread of its quarter; the last stage of each
@@ -696,8 +698,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
 using namespace dgnn;
 
 extern "C" int dgnn_gather_tc_supported(int f, int fe) {
-    return (f % 4 == 0 && f >= 4 && f <= 128 && fe % 4 == 0 && fe >= 4 && fe <= 28) ? 1 : 0;
+    return (f % 4 == 0 && f >= 4 && fe % 4 == 0 && fe >= 4 && fe <= 28) ? 1 : 0;   // any width: 128-feature slices
 }
+
+constexpr int G_FSLICE = 128;   // features per launch: 4 PHI buffers x 128 columns = the 512 TMEM columns
 
 static int fp_of(int f) { return f <= 32 ? 32 : (f <= 64 ? 64 : 128); }
 
@@ -707,13 +711,7 @@ static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* 
     size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + (size_t)2 * G_NCW * 32 * p.fp + (size_t)8 * p.fp + 1024;
 #define LAUNCH_G(CPT)                                                                                          \
     do {                                                                                                       \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
-            cudaError_t e = cudaFuncSetAttribute(gather_tc_kernel<CPT, MODE>,                                  \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);     \
-            if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                    \
-            configured = true;                                                                                 \
-        }                                                                                                      \
+        if (int rc_ = ensure_dyn_smem((const void*)gather_tc_kernel<CPT, MODE>, 226 * 1024, what)) return rc_;    \
         gather_tc_kernel<CPT, MODE><<<sm_count(), G_THREADS, smem, st>>>(p);                                   \
     } while (0)
     switch (cpt) {
@@ -731,13 +729,7 @@ static int launch_dwe_tc(const GatherTcArgs& p, cudaStream_t st, const char* wha
     size_t smem = (size_t)4 * G_P_BYTES + (size_t)2 * G_NCW * 32 * p.fp + 1024;
 #define LAUNCH_D(CPT)                                                                                          \
     do {                                                                                                       \
-        static bool configured = false;                                                                        \
-        if (!configured) {                                                                                     \
-            cudaError_t e = cudaFuncSetAttribute(dwe_tc_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                 226 * 1024);                                                  \
-            if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));                                    \
-            configured = true;                                                                                 \
-        }                                                                                                      \
+        if (int rc_ = ensure_dyn_smem((const void*)dwe_tc_kernel<CPT>, 226 * 1024, what)) return rc_;             \
         dwe_tc_kernel<CPT><<<sm_count(), G_THREADS, smem, st>>>(p);                                            \
     } while (0)
     switch (cpt) {
@@ -757,10 +749,17 @@ extern "C" int dgnn_gather_tc_fwd(const float* x_in, const float* in_scale, cons
     DGNN_REQUIRE(x_in && nbr && ea && w_e && b_e && agg, "null pointer");
     GatherTcArgs p;
     memset(&p, 0, sizeof(p));
-    p.x = x_in; p.scale = in_scale; p.shift = in_shift; p.relu = relu_in;
-    p.nbr = nbr; p.ea = ea; p.w_e = w_e; p.b_e = b_e; p.fe = fe;
-    p.n_rows = n_tgt; p.f = f_in; p.fp = fp_of(f_in); p.out = agg;
-    return launch_gather_tc<0>(p, as_stream(stream), "dgnn_gather_tc_fwd");
+    p.relu = relu_in; p.nbr = nbr; p.ea = ea; p.fe = fe;
+    p.n_rows = n_tgt; p.ld = f_in; p.s_ld = f_in;
+    for (int f0 = 0; f0 < f_in; f0 += G_FSLICE) {
+        const int w = f_in - f0 < G_FSLICE ? f_in - f0 : G_FSLICE;
+        p.f = w; p.fp = fp_of(w);
+        p.x = x_in + f0; p.out = agg + f0;
+        p.scale = in_scale ? in_scale + f0 : nullptr; p.shift = in_shift ? in_shift + f0 : nullptr;
+        p.w_e = w_e + (size_t)f0 * fe; p.b_e = b_e + f0;
+        if (int rc = launch_gather_tc<0>(p, as_stream(stream), "dgnn_gather_tc_fwd")) return rc;
+    }
+    return 0;
 }
 
 extern "C" int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const int32_t* onbr, const float* ea_own,
@@ -773,16 +772,25 @@ extern "C" int dgnn_gather_tc_bwd(const float* d_agg, const float* d_self, const
     DGNN_REQUIRE(dwe_partials == nullptr || z_prev != nullptr, "dW_e needs the layer input (z_prev)");
     GatherTcArgs p;
     memset(&p, 0, sizeof(p));
-    p.x = d_agg; p.nbr = onbr; p.ea = ea_own; p.w_e = w_e; p.b_e = b_e; p.fe = fe;
-    p.n_rows = n_src; p.f = f_in; p.fp = fp_of(f_in); p.out = dy_prev;
-    p.addend = d_self; p.n_add_rows = n_tgt;
-    p.z_prev = z_prev; p.p_scale = p_scale; p.p_shift = p_shift; p.p_mean = p_mean; p.p_rstd = p_rstd;
-    p.p_relu = p_relu; p.s_partials = s_partials; p.dwe_partials = dwe_partials;
+    p.nbr = onbr; p.ea = ea_own; p.fe = fe;
+    p.n_rows = n_src; p.ld = f_in; p.s_ld = f_in;
+    p.n_add_rows = n_tgt; p.p_relu = p_relu;
     cudaStream_t st = as_stream(stream);
-    if (dy_prev != nullptr || s_partials != nullptr) {
-        int rc = launch_gather_tc<1>(p, st, "dgnn_gather_tc_bwd");
-        if (rc) return rc;
+    for (int f0 = 0; f0 < f_in; f0 += G_FSLICE) {
+        const int w = f_in - f0 < G_FSLICE ? f_in - f0 : G_FSLICE;
+        p.f = w; p.fp = fp_of(w);
+        p.x = d_agg + f0; p.out = dy_prev ? dy_prev + f0 : nullptr;
+        p.w_e = w_e + (size_t)f0 * fe; p.b_e = b_e + f0;
+        p.addend = d_self ? d_self + f0 : nullptr;
+        p.z_prev = z_prev ? z_prev + f0 : nullptr;
+        p.p_scale = p_scale ? p_scale + f0 : nullptr; p.p_shift = p_shift ? p_shift + f0 : nullptr;
+        p.p_mean = p_mean ? p_mean + f0 : nullptr; p.p_rstd = p_rstd ? p_rstd + f0 : nullptr;
+        p.s_partials = s_partials ? s_partials + f0 : nullptr;
+        p.dwe_partials = dwe_partials ? dwe_partials + (size_t)f0 * 32 : nullptr;
+        if (dy_prev != nullptr || s_partials != nullptr)
+            if (int rc = launch_gather_tc<1>(p, st, "dgnn_gather_tc_bwd")) return rc;
+        if (dwe_partials != nullptr)
+            if (int rc = launch_dwe_tc(p, st, "dgnn_gather_tc_bwd(dW_e)")) return rc;
     }
-    if (dwe_partials != nullptr) return launch_dwe_tc(p, st, "dgnn_gather_tc_bwd(dW_e)");
     return 0;
 }

@@ -41,11 +41,13 @@ __global__ void ell_from_adj_kernel(const int32_t* __restrict__ adj, long long n
 }
 
 __global__ void ell_fill_kernel(const long long* __restrict__ src, const long long* __restrict__ tgt, long long ne,
-                                long long n_rows, int32_t* __restrict__ nbr, int32_t* __restrict__ eid,
-                                int32_t* __restrict__ cnt, int32_t* err) {
+                                long long n_rows, long long n_other, int32_t* __restrict__ nbr,
+                                int32_t* __restrict__ eid, int32_t* __restrict__ cnt, int32_t* err) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
         long long t = tgt[e];
         if (t < 0 || t >= n_rows) { atomicMax(err, 4); continue; }
+        const long long sv = src[e];
+        if (sv < 0 || sv >= n_other) { atomicMax(err, 4); continue; }   // a malformed edge_index must not become a gather index
         int slot = atomicAdd(&cnt[t], 1);
         if (slot >= 4) { atomicMax(err, 3); continue; }
         nbr[t * 4 + slot] = (int32_t)src[e];
@@ -53,9 +55,10 @@ __global__ void ell_fill_kernel(const long long* __restrict__ src, const long lo
     }
 }
 
-// sort each row's <=4 entries by edge id so the layout is deterministic; pad with -1
+// sort each row's <=4 entries by edge id (by_source: by (source, edge id), the order of PyG's
+// SparseTensor(row=src, col=tgt).t() rows) so the layout is deterministic; pad with -1
 __global__ void ell_sort_kernel(long long n_rows, int32_t* __restrict__ nbr, int32_t* __restrict__ eid,
-                                int32_t* __restrict__ cnt) {
+                                int32_t* __restrict__ cnt, int by_source) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_rows; t += (long long)gridDim.x * blockDim.x) {
         int c = cnt[t];
         if (c > 4) { c = 4; cnt[t] = 4; }
@@ -68,7 +71,8 @@ __global__ void ell_sort_kernel(long long n_rows, int32_t* __restrict__ nbr, int
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3 - a; ++b)
-                if (ev[b] > ev[b + 1]) {
+                if (by_source ? (nv[b + 1] >= 0 && (nv[b] < 0 || nv[b] > nv[b + 1] || (nv[b] == nv[b + 1] && ev[b] > ev[b + 1])))
+                              : (ev[b] > ev[b + 1])) {
                     int t1 = ev[b]; ev[b] = ev[b + 1]; ev[b + 1] = t1;
                     int t2 = nv[b]; nv[b] = nv[b + 1]; nv[b + 1] = t2;
                 }
@@ -201,16 +205,17 @@ extern "C" int dgnn_ell_from_adjacency(const int32_t* adj, int64_t n, int32_t* n
     return check_launch("dgnn_ell_from_adjacency");
 }
 
-extern "C" int dgnn_ell_build(const int64_t* src, const int64_t* tgt, int64_t n_edges, int64_t n_rows, int32_t* nbr,
-                              int32_t* eid, int32_t* cnt, int32_t* err_flag, void* stream) {
+extern "C" int dgnn_ell_build(const int64_t* src, const int64_t* tgt, int64_t n_edges, int64_t n_rows, int64_t n_other,
+                              int by_source, int32_t* nbr, int32_t* eid, int32_t* cnt, int32_t* err_flag, void* stream) {
     DGNN_REQUIRE(nbr && eid && cnt && err_flag, "null pointer");
+    DGNN_REQUIRE(n_other < ((int64_t)1 << 31) && n_rows < ((int64_t)1 << 31), "more than 2^31 cells");
     cudaStream_t st = as_stream(stream);
     if (n_edges > 0) {
         ell_fill_kernel<<<ggrid(n_edges), 256, 0, st>>>((const long long*)src, (const long long*)tgt, n_edges, n_rows,
-                                                        nbr, eid, cnt, err_flag);
+                                                        n_other, nbr, eid, cnt, err_flag);
         if (check_launch("dgnn_ell_build")) return 1;
     }
-    if (n_rows > 0) ell_sort_kernel<<<ggrid(n_rows), 256, 0, st>>>(n_rows, nbr, eid, cnt);
+    if (n_rows > 0) ell_sort_kernel<<<ggrid(n_rows), 256, 0, st>>>(n_rows, nbr, eid, cnt, by_source);
     return check_launch("dgnn_ell_build");
 }
 

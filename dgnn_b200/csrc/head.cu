@@ -3,20 +3,40 @@
 // learning/runModel.py:109-211,282,290; processing/generate_mesh.py:75,94-105.)
 #include <math.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.cuh"
 
 namespace dgnn {
 
 thread_local char g_err[512] = {0};
 
-static int g_sms = 0;
+static int g_sms[64] = {0};
 int sm_count() {
-    if (g_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-        if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (g_sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        g_sms[dev] = n;
     }
-    return g_sms;
+    return g_sms[dev];
+}
+
+// (kernel, device) pairs whose dynamic shared-memory limit has been raised
+static std::mutex g_cfg_mu;
+static std::set<std::pair<const void*, int>> g_cfg;
+int ensure_dyn_smem(const void* kernel, int bytes, const char* what) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(what, "cudaGetDevice failed");
+    std::lock_guard<std::mutex> lk(g_cfg_mu);
+    if (g_cfg.count({kernel, dev})) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));
+    g_cfg.insert({kernel, dev});
+    return 0;
 }
 
 // ---- norm finalize ------------------------------------------------------------------------
@@ -281,6 +301,31 @@ __global__ void __launch_bounds__(256) edge_reg_kernel(const float* __restrict__
         s += (double)fabsf(pa - pb);
     }
     block_sum2(s, 0.0, partials + 2 * blockIdx.x);
+}
+
+// backward of the regulariser: d|pa - pb| = sign(pa - pb) (d pa - d pb), p = sigmoid(z0 - z1).  The per-cell sum of the
+// signs over its edges is an INTEGER, so it is accumulated with integer atomics (exact, order-independent) ...
+__global__ void __launch_bounds__(256) edge_reg_sign_kernel(const float* __restrict__ z, const long long* __restrict__ src,
+                                                            const long long* __restrict__ tgt, long long ne,
+                                                            int* __restrict__ cnt) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (long long)gridDim.x * blockDim.x) {
+        long long a = src[e], b = tgt[e];
+        float pa = 1.f / (1.f + expf(z[a * 2 + 1] - z[a * 2]));
+        float pb = 1.f / (1.f + expf(z[b * 2 + 1] - z[b * 2]));
+        int sg = (pa > pb) - (pa < pb);
+        if (sg != 0) { atomicAdd(&cnt[a], sg); atomicAdd(&cnt[b], -sg); }
+    }
+}
+// ... and turned into the logit gradient per cell: dz0 = gout * scale * p (1 - p) * cnt, dz1 = -dz0
+__global__ void __launch_bounds__(256) edge_reg_bwd_kernel(const float* __restrict__ z, const int* __restrict__ cnt,
+                                                           long long n, float scale, const float* __restrict__ gout,
+                                                           float* __restrict__ dz) {
+    const float g0 = gout[0] * scale;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        float p = 1.f / (1.f + expf(z[c * 2 + 1] - z[c * 2]));
+        float g = g0 * p * (1.f - p) * (float)cnt[c];
+        reinterpret_cast<float2*>(dz)[c] = make_float2(g, -g);
+    }
 }
 
 // ---- generic partial reductions ---------------------------------------------------------------
@@ -563,6 +608,23 @@ extern "C" int dgnn_edge_reg_fwd(const float* logits, const int64_t* src, const 
     edge_reg_kernel<<<dgnn_small_grid(), 256, 0, as_stream(stream)>>>(logits, (const long long*)src,
                                                                       (const long long*)tgt, n_edges, partials);
     return check_launch("dgnn_edge_reg_fwd");
+}
+
+extern "C" int dgnn_edge_reg_bwd(const float* logits, const int64_t* src, const int64_t* tgt, int64_t n_edges,
+                                 int64_t n_rows, float scale, const float* grad_out, int32_t* sign_count, float* dlogits,
+                                 void* stream) {
+    DGNN_REQUIRE(logits && grad_out && sign_count && dlogits, "null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (n_edges > 0) {
+        DGNN_REQUIRE(src && tgt, "null pointer");
+        edge_reg_sign_kernel<<<grid_for(n_edges, 256, sm_count() * 8), 256, 0, st>>>(logits, (const long long*)src,
+                                                                                    (const long long*)tgt, n_edges, sign_count);
+        if (check_launch("dgnn_edge_reg_bwd")) return 1;
+    }
+    if (n_rows > 0)
+        edge_reg_bwd_kernel<<<grid_for(n_rows, 256, sm_count() * 8), 256, 0, st>>>(logits, sign_count, n_rows, scale, grad_out,
+                                                                                  dlogits);
+    return check_launch("dgnn_edge_reg_bwd");
 }
 
 extern "C" int dgnn_reduce_partials(const double* partials, int n_partials, int len, float* out, void* stream) {

@@ -482,12 +482,7 @@ extern "C" int dgnn_dense_bwd(const float* dy, const float* z, const float* g, c
     p.d_agg = d_agg; p.d_self = d_self; p.db_partials = db_partials;
     size_t smem = ((size_t)TM * p.lda + 2 * TK * TN + ((f_out + 3) & ~3) + TM) * sizeof(float);
     DGNN_REQUIRE(smem <= 200 * 1024, "layer too wide for the generic FP32 path");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return fail("dgnn_dense_bwd", cudaGetErrorString(e));
-        configured = true;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)dense_bwd_kernel, 200 * 1024, "dgnn_dense_bwd")) return rc_;
     int grid = dgnn_layer_grid(f_in, f_out);
     dense_bwd_kernel<<<grid, NT, smem, as_stream(stream)>>>(p);
     return check_launch("dgnn_dense_bwd");
@@ -526,12 +521,7 @@ template <int FE>
 static int launch_gather_bwd(const GatherBwdArgs& p, cudaStream_t st) {
     size_t smem = (size_t)(p.f_in * (FE + 1) + 2 * p.f_in) * sizeof(double);
     if (smem > 200 * 1024) return fail("dgnn_gather_bwd", "f_in too wide for the shared reduction");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gather_bwd_kernel<FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return fail("dgnn_gather_bwd", cudaGetErrorString(e));
-        configured = true;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)gather_bwd_kernel<FE>, 200 * 1024, "dgnn_gather_bwd")) return rc_;
     gather_bwd_kernel<FE><<<dgnn_gather_bwd_grid(p.f_in), NT, smem, st>>>(p);
     return check_launch("dgnn_gather_bwd");
 }

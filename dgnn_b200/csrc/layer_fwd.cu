@@ -276,12 +276,7 @@ extern "C" int dgnn_layer_grid(int f_in, int f_out) {
 
 template <int FE>
 static int launch_layer_fwd(const LayerFwdArgs& p, size_t smem, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(layer_fwd_kernel<FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return fail("dgnn_layer_fwd", cudaGetErrorString(e));
-        configured = true;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)layer_fwd_kernel<FE>, 200 * 1024, "dgnn_layer_fwd")) return rc_;
     layer_fwd_kernel<FE><<<grid, NT, smem, st>>>(p);
     return check_launch("dgnn_layer_fwd");
 }

@@ -1,5 +1,6 @@
-// Tensor-core (tcgen05 + TMEM) version of the fused layer kernels for widths that fit one
-// UMMA tile: f_out (forward) / k_total (backward) <= 256.
+// Tensor-core (tcgen05 + TMEM) version of the fused layer kernels.  One launch covers an N slice of at most
+// 256 output columns (one UMMA tile, two TMEM accumulator buffers); wider layers (modelnet.yaml's 512 / 1024) are
+// run as several column slices by the launch wrappers, the contraction length K (streamed K-atoms) is unbounded.
 //
 //   forward :  z = [agg | h] . [W_j | W_i]^T       (dgnn_layer_fwd_tc, gather or dense mode)
 //   backward:  [d_agg | d_self] = dz . [W_j | W_i]  (dgnn_dense_bwd_tc)
@@ -57,12 +58,16 @@ struct TcArgs {
     const float* b_packed;  // [KA][2][NP][32] swizzled atoms (hi, lo)
     int ka;                 // K-atoms
     int ka_agg;             // atoms of the agg segment (gather mode), 0 otherwise
-    int np;                 // padded N (multiple of 32, <= 256)
+    int np;                 // padded N of this launch's column slice (multiple of 32, <= 256)
     int stages;
+    int n_off;              // backward: first column of the slice inside [d_agg | d_self]
+    int n_total;            // backward: real columns of [d_agg | d_self] (2 f_in or f_in)
+    int out_ld;             // forward: row stride of `out` (the layer's full f_out; `out`, bias, out_scale ... are pre-offset)
+    int stats_ld;           // forward: full f_out (stride between the sum and sum^2 blocks of `stats`, pre-offset)
     // sizes
     int64_t n_tgt;
     int f_in;   // forward: input width; backward: width of d_agg / d_self
-    int f_out;  // forward: output width (N); backward: K (width of dy)
+    int f_out;  // forward: output width of the slice (N); backward: K (width of dy)
     // forward epilogue
     const float* bias;
     const float* out_scale;
@@ -359,7 +364,7 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
     const int r = q * 32 + lane;
     const int64_t t = tile0 + r;
     const bool tv = t < p.n_tgt;
-    const int n_real = MODE == MODE_BWD ? (p.nbr ? 2 * p.f_in : p.f_in) : p.f_out;
+    const int n_real = MODE == MODE_BWD ? p.n_total - p.n_off : p.f_out;   // real columns from the slice start
     float icnt = 1.f;
     if (MODE == MODE_BWD && p.nbr != nullptr && tv) {   // nb = nbr[t], loaded by the caller a tile earlier
         int cnt = (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
@@ -382,7 +387,7 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                 v[i] += bi.x; v[i + 1] += bi.y; v[i + 2] += bi.z; v[i + 3] += bi.w;
             }
             if (tv) {
-                const bool al8 = (p.f_out & 7) == 0;
+                const bool al8 = (p.out_ld & 7) == 0;
                 float4 held = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -397,9 +402,9 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                     if (p.relu_out) {
                         o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
                     }
-                    if (!al8) *reinterpret_cast<float4*>(p.out + (size_t)t * p.f_out + n) = o;
+                    if (!al8) *reinterpret_cast<float4*>(p.out + (size_t)t * p.out_ld + n) = o;
                     else if ((i & 4) == 0) held = o;                      // pair two float4 into one 32-byte store
-                    else stg8(p.out + (size_t)t * p.f_out + n - 4, held, o);
+                    else stg8(p.out + (size_t)t * p.out_ld + n - 4, held, o);
                 }
             }
             if (want_stats) {
@@ -416,10 +421,11 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
             // columns [0, f_in) of the tile are d_agg (x 1/cnt), [f_in, 2 f_in) d_self.  A 32-column chunk lies entirely in one
             // of them at the 32-multiple widths; its row pointer is formed once (not re-read from the constant bank per store)
             const bool has_agg = p.nbr != nullptr;
-            const bool all_agg = has_agg && c0 + 32 <= p.f_in;
-            const bool all_self = !has_agg || c0 >= p.f_in;
+            const int ca = p.n_off + c0;                // column of the chunk inside [d_agg | d_self]
+            const bool all_agg = has_agg && ca + 32 <= p.f_in;
+            const bool all_self = !has_agg || ca >= p.f_in;
             if ((all_agg || all_self) && c0 + 32 <= n_real && (p.f_in & 7) == 0) {
-                float* dst = (all_agg ? p.d_agg : p.d_self) + (size_t)t * p.f_in + (all_agg ? c0 : (has_agg ? c0 - p.f_in : c0));
+                float* dst = (all_agg ? p.d_agg : p.d_self) + (size_t)t * p.f_in + (all_agg ? ca : (has_agg ? ca - p.f_in : ca));
                 const float s = all_agg ? icnt : 1.f;
 #pragma unroll
                 for (int i = 0; i < 32; i += 8)
@@ -430,10 +436,11 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
                 for (int i = 0; i < 32; i += 4) {
                     const int n = c0 + i;
                     if (n >= n_real) continue;
-                    const bool is_agg = has_agg && n < p.f_in;
+                    const int na = p.n_off + n;
+                    const bool is_agg = has_agg && na < p.f_in;
                     float s = is_agg ? icnt : 1.f;
                     float* dst = is_agg ? p.d_agg : p.d_self;
-                    int col = is_agg ? n : (has_agg ? n - p.f_in : n);
+                    int col = is_agg ? na : (has_agg ? na - p.f_in : na);
                     *reinterpret_cast<float4*>(dst + (size_t)t * p.f_in + col) =
                         make_float4(v[i] * s, v[i + 1] * s, v[i + 2] * s, v[i + 3] * s);
                 }
@@ -618,10 +625,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
     tc_fence_before_sync();
     __syncthreads();
     if (MODE != MODE_BWD && p.stats != nullptr) {
-        double* my = p.stats + (size_t)blockIdx.x * 2 * p.f_out;
+        double* my = p.stats + (size_t)blockIdx.x * 2 * p.stats_ld;
         for (int c = tid; c < p.f_out; c += TC_THREADS) {
             my[c] = red_st[c];
-            my[p.f_out + c] = red_st[256 + c];
+            my[p.stats_ld + c] = red_st[256 + c];
         }
     }
     if (MODE == MODE_BWD && p.db_partials != nullptr) {
@@ -632,6 +639,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
 }
 
 // ---- weight packing: w[n, k] (row stride ld) -> per K-atom swizzled hi / lo images ---------------
+// Rows are packed in slices of TC_NSLICE (= one launch's N): slice s holds [KA][2][np_s][32] with np_s = its padded rows.
+constexpr int TC_NSLICE = 256;
 __global__ void pack_b_kernel(const float* __restrict__ w, int n_rows, int ld, int seg_len, int n_segs, int seg_pad,
                               int np, float* __restrict__ packed) {
     const int ka = n_segs * seg_pad / ATOM_K;
@@ -646,10 +655,12 @@ __global__ void pack_b_kernel(const float* __restrict__ w, int n_rows, int ld, i
         if (n < n_rows && kk < seg_len) v = w[(size_t)n * ld + seg * seg_len + kk];
         float hi, lo;
         split_tf32(v, hi, lo);
-        size_t base = (size_t)a * 2 * np * ATOM_K;
-        uint32_t off = atom_off(n, k) / 4;
+        const int sl = n / TC_NSLICE, nl = n - sl * TC_NSLICE;
+        const int nps = np - sl * TC_NSLICE < TC_NSLICE ? np - sl * TC_NSLICE : TC_NSLICE;
+        size_t base = (size_t)sl * ka * 2 * TC_NSLICE * ATOM_K + (size_t)a * 2 * nps * ATOM_K;
+        uint32_t off = atom_off(nl, k) / 4;
         packed[base + off] = hi;
-        packed[base + (size_t)np * ATOM_K + off] = lo;
+        packed[base + (size_t)nps * ATOM_K + off] = lo;
     }
 }
 
@@ -690,23 +701,38 @@ static int tc_stage_config(int np, bool gather, int* stages, size_t* smem, int r
 
 template <int MODE, int FE>
 static int launch_tc(const TcArgs& p, size_t smem, cudaStream_t st, const char* what) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(layer_tc_kernel<MODE, FE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             210 * 1024);
-        if (e != cudaSuccess) return fail(what, cudaGetErrorString(e));
-        configured = true;
-    }
+    if (int rc_ = ensure_dyn_smem((const void*)layer_tc_kernel<MODE, FE>, 210 * 1024, what)) return rc_;
     layer_tc_kernel<MODE, FE><<<sm_count(), TC_THREADS, smem, st>>>(p);
     return check_launch(what);
 }
 
 extern "C" int dgnn_tc_grid(void) { return sm_count(); }
 
-// 1 if the tensor-core path supports these widths
+// 1 if the tensor-core path supports these widths (any multiple of 4: wide layers run as column slices)
 extern "C" int dgnn_tc_supported(int f_in, int f_out, int gather) {
     (void)gather;
-    return (f_in % 4 == 0 && f_out % 4 == 0 && ceil32(f_out) <= 256 && ceil32(2 * f_in) <= 256) ? 1 : 0;
+    return (f_in % 4 == 0 && f_out % 4 == 0 && f_in > 0 && f_out > 0) ? 1 : 0;
+}
+
+// forward launches, one per slice of <= TC_NSLICE output columns
+template <int MODE, int FE>
+static int fwd_slices(TcArgs p, int f_out, bool gather, int raw_ring, cudaStream_t st, const char* what) {
+    const float* bias = p.bias; const float* osc = p.out_scale; const float* osh = p.out_shift;
+    float* out = p.out; double* stats = p.stats; const float* bp = p.b_packed;
+    p.out_ld = f_out; p.stats_ld = f_out;
+    for (int n0 = 0; n0 < f_out; n0 += TC_NSLICE) {
+        const int w = f_out - n0 < TC_NSLICE ? f_out - n0 : TC_NSLICE;
+        p.f_out = w; p.np = ceil32(w);
+        p.bias = bias ? bias + n0 : nullptr;
+        p.out_scale = osc ? osc + n0 : nullptr; p.out_shift = osh ? osh + n0 : nullptr;
+        p.out = out + n0; p.stats = stats ? stats + n0 : nullptr;
+        p.b_packed = bp + (size_t)(n0 / TC_NSLICE) * p.ka * 2 * TC_NSLICE * ATOM_K;
+        if (n0 > 0) p.agg_save = nullptr;          // the aggregate does not depend on the slice
+        size_t smem;
+        if (tc_stage_config(p.np, gather, &p.stages, &smem, raw_ring)) return fail(what, "tile does not fit shared memory");
+        if (int rc = launch_tc<MODE, FE>(p, smem, st, what)) return rc;
+    }
+    return 0;
 }
 
 extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
@@ -715,7 +741,6 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
                                  const float* out_shift, int relu_out, int64_t n_tgt, int f_in, int f_out, float* out,
                                  float* agg_save, double* stats, void* stream) {
     DGNN_REQUIRE(f_in % 4 == 0 && f_out % 4 == 0, "widths must be multiples of 4");
-    DGNN_REQUIRE(ceil32(f_out) <= 256, "f_out too wide for one UMMA tile");
     DGNN_REQUIRE(x_in && b_packed && out, "null pointer");
     if (w_e == nullptr) fe = 0;
     DGNN_REQUIRE(fe % 4 == 0 && fe <= 32, "edge feature width must be a multiple of 4 and <= 32");
@@ -726,27 +751,24 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
     const int seg = ceil32(f_in) / ATOM_K;
     p.ka_agg = nbr ? seg : 0;
     p.ka = nbr ? 2 * seg : seg;
-    p.np = ceil32(f_out);
-    p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
+    p.n_tgt = n_tgt; p.f_in = f_in;
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.agg_save = agg_save; p.stats = stats;
-    size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, nbr != nullptr, &p.stages, &smem, nbr == nullptr ? RAW_DEPTH * A_ATOM_BYTES : 0) == 0,
-                 "tile does not fit shared memory");
     cudaStream_t st = as_stream(stream);
-    if (nbr == nullptr) return launch_tc<MODE_FWD_DENSE, 0>(p, smem, st, "dgnn_layer_fwd_tc");
+    const char* what = "dgnn_layer_fwd_tc";
+    if (nbr == nullptr) return fwd_slices<MODE_FWD_DENSE, 0>(p, f_out, false, RAW_DEPTH * A_ATOM_BYTES, st, what);
     switch (fe) {
-        case 0: return launch_tc<MODE_FWD_GATHER, 0>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 4: return launch_tc<MODE_FWD_GATHER, 4>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 8: return launch_tc<MODE_FWD_GATHER, 8>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 12: return launch_tc<MODE_FWD_GATHER, 12>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 16: return launch_tc<MODE_FWD_GATHER, 16>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 20: return launch_tc<MODE_FWD_GATHER, 20>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 24: return launch_tc<MODE_FWD_GATHER, 24>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 28: return launch_tc<MODE_FWD_GATHER, 28>(p, smem, st, "dgnn_layer_fwd_tc");
-        case 32: return launch_tc<MODE_FWD_GATHER, 32>(p, smem, st, "dgnn_layer_fwd_tc");
+        case 0: return fwd_slices<MODE_FWD_GATHER, 0>(p, f_out, true, 0, st, what);
+        case 4: return fwd_slices<MODE_FWD_GATHER, 4>(p, f_out, true, 0, st, what);
+        case 8: return fwd_slices<MODE_FWD_GATHER, 8>(p, f_out, true, 0, st, what);
+        case 12: return fwd_slices<MODE_FWD_GATHER, 12>(p, f_out, true, 0, st, what);
+        case 16: return fwd_slices<MODE_FWD_GATHER, 16>(p, f_out, true, 0, st, what);
+        case 20: return fwd_slices<MODE_FWD_GATHER, 20>(p, f_out, true, 0, st, what);
+        case 24: return fwd_slices<MODE_FWD_GATHER, 24>(p, f_out, true, 0, st, what);
+        case 28: return fwd_slices<MODE_FWD_GATHER, 28>(p, f_out, true, 0, st, what);
+        case 32: return fwd_slices<MODE_FWD_GATHER, 32>(p, f_out, true, 0, st, what);
     }
-    return fail("dgnn_layer_fwd_tc", "unsupported edge feature width");
+    return fail(what, "unsupported edge feature width");
 }
 
 // z = [agg | h(x_in)] . W^T with agg read from memory (agg may be NULL: plain dense layer)
@@ -755,7 +777,6 @@ extern "C" int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const floa
                                  const float* out_shift, int relu_out, int64_t n_tgt, int f_in, int f_out, float* out,
                                  double* stats, void* stream) {
     DGNN_REQUIRE(f_in % 4 == 0 && f_out % 4 == 0, "widths must be multiples of 4");
-    DGNN_REQUIRE(ceil32(f_out) <= 256, "f_out too wide for one UMMA tile");
     DGNN_REQUIRE(x_in && b_packed && out, "null pointer");
     TcArgs p;
     memset(&p, 0, sizeof(p));
@@ -764,13 +785,10 @@ extern "C" int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const floa
     const int seg = ceil32(f_in) / ATOM_K;
     p.ka_agg = agg ? seg : 0;
     p.ka = agg ? 2 * seg : seg;
-    p.np = ceil32(f_out);
-    p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
+    p.n_tgt = n_tgt; p.f_in = f_in;
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.stats = stats;
-    size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem, RAW_DEPTH * A_ATOM_BYTES) == 0, "tile does not fit shared memory");
-    return launch_tc<MODE_FWD_DENSE, 0>(p, smem, as_stream(stream), "dgnn_dense_fwd_tc");
+    return fwd_slices<MODE_FWD_DENSE, 0>(p, f_out, false, RAW_DEPTH * A_ATOM_BYTES, as_stream(stream), "dgnn_dense_fwd_tc");
 }
 
 extern "C" int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g, const float* a, const float* b,
@@ -779,18 +797,25 @@ extern "C" int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g
                                  void* stream) {
     DGNN_REQUIRE(f_in % 4 == 0 && f_out % 4 == 0, "widths must be multiples of 4");
     const int n_real = nbr ? 2 * f_in : f_in;
-    DGNN_REQUIRE(ceil32(n_real) <= 256, "2*f_in too wide for one UMMA tile");
-    DGNN_REQUIRE(f_out <= 256, "f_out too wide for the shared column sums");
+    DGNN_REQUIRE(f_out <= 256 || db_partials == nullptr, "f_out too wide for the shared column sums (take db from the dW kernel)");
     DGNN_REQUIRE(dy && b_packed && d_self && (!nbr || d_agg), "null pointer");
     TcArgs p;
     memset(&p, 0, sizeof(p));
     p.dy = dy; p.z = z; p.ng = g; p.na = a; p.nb = b; p.nmean = mean; p.nrstd = rstd;
-    p.b_packed = b_packed; p.nbr = nbr;
+    p.nbr = nbr;
     p.ka = ceil32(f_out) / ATOM_K; p.ka_agg = 0;
-    p.np = ceil32(n_real);
     p.n_tgt = n_tgt; p.f_in = f_in; p.f_out = f_out;
-    p.d_agg = d_agg; p.d_self = d_self; p.db_partials = db_partials;
-    size_t smem;
-    DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem) == 0, "tile does not fit shared memory");
-    return launch_tc<MODE_BWD, 0>(p, smem, as_stream(stream), "dgnn_dense_bwd_tc");
+    p.d_agg = d_agg; p.d_self = d_self;
+    p.n_total = n_real;
+    cudaStream_t st = as_stream(stream);
+    for (int n0 = 0; n0 < n_real; n0 += TC_NSLICE) {
+        const int w = n_real - n0 < TC_NSLICE ? n_real - n0 : TC_NSLICE;
+        p.np = ceil32(w); p.n_off = n0;
+        p.b_packed = b_packed + (size_t)(n0 / TC_NSLICE) * p.ka * 2 * TC_NSLICE * ATOM_K;
+        p.db_partials = n0 == 0 ? db_partials : nullptr;
+        size_t smem;
+        DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem) == 0, "tile does not fit shared memory");
+        if (int rc = launch_tc<MODE_BWD, 0>(p, smem, st, "dgnn_dense_bwd_tc")) return rc;
+    }
+    return 0;
 }

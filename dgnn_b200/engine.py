@@ -83,6 +83,7 @@ class NetSpec:
     dec3_w: Optional[torch.Tensor] = None
     dec3_b: Optional[torch.Tensor] = None
     out_dim: int = 2
+    cache: Optional[dict] = None                  # packed-weight cache owned by the module (see pack_conv)
 
 
 def _pad2(w: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
@@ -115,9 +116,21 @@ class PackedConv:
     b_bwd: Optional[torch.Tensor] = None   # tcgen05 operand of the backward ([W_j | W_i]^T)
 
 
-def pack_conv(c: ConvSpec, fe_p: int) -> PackedConv:
+def _wkey(*ts):
+    return tuple(None if t is None else (id(t), t._version) for t in ts)
+
+
+def pack_conv(c: ConvSpec, fe_p: int, cache: Optional[dict] = None, slot=None) -> PackedConv:
     """Concatenate / transpose / zero-pad one layer's weights into the kernel layouts.
-    (Tiny per-step glue on the weights; activations never pass through torch ops.)"""
+    (Tiny glue on the weights; activations never pass through torch ops.)  With ``cache`` (a dict owned by the
+    module) the packed operands are reused until a weight tensor is replaced or modified in place (tensor identity +
+    autograd version counter; ``runModel.Adam`` bumps the counter after its kernel has written the parameters)."""
+    key = None
+    if cache is not None:
+        key = ("conv", fe_p, use_tensor_cores()) + _wkey(c.w_i, c.w_j, c.b_j, c.w_e, c.b_e)
+        hit = cache.get(slot)
+        if hit is not None and hit[0] == key:
+            return hit[1]
     fi = pad4(c.f_in)
     if c.f_out % 4:
         raise NotImplementedError("hidden widths must be multiples of 4 (got %d)" % c.f_out)
@@ -133,6 +146,8 @@ def pack_conv(c: ConvSpec, fe_p: int) -> PackedConv:
                     w_e, b_e)
     if use_tensor_cores() and lib().dgnn_tc_supported(fi, c.f_out, 1):
         pk.b_fwd = pack_b(w_cat, c.f_out, fi, 2)
+    if cache is not None:
+        cache[slot] = (key, pk)
     return pk
 
 
@@ -301,7 +316,7 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
     batch_stats = training or any(c.norm is not None and c.norm.mode == 1 for c in spec.convs)
     for l, c in enumerate(spec.convs):
         g = graphs[l]
-        pk = pack_conv(c, fe_p)
+        pk = pack_conv(c, fe_p, spec.cache, l)
         if h.shape[1] != pk.f_in:
             raise ValueError("layer %d expects %d input features, got %d" % (l, pk.f_in, h.shape[1]))
         if c.norm is None:
@@ -365,7 +380,14 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
     dn = spec.dec_norm
     bd = None
     if use_tensor_cores() and lib().dgnn_tc_supported(f_last, f_d, 0):
-        bd = pack_b(spec.dec0_w.detach(), f_d, f_last, 1)
+        dkey = ("dec",) + _wkey(spec.dec0_w)
+        hit = spec.cache.get("dec") if spec.cache is not None else None
+        if hit is not None and hit[0] == dkey:
+            bd = hit[1]
+        else:
+            bd = pack_b(spec.dec0_w.detach(), f_d, f_last, 1)
+            if spec.cache is not None:
+                spec.cache["dec"] = (dkey, bd)
     if batch_stats:
         z_d, _, stats = _layer_fwd(h, in_aff, relu_in, None, wt, b0, None, None, 0, None, False, n_out, f_last, f_d,
                                    False, True, b_packed=bd)
@@ -422,8 +444,10 @@ def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, i
     d_self = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev)
     d_agg = torch.empty((agg_rows or n_tgt, f_in), dtype=torch.float32, device=dev) if g is not None else None
     tc_dw = use_tensor_cores() and lib().dgnn_dw_tc_supported(f_out, k_total)
-    tc_dense = use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 1 if g is not None else 0) and f_out <= 256
+    tc_dense = use_tensor_cores() and lib().dgnn_tc_supported(f_in, f_out, 1 if g is not None else 0)
     db_from_dw = tc_dw and tc_dense          # the dW kernel forms dz anyway and sums its columns (db) on the way
+    if tc_dense and not db_from_dw and f_out > 256:
+        tc_dense = False                     # the dense backward's shared column sums hold 256 channels
     if tc_dense:
         # operand B of the backward: [W_j | W_i]^T, i.e. rows = columns of d[agg|self], K = f_out
         b_bwd = pack_b(w_cat.t().contiguous(), k_total, f_out, 1)

@@ -198,17 +198,17 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
     fe = 0 if edge_attr is None else pad4(edge_attr.shape[1])
     err = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def one_side(src, tgt, rows):
+    def one_side(src, tgt, rows, others):
         nb = torch.empty((rows, 4), dtype=torch.int32, device=dev)
         eid = torch.empty((rows, 4), dtype=torch.int32, device=dev)
         cnt = torch.zeros(rows, dtype=torch.int32, device=dev)
-        call("dgnn_ell_build", ptr(src), ptr(tgt), E, rows, ptr(nb), ptr(eid), ptr(cnt), ptr(err), st)
+        call("dgnn_ell_build", ptr(src), ptr(tgt), E, rows, others, 0, ptr(nb), ptr(eid), ptr(cnt), ptr(err), st)
         return nb, eid
 
-    nbr, eid_in = one_side(ei[0], ei[1], n_tgt)
+    nbr, eid_in = one_side(ei[0], ei[1], n_tgt, n_src)
     onbr = eid_out = None
     if need_backward:
-        onbr, eid_out = one_side(ei[1], ei[0], n_src)
+        onbr, eid_out = one_side(ei[1], ei[0], n_src, n_tgt)
     code = int(err.item())
     if code == 3:
         raise _lib.DgnnError("a cell has more than 4 facet neighbours: not a Delaunay cell graph "

@@ -277,7 +277,7 @@ class PartitionedInference:
 
     def prepare(self, data_all):
         g, maps, x0, ids, n = _local_plan(self.model, data_all, self.world, self.rank, need_backward=False)
-        self._plan = (g, maps, x0, ids)
+        self._plan = (g, maps, x0, ids, HaloComm(maps, n, self.group))   # n: cells of ALL ranks (graph LayerNorm statistics)
         return self._plan
 
     @torch.no_grad()
@@ -285,9 +285,8 @@ class PartitionedInference:
         from . import engine
         if self._plan is None:
             self.prepare(data_all)
-        g, maps, x0, ids = self._plan
+        g, maps, x0, ids, comm = self._plan
         net = self.model
         with torch.cuda.device(x0.device):
-            out, _ = engine.forward(net._spec(), [g] * net.num_layers, x0, training=False, save=False,
-                                    comm=HaloComm(maps, 0, self.group))
+            out, _ = engine.forward(net._spec(), [g] * net.num_layers, x0, training=False, save=False, comm=comm)
         return ids, out

@@ -122,15 +122,49 @@ def cell_loss(logits, batch_gt, batch_x, clf, return_sums=False, group=None, dis
     return (loss, sums) if return_sums else loss
 
 
+class _EdgeReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, ei, edge_weight):
+        dev = logits.device
+        z = logits.contiguous()
+        grid = lib().dgnn_small_grid()
+        part = torch.empty((grid, 2), dtype=torch.float64, device=dev)
+        call("dgnn_edge_reg_fwd", ptr(z), ptr(ei[0]), ptr(ei[1]), ei.shape[1], ptr(part), _stream())
+        ctx.save_for_backward(z, ei)
+        ctx.scale = float(edge_weight) / max(int(ei.shape[1]), 1)
+        return (part[:, 0].sum() * ctx.scale).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, ei = ctx.saved_tensors
+        cnt = torch.zeros(z.shape[0], dtype=torch.int32, device=z.device)
+        d = torch.empty_like(z)
+        gout = gout.contiguous().to(torch.float32)
+        call("dgnn_edge_reg_bwd", ptr(z), ptr(ei[0]), ptr(ei[1]), ei.shape[1], z.shape[0], ctx.scale, ptr(gout), ptr(cnt),
+             ptr(d), _stream())
+        return d, None, None
+
+
 def edge_regularization(logits, edge_index, edge_weight):
-    """``Trainer.calcRegularization`` forward value (``runModel.py:109-160``); disabled in every
-    shipped config (``edge_epoch: null``), so only the value (no gradient) is provided."""
-    dev = logits.device
-    ei = edge_index.to(dev, dtype=torch.int64).contiguous()
-    grid = lib().dgnn_small_grid()
-    part = torch.empty((grid, 2), dtype=torch.float64, device=dev)
-    call("dgnn_edge_reg_fwd", ptr(logits.contiguous()), ptr(ei[0]), ptr(ei[1]), ei.shape[1], ptr(part), _stream())
-    return (part[:, 0].sum() * (edge_weight / ei.shape[1])).to(torch.float32)
+    """``Trainer.calcRegularization`` (``runModel.py:109-160``): ``mean_e |p0[src_e] - p0[tgt_e]| * edge_weight`` with
+    ``p = softmax(logits)``; differentiable (the reference adds it to the training loss once ``regularization.edge_epoch``
+    is reached, ``runModel.py:250-255``).  ``logits`` float32[n, 2] on the device."""
+    if logits.dim() != 2 or logits.shape[1] != 2:
+        raise ValueError("the regulariser needs two logits per cell (loss 'kl')")
+    ei = edge_index.to(logits.device, dtype=torch.int64).contiguous()
+    return _EdgeReg.apply(logits, ei, edge_weight)
+
+
+def calc_regularization(logits_cell, data, clf, num_layers):
+    """The reference's call (``runModel.py:109-125``): on a sampled batch the innermost adjacency
+    ``data.batch_adjs[num_layers]`` (local ids; needs ``graph.additional_num_hops == 1``) over the first ``size[0]``
+    logits, otherwise ``data.edge_index`` over all of them."""
+    adjs = getattr(data, "batch_adjs", None)
+    if adjs:
+        adj = adjs[num_layers]
+        ei, size = adj[0], adj[2]
+        return edge_regularization(logits_cell[:size[0]], ei, clf.regularization.edge_weight)
+    return edge_regularization(logits_cell, data.edge_index, clf.regularization.edge_weight)
 
 
 def labels(logits):
@@ -244,3 +278,6 @@ class Adam(torch.optim.Optimizer):
             call("dgnn_adam_multi", ptr(table), len(rows), max_n, float(group["lr"]), float(b1), float(b2),
                  float(group["eps"]), self._step, _stream())
             group["_table"] = table
+            for p in group["params"]:           # the kernel wrote the parameters behind autograd's back: record the
+                if p.grad is not None:          # in-place update so that version-keyed caches (packed weights) notice
+                    torch.autograd.graph.increment_version(p)

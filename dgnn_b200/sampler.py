@@ -10,7 +10,7 @@ the in-edge ELL-4 table (``dgnn_sampler_*``), bit-exact against the oracle's res
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import NamedTuple, Optional, Tuple
 
 import torch
 
@@ -21,25 +21,54 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class Adj(NamedTuple):
+    """One hop of a sampled closure, PyG's ``Adj`` (``edge_index`` in local ids, ``e_id`` into the full edge list or
+    ``None`` without ``return_e_id``, ``size = (n_src, n_tgt)``).  The reference reads ``adj.size[1]``
+    (``runModel.py:274``) and ``adj.edge_index`` (``runModel.py:119,239``) as well as unpacking it as a tuple
+    (``Static:215``)."""
+    edge_index: torch.Tensor
+    e_id: Optional[torch.Tensor]
+    size: Tuple[int, int]
+
+    def to(self, *args, **kwargs):
+        return Adj(self.edge_index.to(*args, **kwargs),
+                   self.e_id.to(*args, **kwargs) if self.e_id is not None else None, self.size)
+
+
 class NeighborSampler:
-    """Drop-in for the way the reference uses PyG's ``NeighborSampler`` (all neighbours, ``return_e_id=True``).
+    """Drop-in for the way the reference uses PyG's ``NeighborSampler`` (``run.py:72-74,222-223``): all neighbours
+    (``sizes = [-1] * hops``), keyword arguments ``node_idx`` (index tensor or BOOL mask, as ``reduceDataset`` returns),
+    ``batch_size``, ``shuffle``, ``drop_last``, ``return_e_id``, ``sampler=None``.
 
-    ``edge_index`` int64[2, E] (``[0]`` = source, ``[1]`` = target; at most 4 in-edges per node, as in a cell graph);
-    ``sizes`` must be all -1; ``node_idx`` = the seed nodes (default: all); ``shuffle`` draws a new seed permutation
-    every epoch with ``torch.randperm`` on the device.  Iterating yields ``(batch_size, n_id, adjs)`` with all tensors on
-    ``device``."""
+    ``edge_index`` int64[2, E] (``[0]`` = source, ``[1]`` = target; at most 4 in-edges per node, as in a cell graph).
+    The in-edges of a node are visited in ascending (source id, edge id) order - the row order of PyG's
+    ``SparseTensor(row, col, value).t()`` that ``sample_adj`` walks.  ``shuffle`` draws a new seed permutation every epoch
+    with ``torch.randperm`` on the device.  Iterating yields ``(batch_size, n_id, adjs)`` with all tensors on ``device``;
+    ``adjs`` is a list of ``Adj`` (outermost hop first), or a single ``Adj`` for one hop."""
 
-    def __init__(self, edge_index: torch.Tensor, sizes, batch_size: int, node_idx: Optional[torch.Tensor] = None,
-                 num_nodes: Optional[int] = None, shuffle: bool = False, device="cuda:0"):
+    def __init__(self, edge_index: torch.Tensor, sizes, node_idx: Optional[torch.Tensor] = None,
+                 num_nodes: Optional[int] = None, return_e_id=True, transform=None, batch_size: int = 1,
+                 shuffle: bool = False, drop_last: bool = False, sampler=None, device="cuda:0", **loader_kwargs):
+        if isinstance(sizes, int):
+            sizes = [sizes]
         if any(s != -1 for s in sizes):
             raise NotImplementedError("only full neighbourhoods (sizes = [-1] * hops), as in every reference config")
+        if sampler is not None or transform is not None:
+            raise NotImplementedError("custom sampler / transform objects are not supported (run.py passes sampler=None)")
+        unknown = set(loader_kwargs) - {"num_workers", "pin_memory", "persistent_workers", "prefetch_factor"}
+        if unknown:
+            raise TypeError("unexpected NeighborSampler arguments: %s" % sorted(unknown))
         self.device = torch.device(device)
         check_device(self.device.index or 0)
         self.sizes = list(sizes)
         self.batch_size = int(batch_size)
-        self.shuffle = shuffle
+        self.shuffle = bool(shuffle)
+        self.drop_last = bool(drop_last)
+        self.return_e_id = bool(return_e_id)
         ei = edge_index.to(self.device, dtype=torch.int64).contiguous()
-        n = int(ei.max().item()) + 1 if num_nodes is None else int(num_nodes)
+        if num_nodes is None and node_idx is not None and node_idx.dtype == torch.bool:
+            num_nodes = node_idx.numel()                       # PyG: a mask fixes the node count
+        n = (int(ei.max().item()) + 1 if ei.numel() else 0) if num_nodes is None else int(num_nodes)
         self.num_nodes = n
         e = ei.shape[1]
         with torch.cuda.device(self.device):
@@ -47,20 +76,34 @@ class NeighborSampler:
             self.in_eid = torch.empty((n, 4), dtype=torch.int32, device=self.device)
             cnt = torch.zeros(n, dtype=torch.int32, device=self.device)
             err = torch.zeros(1, dtype=torch.int32, device=self.device)
-            call("dgnn_ell_build", ptr(ei[0]), ptr(ei[1]), e, n, ptr(self.in_src), ptr(self.in_eid), ptr(cnt), ptr(err),
-                 _stream())
+            call("dgnn_ell_build", ptr(ei[0]), ptr(ei[1]), e, n, n, 1, ptr(self.in_src), ptr(self.in_eid), ptr(cnt),
+                 ptr(err), _stream())
             code = int(err.item())
         if code == 3:
             raise DgnnError("a node has more than 4 in-edges: not a Delaunay cell graph")
         if code:
             raise DgnnError("dgnn_ell_build: edge endpoint out of range (code %d)" % code)
-        self.node_idx = (torch.arange(n, device=self.device) if node_idx is None
-                         else node_idx.to(self.device, dtype=torch.int64).contiguous())
+        if node_idx is None:
+            idx = torch.arange(n, device=self.device)
+        elif node_idx.dtype == torch.bool:                     # run.py:51,72: reduceDataset's train_mask
+            if node_idx.numel() != n:
+                raise ValueError("node_idx mask has %d entries for %d nodes" % (node_idx.numel(), n))
+            idx = node_idx.to(self.device).nonzero().view(-1)
+        else:
+            idx = node_idx.to(self.device, dtype=torch.int64).contiguous().view(-1)
+        if idx.numel():
+            if int(idx.min().item()) < 0 or int(idx.max().item()) >= n:
+                raise ValueError("node_idx out of range [0, %d)" % n)
+            if torch.unique(idx).numel() != idx.numel():
+                raise ValueError("node_idx holds duplicate seeds")
+        self.node_idx = idx
         # scratch shared by all batches: local id of a node in the current n_id (-1 = absent), first-appearance position
         self._loc = torch.full((n,), -1, dtype=torch.int32, device=self.device)
         self._first = torch.full((n,), 0x7fffffff, dtype=torch.int32, device=self.device)
 
     def __len__(self):
+        if self.drop_last:
+            return self.node_idx.numel() // self.batch_size
         return (self.node_idx.numel() + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
@@ -68,7 +111,10 @@ class NeighborSampler:
         if self.shuffle:
             idx = idx[torch.randperm(idx.numel(), device=self.device)]
         for s in range(0, idx.numel(), self.batch_size):
-            yield self.sample(idx[s:s + self.batch_size])
+            batch = idx[s:s + self.batch_size]
+            if self.drop_last and batch.numel() < self.batch_size:
+                break
+            yield self.sample(batch)
 
     def sample(self, batch: torch.Tensor):
         dev = self.device
@@ -97,7 +143,7 @@ class NeighborSampler:
                 call("dgnn_sampler_assign", ptr(src_g), n_e, ptr(flag), ptr(rank), n_tgt, ptr(self._loc), ptr(self._first),
                      ptr(new_ids), ptr(edge_local[0]), st)
                 n_id = torch.cat([n_id, new_ids]) if n_new else n_id
-                adjs.append((edge_local, e_id, (n_id.numel(), n_tgt)))
+                adjs.append(Adj(edge_local, e_id if self.return_e_id else None, (n_id.numel(), n_tgt)))
             call("dgnn_sampler_set_loc", ptr(n_id), n_id.numel(), -1, ptr(self._loc), st)   # scratch back to "absent"
         adjs = adjs[0] if len(adjs) == 1 else adjs[::-1]
         return batch.numel(), n_id, adjs

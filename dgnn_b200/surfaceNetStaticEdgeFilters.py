@@ -143,6 +143,7 @@ class SurfaceNet(nn.Module):
             self.decoder.add_module("3", nn.Linear(int(last / 2), self.output_dim))
         #: cache graph layouts on the data object between calls (set False to rebuild every call)
         self.cache_graphs = True
+        self._pack_cache = {}     # packed kernel operands of the weights, valid until a weight changes (engine.pack_conv)
 
     # ------------------------------------------------------------------ parameter views
     def _spec(self) -> NetSpec:
@@ -160,7 +161,7 @@ class SurfaceNet(nn.Module):
                                   c.lin_j.bias, le.weight if le is not None else None,
                                   le.bias if le is not None else None, norm))
         dec = self.clf.model.decoder or 0
-        spec = NetSpec(convs, dec, out_dim=self.output_dim)
+        spec = NetSpec(convs, dec, out_dim=self.output_dim, cache=self._pack_cache)
         if dec == 1:
             spec.dec0_w, spec.dec0_b = self.decoder[0].weight, self.decoder[0].bias
         elif dec == 2:
@@ -212,7 +213,11 @@ class SurfaceNet(nn.Module):
         out, _ = engine.forward(self._spec(), graphs, x0, training=self.training, save=False, comm=comm)
         return out
 
-    def _cached(self, holder, key, build):
+    def _cached(self, holder, kind, tensors, build):
+        """Graph layout cached on the data object.  The entry is valid only for the very same tensor OBJECTS, unmodified
+        since the build (identity + ``_version`` counter); the entry keeps references to them, so an address can not be
+        reused by another tensor while the entry lives."""
+        key = (kind,) + tuple(None if t is None else (id(t), t._version, t.data_ptr(), tuple(t.shape)) for t in tensors)
         if self.cache_graphs:
             c = getattr(holder, "_dgnn_plan", None)
             if c is not None and c[0] == key:
@@ -220,7 +225,7 @@ class SurfaceNet(nn.Module):
         plan = build()
         if self.cache_graphs:
             try:
-                holder._dgnn_plan = (key, plan)
+                holder._dgnn_plan = (key, plan, list(tensors))
             except Exception:
                 pass
         return plan
@@ -237,7 +242,7 @@ class SurfaceNet(nn.Module):
             ea_all = data.all.edge_attr if self.clf.model.edge_convs else None
             full = all(a[2][0] == a[2][1] == n_id.numel() for a in adjs) and \
                 all(a[0].data_ptr() == adjs[0][0].data_ptr() for a in adjs) and self.clf.model.edge_convs != 2
-            key = ("train", n_id.data_ptr(), tuple(a[0].data_ptr() for a in adjs), n_id.numel())
+            keyed = [n_id, ea_all, getattr(data.all, "pos", None)] + [a[0] for a in adjs] + [a[1] for a in adjs]
 
             def build():
                 if full:
@@ -249,7 +254,7 @@ class SurfaceNet(nn.Module):
                     return [g] * self.num_layers
                 return [build_from_edges(ei, e_id, ea_all, size[0], size[1], dev) for (ei, e_id, size) in adjs]
 
-            graphs = self._cached(data, key, build)
+            graphs = self._cached(data, "train", keyed, build)
             xa = data.all.x
             cols = slice(1, None) if self.clf.regularization.cell_type else slice(None)
             if n_id.numel() * 2 >= xa.shape[0]:   # most rows used: upload once, select on the device
@@ -267,7 +272,8 @@ class SurfaceNet(nn.Module):
             cols = slice(1, None) if self.clf.regularization.cell_type else slice(None)
             x = data_all.x[:, cols].to(dev, dtype=torch.float32, non_blocking=True)
             n = x.shape[0]
-            key = ("infer", data_all.edge_index.data_ptr(), n)
+            keyed = [data_all.edge_index, data_all.edge_attr if self.clf.model.edge_convs else None,
+                     getattr(data_all, "pos", None)]
 
             def build():
                 ea = None
@@ -279,7 +285,7 @@ class SurfaceNet(nn.Module):
                 return build_full_graph(data_all.edge_index.to(torch.long), ea, n, dev, pos=pos, order="auto",
                                         need_backward=False)
 
-            g = self._cached(data_all, key, build)
+            g = self._cached(data_all, "infer", keyed, build)
             x0 = g.permute_rows(pad_cols(x, pad4(x.shape[1])))
             with torch.no_grad():
                 out = self._run([g] * self.num_layers, x0)
@@ -287,10 +293,19 @@ class SurfaceNet(nn.Module):
 
     def inference_layer_batch(self, data_all, batch_loader):
         """Reference: layer-by-layer over 1-hop batches with host staging (Static:279-320).
-        The result is the whole-graph forward; it is computed as such on the device."""
+        The result is the whole-graph forward; it is computed as such on the device.  (Not so for ``normalization: l``:
+        the reference's graph LayerNorm then normalises every batch by itself, Static:288-296 - no shipped config.)"""
+        self._no_batched_layernorm()
         return self.inference_layer(data_all)
 
     def inference_batch_layer(self, data_all, batch_loader):
         """Reference: per seed batch, recompute the L-hop closure (Static:232-275).  Every
         seed's logits equal the whole-graph forward's; computed once on the device."""
+        self._no_batched_layernorm()
         return self.inference_layer(data_all)
+
+    def _no_batched_layernorm(self):
+        if self.norm_type == 'l':
+            raise NotImplementedError("batched inference schedules with normalization 'l': PyG's graph LayerNorm takes its "
+                                      "statistics over each batch, which the whole-graph forward does not reproduce; use "
+                                      "inference_layer (batch_size 0)")

@@ -19,7 +19,7 @@
  *   learning/surfaceNetStaticEdgeFilters.py:180-187 decoder                    -> dgnn_layer_fwd(no gather) + dgnn_rowdot_*
  *   learning/surfaceNetUpdatedEdgeFilters.py:147-176 SAGEConv (updated filters) -> dgnn_layer_fwd with chained edge state
  *   learning/runModel.py:163-211                    calcLossAndOA (kl)         -> dgnn_kl_loss_fwd / _bwd
- *   learning/runModel.py:109-160                    calcRegularization         -> dgnn_edge_reg_fwd
+ *   learning/runModel.py:109-160                    calcRegularization         -> dgnn_edge_reg_fwd / _bwd
  *   learning/runModel.py:290,282                    Adam step                  -> dgnn_adam_step
  *   processing/data.py:434-439                      adjacency -> edge_index    -> dgnn_ell_from_adjacency / dgnn_ell_build
  *   processing/generate_mesh.py:75,94-105           labels, interface facets   -> dgnn_argmax_labels / dgnn_interface_facets
@@ -50,11 +50,14 @@ int dgnn_sm_count(void);
 int dgnn_ell_from_adjacency(const int32_t* adj, int64_t n, int32_t* nbr, uint8_t* rslot,
                             int32_t* err_flag, void* stream);
 /* generic: edge list (src[e] -> tgt[e], int64 as in edge_index) -> per-target rows of <=4
- * in-edges in ascending edge id.  nbr int32[n_rows,4] (source ids, -1 pad), eid
- * int32[n_rows,4] (edge id e, -1 pad), cnt int32[n_rows] (caller-zeroed).  *err_flag=3 if
- * a row has more than 4 in-edges. */
+ * in-edges in ascending edge id (by_source = 0) or ascending (source id, edge id) (by_source = 1:
+ * the row order of PyG's SparseTensor(row=src, col=tgt).t(), which NeighborSampler walks).
+ * nbr int32[n_rows,4] (source ids, -1 pad), eid int32[n_rows,4] (edge id e, -1 pad), cnt
+ * int32[n_rows] (caller-zeroed).  *err_flag = 3 if a row has more than 4 in-edges, 4 if a
+ * target is outside [0, n_rows) or a source outside [0, n_other). */
 int dgnn_ell_build(const int64_t* src, const int64_t* tgt, int64_t n_edges, int64_t n_rows,
-                   int32_t* nbr, int32_t* eid, int32_t* cnt, int32_t* err_flag, void* stream);
+                   int64_t n_other, int by_source, int32_t* nbr, int32_t* eid, int32_t* cnt,
+                   int32_t* err_flag, void* stream);
 /* 3*bits-bit Morton code of pos float32[n,3] quantised over [lo,hi] (host float[3]) */
 int dgnn_morton_codes(const float* pos, int64_t n, const float* lo_host, const float* hi_host,
                       int bits, uint64_t* codes, void* stream);
@@ -191,10 +194,6 @@ int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, const float*
                    int64_t n_tgt, int f_in, int f_out, int k_total, float* partials, double* db_partials,
                    void* stream);
 
-/* development probe (tools/probe_umma.py): one tcgen05.mma on caller-provided smem images */
-int dgnn_debug_umma(const uint8_t* a_img, int a_bytes, const uint8_t* b_img, int b_bytes, uint64_t a_desc,
-                    uint64_t b_desc, uint32_t idesc, int n, float* out, void* stream);
-
 /* Updated-edge-filter variant (learning/surfaceNetUpdatedEdgeFilters.py:157-176): aggregation with a
  * materialised edge state phi float32[n_tgt,4,f]:  agg[t] = mean_k h(x_in[nbr[t,k]]) (*) phi[t,k,:] */
 int dgnn_gather_phi_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
@@ -262,6 +261,13 @@ int dgnn_point_loss_bwd(const float* logits, const float* y, int y_stride, const
 /* runModel.py:109-160: partial sums of |p0[src]-p0[tgt]| over an edge list (int64) */
 int dgnn_edge_reg_fwd(const float* logits, const int64_t* src, const int64_t* tgt, int64_t n_edges,
                       double* partials, void* stream);
+/* its gradient (reg_loss is added to the training loss from regularization.edge_epoch on,
+ * runModel.py:250-255): dlogits[c] = grad_out[0] * scale * p(1-p) * (sum of sign(p_src - p_tgt) over the
+ * edges of c) * (+1, -1).  sign_count int32[n_rows], caller-zeroed workspace (integer atomics: exact and
+ * order-independent); scale = edge_weight / n_edges; grad_out is a device scalar. */
+int dgnn_edge_reg_bwd(const float* logits, const int64_t* src, const int64_t* tgt, int64_t n_edges,
+                      int64_t n_rows, float scale, const float* grad_out, int32_t* sign_count,
+                      float* dlogits, void* stream);
 
 /* ---- backward ---------------------------------------------------------------------------
  * Normalisation backward is carried by per-channel coefficient vectors

@@ -243,25 +243,36 @@ class NeighborSampler:
     Appendix A; ``run.py:72-74,222-223``).  Yields ``(batch_size, n_id, adjs)`` with
     ``adjs`` outermost hop first; a single hop yields one tuple, not a list."""
 
-    def __init__(self, edge_index, sizes, batch_size, node_idx=None, num_nodes=None):
+    def __init__(self, edge_index, sizes, batch_size, node_idx=None, num_nodes=None, drop_last=False):
         self.edge_index = edge_index
         self.sizes = list(sizes)
         self.batch_size = batch_size
+        self.drop_last = drop_last
+        if node_idx is not None and node_idx.dtype == torch.bool:    # PyG: a mask selects its nonzero positions
+            num_nodes = node_idx.numel() if num_nodes is None else num_nodes
+            node_idx = node_idx.nonzero(as_tuple=False).view(-1)
         N = int(edge_index.max()) + 1 if num_nodes is None else num_nodes
         self.N = N
         self.node_idx = torch.arange(N) if node_idx is None else node_idx
-        # CSR by target (adj_t rows = targets), edges in ascending edge id within a row
+        # CSR by target: adj_t = SparseTensor(row=src, col=tgt, value=arange(E)).t() has rows = targets whose entries are
+        # sorted by source id (torch_sparse sorts by row * n + col, then transposes with a stable sort by col)
         tgt = edge_index[1]
-        order = torch.argsort(tgt, stable=True)
+        by_src = torch.argsort(edge_index[0], stable=True)
+        order = by_src[torch.argsort(tgt[by_src], stable=True)]
         self.order = order
         cnt = torch.bincount(tgt, minlength=N)
         self.rowptr = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(cnt, 0)])
 
     def __iter__(self):
         for s in range(0, self.node_idx.numel(), self.batch_size):
-            yield self.sample(self.node_idx[s:s + self.batch_size])
+            b = self.node_idx[s:s + self.batch_size]
+            if self.drop_last and b.numel() < self.batch_size:
+                break
+            yield self.sample(b)
 
     def __len__(self):
+        if self.drop_last:
+            return self.node_idx.numel() // self.batch_size
         return (self.node_idx.numel() + self.batch_size - 1) // self.batch_size
 
     def sample(self, batch):

@@ -1,0 +1,212 @@
+"""Parity at the BASELINE.json shapes and at every width list the reference ships:
+cfg1 (50 k-point scan graph, ~335 k cells) inference, a cfg2 batch (8 collated ~19.7 k-cell objects) train step,
+`configs/eth.yaml:56` widths [64,128,256,512] and `configs/modelnet.yaml:56` widths [128,256,512,1024], the decoder-0
+case, the generic FP32 path (DGNN_FMA_ONLY=1) through a whole model, the regulariser's gradient (row R), and the two
+caches (graph plan, packed weights).  Tolerances: tests/helpers.py (logits 1e-4 of the logit scale, labels identical
+off ties, gradients relative Frobenius 1e-2 + median 1e-3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as og
+from oracle import trainer as otr
+from oracle.static_model import NeighborSampler, SurfaceNet as OracleNet, make_clf, to_attr
+from tests.helpers import data_all, full_batch, grad_close, labels_equal_off_ties, logits_close, make_graph
+from tests.test_gpu_model import _train_compare, cuda_net, golden_data
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_cfg1_inference_50k_point_scan_graph_vs_oracle(kf96_state):
+    """BASELINE configs[0]/cfg1: reconbench.yaml StaticEdgeFilters inference on one ~335 k-cell scan graph."""
+    g = make_graph(50_000, seed=0)
+    assert g["n"] > 300_000
+    d = data_all(g, with_pos=True)
+    ref = OracleNet(make_clf()); ref.load_state_dict(kf96_state); ref.eval()
+    with torch.no_grad():
+        zr = ref.inference_layer(d).numpy()
+    net = cuda_net({}, kf96_state).eval()
+    z = net.inference_layer(d).cpu().numpy()
+    err, ok = logits_close(z, zr)
+    assert ok, err
+    flips, ties = labels_equal_off_ties(z, zr)
+    assert flips == 0, (flips, ties)
+
+
+def collate_objects(n_objects, points=3000, seed0=0):
+    """Disjoint union of object graphs in the reference's collated layout (run.py:59-61)."""
+    xs, eas, ys, eis, cens, off = [], [], [], [], [], 0
+    for i in range(n_objects):
+        g = make_graph(points, seed=seed0 + 7 * i)
+        xs.append(g["x"]); eas.append(g["ea"]); ys.append(g["y"]); cens.append(g["cen"].astype(np.float32) + 2.0 * i)
+        eis.append(g["adj"].T.astype(np.int64) + off)
+        off += g["n"]
+    return to_attr(dict(x=torch.from_numpy(np.concatenate(xs)), edge_attr=torch.from_numpy(np.concatenate(eas)),
+                        y=torch.from_numpy(np.concatenate(ys)), pos=torch.from_numpy(np.concatenate(cens)),
+                        edge_index=torch.from_numpy(np.concatenate(eis, axis=1)).contiguous()))
+
+
+def test_cfg2_train_step_on_8_collated_objects_vs_oracle():
+    """BASELINE configs[1]/cfg2 (the bench workload) at 8 objects x ~19.7 k cells: logits, loss, every gradient and the
+    running statistics of one whole-batch train step."""
+    d = collate_objects(8, seed0=100)
+    assert d.x.shape[0] > 150_000
+    _train_compare({}, full_batch(d), d, d.x.shape[0])
+
+
+@pytest.mark.parametrize("convs", [(64, 128, 256, 512), (128, 256, 512, 1024)], ids=["eth", "modelnet"])
+def test_shipped_wide_width_lists_match_oracle(convs):
+    """configs/eth.yaml:56 / aerial.yaml:57 and configs/modelnet.yaml:56 / pretrained/modelnet.yaml:56: inference and a
+    whole train step (tensor-core path, column slices beyond one UMMA tile)."""
+    g = make_graph(1500, seed=61)
+    d = data_all(g, with_pos=True)
+    kw = dict(convs=convs)
+    net, ref = _train_compare(kw, full_batch(d), d, d.x.shape[0], seed=2)
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        z, zr = net.inference_layer(d).cpu().numpy(), ref.inference_layer(d).numpy()
+    err, ok = logits_close(z, zr)
+    assert ok, err
+    flips, _ = labels_equal_off_ties(z, zr)
+    assert flips == 0
+
+
+def test_modelnet_state_dict_layout_loads_strict():
+    """The [128,256,512,1024] model (data/models/modelnet/model_best.ptm is a missing blob): same keys and shapes as the
+    oracle's restatement of the reference module tree."""
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    kw = dict(convs=(128, 256, 512, 1024))
+    ref = OracleNet(make_clf(**kw))
+    net = SurfaceNet(make_clf(device=DEV, **kw))
+    net.load_state_dict(ref.state_dict(), strict=True)
+    assert [tuple(v.shape) for v in net.state_dict().values()] == [tuple(v.shape) for v in ref.state_dict().values()]
+
+
+def test_decoder0_hidden_features_and_gradients(golden):
+    """decoder: 0 (Static:180-187 adds no head): the model returns relu(norm(z_L)); a sum-of-squares loss pins the
+    forward and every gradient on a sampled closure."""
+    d = golden_data(golden)
+    kw = dict(convs=(32, 64), decoder=0)
+    smp = NeighborSampler(d.edge_index, [-1] * 3, 96, node_idx=torch.arange(40, 136), num_nodes=d.x.shape[0])
+    _, n_id, adjs = next(iter(smp))
+    data = to_attr(dict(all=d, batch_n_id=n_id, batch_adjs=adjs))
+    torch.manual_seed(4)
+    ref = OracleNet(make_clf(**kw)).train()
+    net = cuda_net(kw, ref.state_dict()).train()
+    yr = ref(data)
+    w = torch.linspace(0.5, 1.5, yr.shape[0])[:, None]
+    (yr.square() * w).sum().backward()
+    y = net(data)
+    assert y.shape == yr.shape
+    err, ok = logits_close(y.detach().cpu().numpy(), yr.detach().numpy())
+    assert ok, err
+    (y.square() * w.to(DEV)).sum().backward()
+    refp = dict(ref.named_parameters())
+    for k, p in net.named_parameters():
+        e, tol = grad_close(p.grad, refp[k].grad)
+        assert e <= tol, (k, e, tol)
+
+
+def test_generic_fp32_path_whole_model(monkeypatch, kf96_state):
+    """DGNN_FMA_ONLY=1 (the generic FMA kernels behind the same C ABI) through a whole train step and inference."""
+    monkeypatch.setenv("DGNN_FMA_ONLY", "1")
+    g = make_graph(900, seed=71)
+    d = data_all(g)
+    net, ref = _train_compare({}, full_batch(d), d, d.x.shape[0])
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        z, zr = net.inference_layer(d).cpu().numpy(), ref.inference_layer(d).numpy()
+    err, ok = logits_close(z, zr)
+    assert ok, err
+
+
+def test_regulariser_value_and_gradient(golden):
+    """Row R: Trainer.calcRegularization (runModel.py:109-160): value against the reference's own number (golden
+    kf96_reg) and the oracle, gradient w.r.t. the logits against torch autograd of the oracle."""
+    from dgnn_b200 import runModel as rm
+    d = golden_data(golden)
+    z0 = torch.from_numpy(golden["kf96_inference_layer"])
+    z = z0.clone().to(DEV).requires_grad_()
+    reg = rm.edge_regularization(z, d.edge_index, 0.4)
+    np.testing.assert_allclose(reg.item(), float(golden["kf96_reg"]), rtol=2e-5)
+    (3.0 * reg).backward()
+    zr = z0.clone().requires_grad_()
+    (3.0 * otr.edge_regularization(zr, d.edge_index, 0.4)).backward()
+    np.testing.assert_allclose(z.grad.cpu().numpy(), zr.grad.numpy(), rtol=1e-4, atol=1e-9)
+    # bitwise reproducible (integer sign counts, no float atomics)
+    z2 = z0.clone().to(DEV).requires_grad_()
+    (3.0 * rm.edge_regularization(z2, d.edge_index, 0.4)).backward()
+    assert torch.equal(z.grad, z2.grad)
+
+
+def test_train_step_with_regulariser_added_to_the_loss(golden):
+    """runModel.py:250-255: from regularization.edge_epoch on, loss = cell loss + reg over the innermost adjacency
+    (batch_adjs[num_layers], additional_num_hops = 1).  Gradients of every parameter through both terms."""
+    from dgnn_b200 import runModel as rm
+    d = golden_data(golden)
+    kw = dict(convs=(16, 32, 32, 32))
+    L = 4
+    _, n_id, adjs = next(iter(NeighborSampler(d.edge_index, [-1] * (L + 1), 96, node_idx=torch.arange(40, 136),
+                                              num_nodes=d.x.shape[0])))
+    data = to_attr(dict(all=d, batch_n_id=n_id, batch_adjs=adjs))
+    torch.manual_seed(5)
+    ref = OracleNet(make_clf(**kw)).train()
+    net = cuda_net(kw, ref.state_dict()).train()
+    clf = make_clf(device=DEV, **kw)
+    n_sup = adjs[L - 1][2][1]
+    gt, bx = d.y[n_id[:n_sup]], d.x[n_id[:n_sup]]
+    zr = ref(data)
+    inner_ei, inner_size = adjs[L][0], adjs[L][2]
+    lr = otr.cell_loss(zr, gt, bx[:, 0])[0] + otr.edge_regularization(zr[:inner_size[0]], inner_ei, 0.4)
+    lr.backward()
+    z = net(data)
+    loss = rm.cell_loss(z, gt, bx, clf) + rm.calc_regularization(z, data, clf, net.num_layers)
+    loss.backward()
+    assert abs(loss.item() - lr.item()) <= 2e-5 * max(1.0, abs(lr.item()))
+    refp = dict(ref.named_parameters())
+    for k, p in net.named_parameters():
+        e, tol = grad_close(p.grad, refp[k].grad)
+        assert e <= tol, (k, e, tol)
+
+
+def test_graph_plan_cache_notices_in_place_edits(kf96_state):
+    """the cached ELL plan is keyed on tensor identity + version; an in-place edit of edge_attr must not
+    reuse stale edge features."""
+    g = make_graph(400, seed=81)
+    d = data_all(g)
+    net = cuda_net({}, kf96_state).eval()
+    z1 = net.inference_layer(d)
+    assert torch.equal(net.inference_layer(d), z1)            # cache hit: same result
+    d.edge_attr.mul_(0.5)                                      # in place: same storage, same data_ptr
+    z2 = net.inference_layer(d)
+    fresh = cuda_net({}, kf96_state).eval()
+    d2 = to_attr(dict(x=d.x, edge_attr=d.edge_attr.clone(), edge_index=d.edge_index))
+    assert torch.equal(z2, fresh.inference_layer(d2))
+    assert not torch.equal(z1, z2)
+
+
+def test_packed_weight_cache_follows_weight_updates(kf96_state):
+    """Packed tcgen05 operands are cached per module until a weight changes (in-place torch ops and runModel.Adam)."""
+    from dgnn_b200 import runModel as rm
+    g = make_graph(300, seed=82)
+    d = data_all(g)
+    net = cuda_net({}, kf96_state).eval()
+    z1 = net.inference_layer(d)
+    with torch.no_grad():
+        net.convs[1].conv.lin_j.weight.mul_(1.5)
+    z2 = net.inference_layer(d)
+    st = {k: v.clone() for k, v in kf96_state.items()}
+    st["convs.1.conv.lin_j.weight"] = st["convs.1.conv.lin_j.weight"] * 1.5
+    assert torch.equal(z2, cuda_net({}, st).eval().inference_layer(d))
+    assert not torch.equal(z1, z2)
+    # Adam writes the parameters from a kernel: the cache must notice that too
+    net.train()
+    opt = rm.Adam(net.parameters(), lr=0.01)
+    clf = make_clf(device=DEV)
+    loss = rm.cell_loss(net(full_batch(d)), d.y, d.x, clf)
+    loss.backward(); opt.step()
+    net.eval()
+    z3 = net.inference_layer(d)
+    fresh = cuda_net({}, {k: v.detach().cpu() for k, v in net.state_dict().items()}).eval()
+    assert torch.equal(z3, fresh.inference_layer(d))

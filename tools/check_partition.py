@@ -47,7 +47,7 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 t = torch.tensor([ms, err], device=dev)
 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-g, maps, _, _ = pi._plan
+g, maps = pi._plan[0], pi._plan[1]
 print("rank %d/%d: n=%d own=%d halo=%d (%.1f%%) max|partitioned - single| = %.2e" % (rank, world, n, maps.n_own, maps.n_halo, 100.0 * maps.n_halo / max(maps.n_own, 1), err), flush=True)
 if rank == 0:
     print("PARTITIONED_INFERENCE world=%d cells=%d ms=%.3f cells/s=%.3e max_err=%.2e" % (world, n, t[0].item(), n / (t[0].item() * 1e-3), t[1].item()), flush=True)

@@ -1,8 +1,10 @@
 // Development probe: run ONE tcgen05.mma (kind::tf32, cta_group::1, M = 128) on caller-provided
 // shared-memory images and descriptor bits, and return the [128 x n] accumulator.  Used by
-// tools/probe_umma.py to validate operand layouts on hardware; not part of the hot path.
-#include "umma.cuh"
-#include "common.cuh"
+// tools/probe_umma.py to validate operand layouts on hardware; not part of the product library:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared tools/debug_umma.cu \
+//        dgnn_b200/csrc/head.o -o gpurun_variants/libdebug_umma.so -lcudart
+#include "../dgnn_b200/csrc/umma.cuh"
+#include "../dgnn_b200/csrc/common.cuh"
 
 namespace dgnn {
 using namespace umma;

@@ -2,7 +2,17 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from dgnn_b200._lib import call, ptr
+import ctypes
+from dgnn_b200._lib import ptr
+
+# the probe kernel lives in its own library (build line: header of tools/debug_umma.cu)
+_dbg = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_variants", "libdebug_umma.so"))
+_dbg.dgnn_debug_umma.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
+                                 ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+
+
+def call(name, *a):
+    assert getattr(_dbg, name)(*a) == 0
 
 M, K = 128, 8
 DEV = "cuda:0"
