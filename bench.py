@@ -10,9 +10,16 @@ scan-like points each, ~19.7 k cells per object incl. infinite cells, random fea
 training mode, volume-weighted KL loss, Adam lr 0.005.  One step = forward + loss + backward +
 Adam over the whole batch.  Metric: Delaunay cells/s (whole job, all GPUs).
 
-N > 1 (launched by torchrun, one rank per GPU): data-parallel over objects — every rank trains on
-its own batch of B objects (weak scaling) and the gradients are averaged with one NCCL all-reduce
-per step before the optimiser step.
+N > 1 (launched by torchrun, one rank per GPU): ONE scene graph partitioned over the GPUs (north_star
+subsystem 4, BASELINE configs[3]/[4]): every rank generates its own shard of an analytic 4-regular
+lattice scene on the device (~8.4 M cells per GPU: 16.8 M / 33.5 M / 67.1 M cells at 2 / 4 / 8 GPUs), the
+halo maps are negotiated between the ranks (no rank holds the whole graph), owned cells are ordered
+boundary-first and every layer's halo exchange (NCCL all-to-all over NVLink) overlaps the interior rows.
+`value` = fwd+loss+bwd+Adam cells/s of the Static kf96 model on that scene (the metric's fwd+bwd; batch
+statistics, loss normaliser and gradients all-reduced).  Extra keys: `scene_inference` = eval inference on
+the FIXED 67.1 M-cell scene at every N (strong scaling; N = 1 carries the single-GPU number of the same
+scene), `partition_vs_single_max_abs` = the partitioned logits against the single-GPU path on a small
+scene, `dp` = the round-1 data-parallel object-batch number.
 
 ``--impl reference`` times the CPU restatement of the reference (oracle/, plain PyTorch with all
 host threads; the reference's own modules need torch_geometric, which cannot be installed here) on
@@ -273,6 +280,356 @@ def cpu_reference(n_objects, steps, warmup, seed0=0):
     return d["n"] * steps / dt, cores, d["n"], dt / steps
 
 
+def parity_vs_oracle(n_objects, dev, seed0=0):
+    """First training step of the CUDA path against the CPU oracle on the cpu_baseline sample (same graphs, same initial
+    weights): max |dz| / max(|z_ref|, mean|z_ref|) over the logits, the loss values, labels off ties."""
+    from oracle import trainer as otr
+    from oracle.static_model import SurfaceNet as OracleNet
+    from dgnn_b200 import runModel as rm
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    from dgnn_b200.synthetic import make_clf, to_attr
+    d = make_objects(n_objects, seed0)
+    data = batch_of(d, to_attr)
+    torch.manual_seed(0)
+    ref = OracleNet(make_clf(convs=WIDTHS)).train()
+    clf = make_clf(convs=WIDTHS, device=str(dev))
+    net = SurfaceNet(clf)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(dev).train()
+    with torch.no_grad():
+        zr = ref(data)
+        lr, _, _ = otr.cell_loss(zr, data.all.y, data.all.x[:, 0])
+        z = net(data)
+        loss = rm.cell_loss(z, data.all.y, data.all.x, clf)
+    zr = zr.double(); z = z.cpu().double()
+    scale = torch.maximum(zr.abs(), zr.abs().mean())
+    ties = (zr[:, 0] - zr[:, 1]).abs() <= 2e-4 * zr.abs().mean()
+    flips = int((((z[:, 1] > z[:, 0]) != (zr[:, 1] > zr[:, 0])) & ~ties).sum())
+    return {"logits_max_rel": float(((z - zr).abs() / scale).max()), "loss_cuda": float(loss.item()), "loss_oracle": float(lr.item()),
+            "label_flips_off_ties": flips, "cells": int(d["n"]), "tolerance": 1e-4}
+
+
+# --------------------------------------------------------------------------- partitioned scene (N > 1)
+
+SCENE_DIMS_WEAK = {1: (128, 128, 256), 2: (128, 256, 256), 4: (256, 256, 256), 8: (256, 256, 512)}   # 8.39 M cells per GPU
+SCENE_DIMS_STRONG = (256, 256, 512)                                                                 # 67.1 M cells
+SCENE_DIMS_PARITY = (32, 32, 32)                                                                    # 65 536 cells
+
+
+def _maxr(v, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _timed_region(fn, steps, warmup, dev, world):
+    """W warm-up + K timed calls between barrier + synchronize, CUDA events, max over ranks (ms for the K calls)."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    return _maxr(e0.elapsed_time(e1), dev, world)
+
+
+def scene_inference(net, dims, rank, world, dev, iters=5, overlap=True):
+    """Eval-mode partitioned inference of the whole lattice scene `dims` (sharded build); cells/s of the whole job."""
+    from dgnn_b200 import scene as sc
+    from dgnn_b200.partition import PartitionedInference
+    n = 2 * dims[0] * dims[1] * dims[2]
+    shard = sc.lattice_scene(dims, rank, world, dev)
+    pi = PartitionedInference(net)
+    g, maps, x0, ids, comm = pi.prepare_scene(shard, overlap=overlap)
+    del shard
+    net.eval()
+    ms = _timed_region(lambda: pi.run(), iters, 2, dev, world) / iters
+    ex_ms = 0.0
+    if world > 1:            # the halo exchange of one 128-wide layer alone (pack + all-to-all), not overlapped
+        h = torch.zeros((g.n_src, 128), dtype=torch.float32, device=dev)
+        ex_ms = _timed_region(lambda: comm.exchange(h), 10, 2, dev, world) / 10
+        del h
+    res = {"cells": n, "dims": list(dims), "ms": round(ms, 3), "cells_per_s": n / (ms * 1e-3),
+           "cells_per_gpu": maps.n_own, "halo_fraction": round(_maxr(maps.n_halo / max(maps.n_own, 1), dev, world), 5),
+           "boundary_fraction": round(_maxr(maps.n_boundary / max(maps.n_own, 1), dev, world), 5),
+           "exchange_ms_per_128wide_layer": round(ex_ms, 4), "exchanges_per_pass": 3,
+           "limiting_collective": "all_to_all_single of boundary rows (NCCL), %.3f ms of %.3f ms per pass when not hidden"
+                                  % (3 * ex_ms, ms),
+           "overlap": bool(overlap and world > 1)}
+    net.train()
+    return res
+
+
+def partition_parity(net, rank, world, dev):
+    """max |partitioned - single GPU| over the logits of a small lattice scene: the partitioned path builds from shards
+    (dgnn_b200.scene.lattice_scene), the single-GPU path from the whole graph through the ordinary loader layout."""
+    import torch.distributed as dist
+    from dgnn_b200 import scene as sc
+    from dgnn_b200.partition import PartitionedInference
+    from dgnn_b200.synthetic import to_attr
+    dims = SCENE_DIMS_PARITY
+    net.eval()
+    pi = PartitionedInference(net)
+    pi.prepare_scene(sc.lattice_scene(dims, rank, world, dev))
+    ids, out = pi.run()
+    n = 2 * dims[0] * dims[1] * dims[2]
+    full = torch.zeros((n, out.shape[1]), dtype=torch.float32, device=dev)
+    full[ids] = out
+    if world > 1:
+        dist.all_reduce(full)                       # every cell is owned by exactly one rank
+    err = None
+    if rank == 0:
+        g = sc.lattice_global(dims)
+        with torch.no_grad():
+            ref = net.inference_layer(to_attr(g))
+        err = float((full - ref).abs().max().item())
+    net.train()
+    return err
+
+
+def run_partitioned(args, rank, world, local_rank):
+    """N > 1: the partitioned-scene benchmark (module docstring)."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from dgnn_b200 import _lib, runModel as rm, scene as sc
+    from dgnn_b200.partition import PartitionedTraining
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    from dgnn_b200.synthetic import make_clf, to_attr
+
+    launches = {"n": 0}
+    orig_call = _lib.call
+    mods = ("dgnn_b200._lib", "dgnn_b200.engine", "dgnn_b200.graph", "dgnn_b200.runModel", "dgnn_b200.partition")
+
+    def counting_call(name, *a):
+        launches["n"] += 1
+        return orig_call(name, *a)
+
+    def set_call(fn):
+        for modname in mods:
+            mod = sys.modules.get(modname)
+            if mod is not None and hasattr(mod, "call"):
+                setattr(mod, "call", fn)
+
+    clf = make_clf(convs=WIDTHS, device=str(dev))
+    torch.manual_seed(0)
+    net = SurfaceNet(clf).to(dev).train()
+    for t in list(net.parameters()) + list(net.buffers()):
+        if t.is_floating_point():
+            dist.broadcast(t.data, 0)
+    opt = rm.Adam(net.parameters(), lr=0.005)
+
+    # parity first (small scene): partitioned logits against the single-GPU path
+    parity = partition_parity(net, rank, world, dev)
+
+    # ---- value: training step on the weak-scaled scene ------------------------------------------------------
+    dims = SCENE_DIMS_WEAK.get(world) or SCENE_DIMS_WEAK[8]
+    n_total = 2 * dims[0] * dims[1] * dims[2]
+    shard = sc.lattice_scene(dims, rank, world, dev, need_backward=True)
+    pt = PartitionedTraining(net)
+    g, maps, x0, ids, comm = pt.prepare_scene(shard)
+    host_feats = (shard.x.cpu().pin_memory(), shard.y.cpu().pin_memory(), shard.w.cpu().pin_memory())
+    order = maps.order
+    del shard
+    set_call(counting_call)
+
+    def step():
+        _, logits = pt.forward()
+        loss = pt.loss(logits)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        pt.allreduce_gradients()
+        opt.step()
+        return loss
+
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.warmup):
+            step()
+        launches["n"] = 0
+        comm.stats = {"exchanges": 0, "bytes_sent": 0}
+        ms = _timed_region(step, args.steps, 0, dev, world)
+    n_launch = launches["n"]
+    ex_per_step = comm.stats["exchanges"] / max(args.steps, 1)
+    ex_bytes = comm.stats["bytes_sent"] / max(args.steps, 1)
+    value = n_total * args.steps / (ms * 1e-3)
+
+    # ---- e2e: node features + supervision of the step come from pinned HOST buffers (uploaded one step ahead on a
+    # copy stream), the loss is read back; topology and edge attributes stay resident (one scene, many steps)
+    copy_stream = torch.cuda.Stream(device=dev)
+    n_own = maps.n_own
+    h2d = sum(t.numel() * t.element_size() for t in host_feats)
+    staged = {}
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            staged["t"] = tuple(t.to(dev, non_blocking=True) for t in host_feats)
+            staged["ev"] = torch.cuda.Event(); staged["ev"].record(copy_stream)
+
+    upload()
+
+    def e2e_step():
+        torch.cuda.current_stream().wait_event(staged["ev"])
+        xs, ys, ws = staged["t"]
+        for t in staged["t"]:
+            t.record_stream(torch.cuda.current_stream())
+        upload()                                            # next step's inputs while this step computes
+        o = order if order is not None else slice(None)
+        x0[:n_own, :xs.shape[1]] = xs[o]
+        comm.exchange(x0)                                   # halo rows of the fresh features
+        pt._sup = (ys[o], ws[o])
+        return step().item()
+
+    e2e_steps = max(3, args.steps // 4)
+    ms_e2e = _timed_region(e2e_step, e2e_steps, 1, dev, world)
+    e2e_value = n_total * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel times of one step on this rank -> roofline of the dominant kernel
+    peak, peak_src = peak_hbm()
+    set_call(orig_call)
+    prof = KernelProfile()
+    prof.install()
+    for _ in range(2):
+        step()
+    prof.uninstall()
+    roofline, table, kernel_ms = prof.summary(2, peak, peak_src)
+
+    # ---- partitioned training against the single-GPU step on the small scene (loss + gradients)
+    train_par = partition_train_parity(clf, rank, world, dev)
+
+    # free the training scene before the big inference scene
+    del pt, g, x0, comm, staged
+    opt.zero_grad(set_to_none=True)
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+    infer = scene_inference(net, SCENE_DIMS_STRONG, rank, world, dev)
+    infer["hbm_frac_per_gpu"] = round(infer["cells_per_s"] / world * 4024 / 1e9 / peak, 4)
+    gc.collect(); torch.cuda.empty_cache()
+    infer_noov = scene_inference(net, SCENE_DIMS_STRONG, rank, world, dev, iters=3, overlap=False)
+    infer["ms_without_overlap"] = infer_noov["ms"]
+    gc.collect(); torch.cuda.empty_cache()
+
+    # ---- the round-1 data-parallel object-batch number, as an extra key
+    dp = dp_objects(args, rank, world, dev, clf)
+
+    if rank == 0:
+        config = {"workload": "configs[3]/[4]-shaped partitioned scene: ONE %d-cell graph (analytic diamond-cubic lattice %s, "
+                              "4-regular, random features of the feat tool's shape) split into %d Morton ranges, per-layer halo "
+                              "exchange over NCCL, Static kf96 model, fwd+loss+bwd+Adam, BN train mode with all-reduced "
+                              "statistics, kl loss" % (n_total, "x".join(map(str, dims)), world),
+                  "widths": [F0] + list(WIDTHS), "decoder": "128->64->2", "edge_features": FE,
+                  "cells_per_gpu": maps.n_own, "parallelism": "graph partition x%d (halo all-to-all + gradient all-reduce)" % world,
+                  "l2_policy": "inputs + saved activations per step (>20 GB per GPU) exceed the 126 MB L2"}
+        out = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+               "cells_per_gpu_per_step": maps.n_own,
+               "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                       "ms_per_step": ms_e2e / e2e_steps,
+                       "resident": "topology and edge attributes of the scene (loaded once); node features, targets and "
+                                   "loss weights are uploaded every step"},
+               "gpu_launches": int(n_launch), "clocks": clocks.summary(), "roofline": roofline,
+               "step_hbm_frac": round(maps.n_own * 19_900 / (ms / args.steps * 1e-3) / 1e9 / peak, 4),
+               "kernel_ms_per_step": round(kernel_ms, 3),
+               "scene": {"cells": n_total, "dims": list(dims), "generator": "diamond-cubic lattice, sharded on-device build",
+                         "halo_fraction": round(maps.n_halo / max(maps.n_own, 1), 5),
+                         "boundary_fraction": round(maps.n_boundary / max(maps.n_own, 1), 5),
+                         "halo_exchanges_per_step": ex_per_step, "halo_bytes_sent_per_gpu_per_step": int(ex_bytes)},
+               "scene_inference": infer,
+               "partition_vs_single_max_abs": parity,
+               "partition_train_vs_single": train_par,
+               "dp": dp, "kernels": table, "cpu_baseline": None}
+        print(json.dumps(out))
+    dist.destroy_process_group()
+
+
+def partition_train_parity(clf, rank, world, dev):
+    """One training step (loss + every gradient) of the partitioned small scene against the single-GPU step."""
+    import torch.distributed as dist
+    from dgnn_b200 import runModel as rm, scene as sc
+    from dgnn_b200.partition import PartitionedTraining
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    from dgnn_b200.synthetic import to_attr
+    dims = SCENE_DIMS_PARITY
+    torch.manual_seed(1)
+    net = SurfaceNet(clf).to(dev).train()
+    for t in list(net.parameters()) + list(net.buffers()):
+        if t.is_floating_point() and world > 1:
+            dist.broadcast(t.data, 0)
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    pt = PartitionedTraining(net)
+    pt.prepare_scene(sc.lattice_scene(dims, rank, world, dev, need_backward=True))
+    _, logits = pt.forward()
+    loss = pt.loss(logits)
+    loss.backward()
+    pt.allreduce_gradients()
+    res = None
+    if rank == 0:
+        ref = SurfaceNet(clf).to(dev).train()
+        ref.load_state_dict(state)
+        g = to_attr(sc.lattice_global(dims))
+        n = g.x.shape[0]
+        ei = g.edge_index
+        batch = to_attr(dict(all=g, batch_n_id=torch.arange(n), batch_adjs=[(ei, torch.arange(ei.shape[1]), (n, n))] * 5))
+        z = ref(batch)
+        lr = rm.cell_loss(z, g.y, g.x, clf)
+        lr.backward()
+        worst = 0.0
+        refp = dict(ref.named_parameters())
+        for k, p in net.named_parameters():
+            gr = refp[k].grad
+            if gr is None or float(gr.norm()) < 1e-6:
+                continue
+            worst = max(worst, float((p.grad - gr).norm() / gr.norm()))
+        res = {"loss_abs_diff": abs(float(loss.item()) - float(lr.item())), "grad_max_rel_frobenius": worst}
+    return res
+
+
+def dp_objects(args, rank, world, dev, clf):
+    """Round-1 multi-GPU mode kept as an extra key: data-parallel over object batches (configs[1] per rank), one
+    gradient all-reduce per step."""
+    import torch.distributed as dist
+    from dgnn_b200 import runModel as rm
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    from dgnn_b200.synthetic import to_attr
+    host = make_objects(args.objects, seed0=1000 * rank)
+    torch.manual_seed(0)
+    net = SurfaceNet(clf).to(dev).train()
+    opt = rm.Adam(net.parameters(), lr=0.005)
+    params = list(net.parameters())
+    dres = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    data = batch_of(dres, to_attr)
+
+    def step():
+        loss = rm.cell_loss(net(data), data.all.y, data.all.x, clf)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat /= world
+        off = 0
+        for p in params:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        opt.step()
+
+    steps = max(5, args.steps // 2)
+    ms = _timed_region(step, steps, 3, dev, world)
+    return {"value": world * host["n"] * steps / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms / steps,
+            "cells_per_gpu_per_step": host["n"], "note": "data-parallel object batches (weak scaling), gradient all-reduce only"}
+
+
 # --------------------------------------------------------------------------- main
 
 
@@ -310,11 +667,13 @@ def main():
                           "e2e": {"value": v, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    if world > 1:
+        run_partitioned(args, rank, world, local_rank)
+        return
+
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     from dgnn_b200 import _lib, runModel as rm
     from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
     from dgnn_b200.synthetic import make_clf, to_attr  # clf / attr-dict stand-ins for Munch
@@ -440,16 +799,31 @@ def main():
     infer_ms = i0.elapsed_time(i1) / 10
     net.train()
 
+    # the fixed 67.1 M-cell scene of the multi-GPU runs on ONE GPU (strong-scaling reference point of `scene_inference`)
+    del data, dres, dall, hb, pinned, pf
+    opt.zero_grad(set_to_none=True)
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+    try:
+        scene_inf = scene_inference(net, SCENE_DIMS_STRONG, 0, 1, dev, iters=3)
+        scene_inf["hbm_frac_per_gpu"] = round(scene_inf["cells_per_s"] * 4024 / 1e9 / peak, 4)
+    except torch.OutOfMemoryError:
+        scene_inf = {"error": "out of memory on one GPU"}
+    gc.collect(); torch.cuda.empty_cache()
+    part_parity = partition_parity(net, 0, 1, dev)       # sharded build (1 shard) against the ordinary loader path
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         v, cores, nc, s_per = cpu_reference(args.cpu_objects, 2, 1)
         cpu = {"value": v, "unit": "cells/s", "cores": cores, "kind": "port",
                "sample": "%d objects (%d cells) per step, 2 steps after 1 warm-up, oracle (plain PyTorch CPU)" % (args.cpu_objects, nc)}
+        parity = parity_vs_oracle(args.cpu_objects, dev)
 
     # whole-step algorithmic bytes (kf96 training fwd+bwd ~ 19.9 KB/cell)
     step_bytes_per_cell = 19_900
@@ -467,11 +841,13 @@ def main():
            "inference": {"cells_per_s_per_gpu": n_cells / (infer_ms * 1e-3), "ms": round(infer_ms, 3),
                          "hbm_frac": round(n_cells * 4024 / (infer_ms * 1e-3) / 1e9 / peak, 4),
                          "note": "eval-mode inference_layer on the same batch, device resident, 4 024 B/cell"},
+           "scene_inference": scene_inf,
+           "partition_vs_single_max_abs": part_parity,
+           "parity": parity,
+           "parity_max_rel": parity["logits_max_rel"] if parity else None,
            "kernels": table,
            "cpu_baseline": cpu}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

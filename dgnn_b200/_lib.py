@@ -24,6 +24,7 @@ SIGNATURES = {
     "dgnn_last_error": [],
     "dgnn_device_check": [I],
     "dgnn_sm_count": [],
+    "dgnn_reserve_sms": [I],
     "dgnn_small_grid": [],
     "dgnn_ell_from_adjacency": [P, L, P, P, P, P],
     "dgnn_ell_build": [P, P, L, L, L, I, P, P, P, P, P],
@@ -46,7 +47,8 @@ SIGNATURES = {
     "dgnn_tc_supported": [I, I, I],
     "dgnn_tc_grid": [],
     "dgnn_tc_packed_floats": [I, I, I],
-    "dgnn_pack_b_tf32": [P, I, I, I, I, P, P],
+    "dgnn_tc_slice": [I],
+    "dgnn_pack_b_tf32": [P, I, I, I, I, I, P, P],
     "dgnn_layer_fwd_tc": [P, P, P, I, P, P, I, P, P, P, P, P, P, I, L, I, I, P, P, P, P],
     "dgnn_dense_bwd_tc": [P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P],
     "dgnn_gather_tc_supported": [I, I],

@@ -35,6 +35,7 @@ constexpr int G_M = 128;
 constexpr int G_EA_STAGES = 2;                       // EA operand ring (hi | lo per stage)
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
 constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
+constexpr int DWE_ROUNDS = 1;                        // dW_e: 1 = P rounded to TF32 once, 2 = P split hi / lo (see dwe_tc_kernel)
 
 struct GatherTcArgs {
     const float* x;        // rows to gather: h source (fwd) or d_agg (bwd)
@@ -476,8 +477,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
 }
 
 // ---------------------------------------------------------------------------------------------------
-// dW_e / db_e = P^T . EA over all edges, P[edge, f] = h(s)[f] * d_agg[onbr[s,k]][f].
-// Per row quarter q one operand stage (P^T hi [128 features x 32 cells] | EA^T hi | EA^T lo); the strips a warp
+// dW_e / db_e = P^T . EA over all edges, P[edge, f] = h(s)[f] * d_agg[onbr[s,k]][f], 3xTF32 (P and EA both split).
+// Per row quarter q one operand stage (P^T [128 features x 32 cells], hi then lo | EA^T hi | EA^T lo); the strips a warp
 // needs (its rows' z_prev strip, then the four gathered d_agg strips) arrive through the same warp-private
 // cp.async ring as in gather_tc_kernel, one item ahead, so no load is waited for in registers.
 template <int CPT>
@@ -510,7 +511,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
 
     {
         const uint32_t idesc = make_idesc_tf32(G_M, 32);
-        const int q = warp & 3, grp = warp >> 2;
+        // row quarter q = warp >> 2: the four warps of a quarter sit on four different schedulers, so a quarter that waits
+        // for its MMAs does not idle a whole scheduler (TMEM is only touched in the read-out below)
+        const int q = warp >> 2, grp = warp & 3;
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;
         uint8_t* xw = x_base + (size_t)warp * WSTAGE;
@@ -615,43 +618,53 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                         }
                     }
                     if (k < 3) load_ev(k + 1);
+                    // Round 0 stores P_hi = rna_tf32(P) (+ EA^T above) and accumulates P_hi . (EA_hi + EA_lo).  DWE_ROUNDS = 2 adds a
+                    // second round over the SAME operand buffer with P_lo = P - P_hi and P_lo . EA_hi (full 3xTF32).  Measured on
+                    // B200 (tools/diag_grad_wide.py, eth widths): the gradient error of lin_e against the fp64 oracle is the same
+                    // with and without it (median 9.7e-4 vs 9.9e-4 of the RMS: ReLU-mask flips dominate, the unbiased 2^-12
+                    // rounding of P does not show), while the round costs 0.27 ms per 128-wide layer => one round.
 #pragma unroll
-                    for (int j = 0; j < CPT; j += 4) {
-                        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid && c0 + j < p.f) d = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
-                        const float dp[4] = {h[j] * d.x, h[j + 1] * d.y, h[j + 2] * d.z, h[j + 3] * d.w};
+                    for (int rnd = 0; rnd < DWE_ROUNDS; ++rnd) {
+                        if (rnd == 1) mbar_wait(&p_empty[q], (it & 1) ^ 1);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            // row = c0 + j + i, column = lane; c0 is a multiple of 8: row & 7 = (j & 4) + i
-                            const uint32_t r8 = (uint32_t)((j & 4) + i);
-                            const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ r8) << 4) + (((uint32_t)lane & 3u) << 2);
-                            sts32(smem_u32(pq) + off, tf32_rna(dp[i]));
-                        }
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence_block();
-                        const int arrived = atomicAdd(&p_count[q], 1);
-                        if (arrived == 3) {            // last warp of the quarter: accumulate P^T . EA of this stage
-                            p_count[q] = 0;
-                            __threadfence_block();
-                            tc_fence_after_sync();
-                            // every quarter accumulates into its own TMEM columns, its stages in order: the sum over
-                            // cells is evaluated in a fixed order whatever the timing of the warps
-                            const uint32_t ph = smem_u32(pq), ehh = ph + G_ATOM, ell = ehh + 32 * 128;
-                            const uint32_t dq = tmem_base + (uint32_t)(q * 32);
+                        for (int j = 0; j < CPT; j += 4) {
+                            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (valid && c0 + j < p.f) d = lds128(smem_u32(xs) + ((((uint32_t)(j >> 2)) ^ swz_l) << 4));
+                            const float dp[4] = {h[j] * d.x, h[j + 1] * d.y, h[j + 2] * d.z, h[j + 3] * d.w};
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                const uint32_t ko = kk * 32;
-                                mma_tf32(dq, make_desc(ph + ko), make_desc(ehh + ko), idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                                mma_tf32(dq, make_desc(ph + ko), make_desc(ell + ko), idesc, 1u);
+                            for (int i = 0; i < 4; ++i) {
+                                // row = c0 + j + i, column = lane; c0 is a multiple of 8: row & 7 = (j & 4) + i
+                                const uint32_t r8 = (uint32_t)((j & 4) + i);
+                                const uint32_t off = (uint32_t)(c0 + j + i) * 128u + ((((uint32_t)lane >> 2) ^ r8) << 4) + (((uint32_t)lane & 3u) << 2);
+                                const float hi = tf32_rna(dp[i]);
+                                sts32(smem_u32(pq) + off, rnd == 0 ? hi : dp[i] - hi);
                             }
-                            mma_commit(&p_empty[q]);
                         }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            const int arrived = atomicAdd(&p_count[q], 1);
+                            if (arrived == 3) {            // last warp of the quarter: accumulate P^T . EA of this round
+                                p_count[q] = 0;
+                                __threadfence_block();
+                                tc_fence_after_sync();
+                                // every quarter accumulates into its own TMEM columns, its rounds in order: the sum over
+                                // cells is evaluated in a fixed order whatever the timing of the warps
+                                const uint32_t ph = smem_u32(pq), ehh = ph + G_ATOM, ell = ehh + 32 * 128;
+                                const uint32_t dq = tmem_base + (uint32_t)(q * 32);
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    const uint32_t ko = kk * 32;
+                                    mma_tf32(dq, make_desc(ph + ko), make_desc(ehh + ko), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                                    if (rnd == 0) mma_tf32(dq, make_desc(ph + ko), make_desc(ell + ko), idesc, 1u);
+                                }
+                                mma_commit(&p_empty[q]);
+                            }
+                        }
+                        __syncwarp();
+                        ++it;
                     }
-                    __syncwarp();
-                    ++it;
                 }
                 __syncwarp();
             }
@@ -661,7 +674,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
         // The quarters run independently; only after every warp has issued its last stage is each p_empty barrier at
         // most one phase behind, which makes the parity wait below unambiguous.
         __syncthreads();
-        if (grp == 0) {
+        if (warp < 4) {                                  // warp w reads TMEM lanes (= feature rows) 32 w .. 32 w + 31
+            const int row = warp * 32 + lane;
             float* outp = p.dwe_partials + (size_t)blockIdx.x * p.s_ld * 32;
             float v[32];
             if (it > 0) {
@@ -669,11 +683,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                 // quarter is the only one nobody has waited for yet
                 for (int qq = 0; qq < 4; ++qq) mbar_wait(&p_empty[qq], (it - 1) & 1);
                 tc_fence_after_sync();
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);          // quarter 0, then + 1, 2, 3 in order
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);       // quarter 0, then + 1, 2, 3 in order
 #pragma unroll 1
                 for (int qq = 1; qq < 4; ++qq) {
                     float w[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(qq * 32), w);
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(qq * 32), w);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += w[i];
                 }

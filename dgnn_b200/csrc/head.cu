@@ -14,6 +14,7 @@ namespace dgnn {
 thread_local char g_err[512] = {0};
 
 static int g_sms[64] = {0};
+static thread_local int g_sm_reserve = 0;   // SMs the persistent kernels leave free (dgnn_reserve_sms)
 int sm_count() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
@@ -22,7 +23,8 @@ int sm_count() {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
         g_sms[dev] = n;
     }
-    return g_sms[dev];
+    const int n = g_sms[dev] - g_sm_reserve;
+    return n > 1 ? n : 1;
 }
 
 // (kernel, device) pairs whose dynamic shared-memory limit has been raised
@@ -110,6 +112,47 @@ __global__ void norm_finalize_kernel(const double* __restrict__ stats, int n_par
             shift[ch] = bv - (float)m * sc;
             mean_o[ch] = (float)m;
             rstd_o[ch] = rs;
+        }
+    }
+}
+
+// BatchNorm (mode 0) finalize, parallel: a block handles 32 channels with 8 lanes each; lane q adds the partials
+// q, q+8, ..., the eight lane sums are combined in lane order (fixed summation tree: reproducible)
+__global__ void __launch_bounds__(256) norm_finalize_bn_kernel(const double* __restrict__ stats, int n_partials,
+                                                               long long n_rows, int c, const float* __restrict__ weight,
+                                                               const float* __restrict__ bias, float eps, float momentum,
+                                                               float* running_mean, float* running_var, float* scale,
+                                                               float* shift, float* mean_o, float* rstd_o) {
+    __shared__ double red_s[8][32], red_q[8][32];
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + lane;
+    double s = 0.0, sq = 0.0;
+    if (ch < c)
+        for (int p = q; p < n_partials; p += 8) {
+            s += stats[(size_t)p * 2 * c + ch];
+            sq += stats[(size_t)p * 2 * c + c + ch];
+        }
+    red_s[q][lane] = s; red_q[q][lane] = sq;
+    __syncthreads();
+    if (q == 0 && ch < c) {
+        double ts = 0.0, tq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ts += red_s[k][lane]; tq += red_q[k][lane]; }
+        const double n = (double)n_rows;
+        const double m = ts / n;
+        double var = tq / n - m * m;
+        if (var < 0.0) var = 0.0;
+        const float rs = (float)(1.0 / sqrt(var + (double)eps));
+        const float w = weight ? weight[ch] : 1.f, b = bias ? bias[ch] : 0.f;
+        const float sc = w * rs;
+        scale[ch] = sc;
+        shift[ch] = b - (float)m * sc;
+        mean_o[ch] = (float)m;
+        rstd_o[ch] = rs;
+        if (running_mean) {
+            const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+            running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
+            running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unb;
         }
     }
 }
@@ -521,6 +564,14 @@ extern "C" int dgnn_device_check(int device) {
 }
 
 extern "C" int dgnn_sm_count(void) { return sm_count(); }
+// The persistent layer kernels fill every SM (one CTA each, all registers).  While a halo exchange runs next to a layer
+// the calling thread reserves a few SMs so that the pack kernel and the NCCL kernels of the communication stream get
+// scheduled immediately instead of behind the layer kernel.  Returns the previous value; thread-local.
+extern "C" int dgnn_reserve_sms(int n) {
+    const int prev = g_sm_reserve;
+    g_sm_reserve = n < 0 ? 0 : n;
+    return prev;
+}
 extern "C" int dgnn_small_grid(void) { return sm_count() * 4; }
 
 extern "C" int dgnn_norm_finalize(const double* stats, int n_partials, int64_t n_rows, int c, const float* weight,
@@ -529,8 +580,13 @@ extern "C" int dgnn_norm_finalize(const double* stats, int n_partials, int64_t n
                                   void* stream) {
     DGNN_REQUIRE(stats && scale && shift && mean && rstd, "null pointer");
     DGNN_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (batch) or 1 (graph layer norm)");
-    norm_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(stats, n_partials, n_rows, c, weight, bias, eps, momentum,
-                                                           mode, running_mean, running_var, scale, shift, mean, rstd);
+    if (mode == 0)
+        norm_finalize_bn_kernel<<<(c + 31) / 32, 256, 0, as_stream(stream)>>>(stats, n_partials, n_rows, c, weight, bias, eps,
+                                                                              momentum, running_mean, running_var, scale,
+                                                                              shift, mean, rstd);
+    else
+        norm_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(stats, n_partials, n_rows, c, weight, bias, eps, momentum,
+                                                               mode, running_mean, running_var, scale, shift, mean, rstd);
     return check_launch("dgnn_norm_finalize");
 }
 

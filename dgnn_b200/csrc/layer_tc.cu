@@ -639,10 +639,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
 }
 
 // ---- weight packing: w[n, k] (row stride ld) -> per K-atom swizzled hi / lo images ---------------
-// Rows are packed in slices of TC_NSLICE (= one launch's N): slice s holds [KA][2][np_s][32] with np_s = its padded rows.
-constexpr int TC_NSLICE = 256;
+// Rows are packed in slices of `slice` rows (= one launch's N): slice s holds [KA][2][np_s][32] with np_s = its padded rows.
+constexpr int TC_NSLICE = 256;      // backward: N = columns of [d_agg | d_self] per launch (2 stages of 96 KB)
+constexpr int TC_FWD_SLICE = 128;   // forward: output columns per launch (the raw-atom ring needs the rest of the shared memory)
 __global__ void pack_b_kernel(const float* __restrict__ w, int n_rows, int ld, int seg_len, int n_segs, int seg_pad,
-                              int np, float* __restrict__ packed) {
+                              int np, int slice, float* __restrict__ packed) {
     const int ka = n_segs * seg_pad / ATOM_K;
     const long long total = (long long)ka * np * ATOM_K;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -655,9 +656,9 @@ __global__ void pack_b_kernel(const float* __restrict__ w, int n_rows, int ld, i
         if (n < n_rows && kk < seg_len) v = w[(size_t)n * ld + seg * seg_len + kk];
         float hi, lo;
         split_tf32(v, hi, lo);
-        const int sl = n / TC_NSLICE, nl = n - sl * TC_NSLICE;
-        const int nps = np - sl * TC_NSLICE < TC_NSLICE ? np - sl * TC_NSLICE : TC_NSLICE;
-        size_t base = (size_t)sl * ka * 2 * TC_NSLICE * ATOM_K + (size_t)a * 2 * nps * ATOM_K;
+        const int sl = n / slice, nl = n - sl * slice;
+        const int nps = np - sl * slice < slice ? np - sl * slice : slice;
+        size_t base = (size_t)sl * ka * 2 * slice * ATOM_K + (size_t)a * 2 * nps * ATOM_K;
         uint32_t off = atom_off(nl, k) / 4;
         packed[base + off] = hi;
         packed[base + (size_t)nps * ATOM_K + off] = lo;
@@ -674,14 +675,17 @@ extern "C" int dgnn_tc_packed_floats(int n_rows, int seg_len, int n_segs) {
     return (n_segs * ceil32(seg_len) / ATOM_K) * 2 * ceil32(n_rows) * ATOM_K;
 }
 
-extern "C" int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len, int n_segs, float* packed,
+extern "C" int dgnn_tc_slice(int backward) { return backward ? TC_NSLICE : TC_FWD_SLICE; }
+
+extern "C" int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len, int n_segs, int slice, float* packed,
                                 void* stream) {
     DGNN_REQUIRE(w && packed, "null pointer");
+    DGNN_REQUIRE(slice == TC_NSLICE || slice == TC_FWD_SLICE, "slice must be dgnn_tc_slice(0) or dgnn_tc_slice(1)");
     int np = ceil32(n_rows), seg_pad = ceil32(seg_len);
     long long total = (long long)(n_segs * seg_pad) * np;
     int grid = (int)((total + 255) / 256);
     if (grid > 1024) grid = 1024;
-    pack_b_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, n_rows, ld, seg_len, n_segs, seg_pad, np, packed);
+    pack_b_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, n_rows, ld, seg_len, n_segs, seg_pad, np, slice, packed);
     return check_launch("dgnn_pack_b_tf32");
 }
 
@@ -714,19 +718,19 @@ extern "C" int dgnn_tc_supported(int f_in, int f_out, int gather) {
     return (f_in % 4 == 0 && f_out % 4 == 0 && f_in > 0 && f_out > 0) ? 1 : 0;
 }
 
-// forward launches, one per slice of <= TC_NSLICE output columns
+// forward launches, one per slice of <= TC_FWD_SLICE output columns
 template <int MODE, int FE>
 static int fwd_slices(TcArgs p, int f_out, bool gather, int raw_ring, cudaStream_t st, const char* what) {
     const float* bias = p.bias; const float* osc = p.out_scale; const float* osh = p.out_shift;
     float* out = p.out; double* stats = p.stats; const float* bp = p.b_packed;
     p.out_ld = f_out; p.stats_ld = f_out;
-    for (int n0 = 0; n0 < f_out; n0 += TC_NSLICE) {
-        const int w = f_out - n0 < TC_NSLICE ? f_out - n0 : TC_NSLICE;
+    for (int n0 = 0; n0 < f_out; n0 += TC_FWD_SLICE) {
+        const int w = f_out - n0 < TC_FWD_SLICE ? f_out - n0 : TC_FWD_SLICE;
         p.f_out = w; p.np = ceil32(w);
         p.bias = bias ? bias + n0 : nullptr;
         p.out_scale = osc ? osc + n0 : nullptr; p.out_shift = osh ? osh + n0 : nullptr;
         p.out = out + n0; p.stats = stats ? stats + n0 : nullptr;
-        p.b_packed = bp + (size_t)(n0 / TC_NSLICE) * p.ka * 2 * TC_NSLICE * ATOM_K;
+        p.b_packed = bp + (size_t)(n0 / TC_FWD_SLICE) * p.ka * 2 * TC_FWD_SLICE * ATOM_K;
         if (n0 > 0) p.agg_save = nullptr;          // the aggregate does not depend on the slice
         size_t smem;
         if (tc_stage_config(p.np, gather, &p.stages, &smem, raw_ring)) return fail(what, "tile does not fit shared memory");

@@ -27,11 +27,13 @@ def use_tensor_cores() -> bool:
     return os.environ.get("DGNN_FMA_ONLY", "0") != "1"
 
 
-def pack_b(w: torch.Tensor, n_rows: int, seg_len: int, n_segs: int) -> torch.Tensor:
-    """``w`` float32[n_rows, n_segs*seg_len] (row-major) -> 128B-swizzled TF32 hi/lo K-atoms."""
+def pack_b(w: torch.Tensor, n_rows: int, seg_len: int, n_segs: int, backward: bool = False) -> torch.Tensor:
+    """``w`` float32[n_rows, n_segs*seg_len] (row-major) -> 128B-swizzled TF32 hi/lo K-atoms, rows grouped in the
+    column slices the forward / backward launches cover."""
     w = w.contiguous()
     out = torch.empty(lib().dgnn_tc_packed_floats(n_rows, seg_len, n_segs), dtype=torch.float32, device=w.device)
-    call("dgnn_pack_b_tf32", ptr(w), n_rows, w.shape[1], seg_len, n_segs, ptr(out), _stream())
+    call("dgnn_pack_b_tf32", ptr(w), n_rows, w.shape[1], seg_len, n_segs, lib().dgnn_tc_slice(1 if backward else 0),
+         ptr(out), _stream())
     return out
 
 
@@ -217,18 +219,46 @@ def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGra
     return out, agg, stats
 
 
+#: SMs left free for the pack + NCCL kernels while a halo exchange overlaps a layer's interior rows
+OVERLAP_RESERVED_SMS = 8
+
+
 def _gather_then_dense(x_in, in_aff, relu_in, g: EllGraph, pk: PackedConv, out_aff, relu_out, want_stats,
-                       out_rows=None):
+                       out_rows=None, comm=None):
     """Tensor-core layer forward as two kernels: aggregation with the edge filter on tcgen05
-    (dgnn_gather_tc_fwd) -> agg, then z = [agg | h] . W^T (dgnn_dense_fwd_tc)."""
+    (dgnn_gather_tc_fwd) -> agg, then z = [agg | h] . W^T (dgnn_dense_fwd_tc).
+
+    With a boundary-first partition (``comm.n_boundary > 0``) the target rows are processed as two ranges: the
+    boundary rows first, then - while their halo exchange runs on the communication stream (``comm.start``) - the
+    interior rows, with a few SMs left free for the exchange.  Returns ``(out, agg, stats, exchange_started)``."""
     dev = x_in.device
     n_tgt = g.n_tgt
-    agg = torch.empty((n_tgt, pk.f_in), dtype=torch.float32, device=dev)
+    f_in, f_out, fe = pk.f_in, pk.f_out, pk.fe
+    agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev)
+    out = torch.empty((out_rows or n_tgt, f_out), dtype=torch.float32, device=dev)
     sc = ptr(in_aff.scale) if in_aff else None
     sh = ptr(in_aff.shift) if in_aff else None
-    call("dgnn_gather_tc_fwd", ptr(x_in), sc, sh, int(relu_in), ptr(g.nbr), ptr(g.ea_in), pk.fe, ptr(pk.w_e),
-         ptr(pk.b_e), n_tgt, pk.f_in, ptr(agg), _stream())
-    return _dense_from_agg(agg, x_in, in_aff, relu_in, n_tgt, pk, out_aff, relu_out, want_stats, out_rows)
+    nb = comm.n_boundary if (comm is not None and out_rows is not None and out_rows > n_tgt) else 0
+    ranges = [(0, nb), (nb, n_tgt)] if 0 < nb < n_tgt else [(0, n_tgt)]
+    grid = lib().dgnn_tc_grid()
+    stats = torch.zeros((len(ranges) * grid, 2, f_out), dtype=torch.float64, device=dev) if want_stats else None
+    started = False
+    for i, (r0, r1) in enumerate(ranges):
+        prev = lib().dgnn_reserve_sms(OVERLAP_RESERVED_SMS) if (i == 1) else None
+        try:
+            call("dgnn_gather_tc_fwd", ptr(x_in), sc, sh, int(relu_in), ptr(g.nbr) + r0 * 16, ptr(g.ea_in) + r0 * 16 * fe, fe,
+                 ptr(pk.w_e), ptr(pk.b_e), r1 - r0, f_in, ptr(agg) + r0 * 4 * f_in, _stream())
+            call("dgnn_dense_fwd_tc", ptr(agg) + r0 * 4 * f_in, ptr(x_in) + r0 * 4 * f_in, sc, sh, int(relu_in), ptr(pk.b_fwd),
+                 ptr(pk.bias), ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None,
+                 int(relu_out), r1 - r0, f_in, f_out, ptr(out) + r0 * 4 * f_out,
+                 ptr(stats) + i * grid * 2 * f_out * 8 if want_stats else None, _stream())
+        finally:
+            if prev is not None:
+                lib().dgnn_reserve_sms(prev)
+        if i == 0 and len(ranges) == 2:
+            comm.start(out)                     # boundary rows are final: pack + all-to-all on the communication stream
+            started = True
+    return out, agg, stats, started
 
 
 def _dense_from_agg(agg, x_in, in_aff, relu_in, n_tgt, pk: PackedConv, out_aff, relu_out, want_stats, out_rows=None):
@@ -330,19 +360,21 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             edge = _edge_mlp_fwd(c.edge_mlp, g, pk.f_in, batch_stats, training)
         if save:
             sv.edge.append(edge)
+        started = False
         if batch_stats:
             if edge is not None:
                 z, agg, stats = _layer_fwd_edge_mlp(h, in_aff, relu_in, g, pk, edge[2], None, False, True, out_rows)
             elif split:
-                z, agg, stats = _gather_then_dense(h, in_aff, relu_in, g, pk, None, False, True, out_rows=out_rows)
+                z, agg, stats, started = _gather_then_dense(h, in_aff, relu_in, g, pk, None, False, True,
+                                                            out_rows=out_rows, comm=comm)
             else:
                 z, agg, stats = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, None,
                                            False, g.n_tgt, pk.f_in, pk.f_out, save, True, b_packed=pk.b_fwd,
                                            out_rows=out_rows)
             stats, n_rows = _global_stats(stats, g.n_tgt, comm)
             aff = batch_affine(c.norm, stats, n_rows, pk.f_out, dev, update_running=training)
-            if comm is not None and l + 1 < L:
-                comm.exchange(z)                       # halo rows carry the owners' pre-norm z; the affine is global
+            if comm is not None and l + 1 < L:         # halo rows carry the owners' pre-norm z; the affine is global
+                comm.finish() if started else comm.exchange(z)
             if save:
                 sv.z.append(z); sv.agg.append(agg); sv.aff.append(aff); sv.packed.append(pk)
             h, in_aff, relu_in = z, aff, True
@@ -351,12 +383,13 @@ def forward(spec: NetSpec, graphs: List[EllGraph], x0: torch.Tensor, training: b
             if edge is not None:
                 h, _, _ = _layer_fwd_edge_mlp(h, in_aff, relu_in, g, pk, edge[2], aff, True, False, out_rows)
             elif split:
-                h, _, _ = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False, out_rows=out_rows)
+                h, _, _, started = _gather_then_dense(h, in_aff, relu_in, g, pk, aff, True, False, out_rows=out_rows,
+                                                      comm=comm)
             else:
                 h, _, _ = _layer_fwd(h, in_aff, relu_in, g, pk.wt_cat, pk.bias, pk.w_e, pk.b_e, pk.fe, aff, True,
                                      g.n_tgt, pk.f_in, pk.f_out, False, False, b_packed=pk.b_fwd, out_rows=out_rows)
             if comm is not None and l + 1 < L:
-                comm.exchange(h)
+                comm.finish() if started else comm.exchange(h)
             in_aff, relu_in = None, False
     n_out = graphs[-1].n_tgt
     f_last = spec.convs[-1].f_out
@@ -450,7 +483,7 @@ def _dense_and_dw(dy, z, coeffs, aff, w_cat, g: Optional[EllGraph], agg, x_in, i
         tc_dense = False                     # the dense backward's shared column sums hold 256 channels
     if tc_dense:
         # operand B of the backward: [W_j | W_i]^T, i.e. rows = columns of d[agg|self], K = f_out
-        b_bwd = pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
+        b_bwd = pack_b(w_cat.t().contiguous(), k_total, f_out, 1, backward=True)
         db_p = torch.empty((lib().dgnn_tc_grid(), f_out), dtype=torch.float64, device=dev)
         call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(aff.mean), ptr(aff.rstd), ptr(b_bwd),
              ptr(g.nbr) if g is not None else None, n_tgt, f_in, f_out, ptr(d_agg), ptr(d_self),

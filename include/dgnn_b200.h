@@ -42,6 +42,10 @@ const char* dgnn_last_error(void);
 int dgnn_device_check(int device);
 /* number of SMs of the current device (grid sizing), <0 on error */
 int dgnn_sm_count(void);
+/* Leave n SMs free in every persistent-kernel grid launched by the calling thread from now on (0 = use all):
+ * lets the halo pack + NCCL kernels of a communication stream run beside a layer kernel.  Returns the
+ * previous value.  dgnn_sm_count / dgnn_tc_grid / dgnn_small_grid follow the reservation. */
+int dgnn_reserve_sms(int n);
 
 /* ---- graph layout (processing/data.py:434-439 re-laid to ELL-4) ------------------------ */
 /* adjacencies int32[4n,2] (row 4i+k = (i, k-th facet neighbour)) -> nbr int32[n,4] and the
@@ -136,20 +140,25 @@ int dgnn_layer_fwd(const float* x_in, const float* in_scale, const float* in_shi
                    int64_t n_tgt, int f_in, int f_out,
                    float* out, float* agg_save, double* stats, void* stream);
 
-/* ---- tensor-core (tcgen05 / TMEM, 3xTF32) variants for widths that fit one UMMA tile --------
+/* ---- tensor-core (tcgen05 / TMEM, 3xTF32) variants ---------------------------------------------
+ * Any width that is a multiple of 4 (configs/modelnet.yaml:56 ships [128,256,512,1024]): a launch covers
+ * one slice of output columns (dgnn_tc_slice(0) = 128 forward, dgnn_tc_slice(1) = 256 backward), wider
+ * layers are run slice by slice inside the call; the contraction length is unbounded.
  * Same semantics as dgnn_layer_fwd / dgnn_dense_bwd; the dense operand is pre-packed by
  * dgnn_pack_b_tf32 into 128B-swizzled K-atoms split into TF32 hi / lo parts:
  *   forward : w = [W_j | W_i] (float32[f_out, 2 f_in] or [f_out, f_in] for a dense layer),
  *             n_rows = f_out, ld = row stride, seg_len = f_in, n_segs = 2 (1 for dense)
  *   backward: w = [W_j | W_i]^T (float32[k_total, f_out]), n_rows = k_total, ld = f_out,
  *             seg_len = f_out, n_segs = 1
- * packed holds dgnn_tc_packed_floats(n_rows, seg_len, n_segs) floats.  Partial-sum workspaces
- * (stats, db_partials) have dgnn_tc_grid() rows. */
+ * packed holds dgnn_tc_packed_floats(n_rows, seg_len, n_segs) floats, rows grouped in slices of
+ * `slice` = dgnn_tc_slice(0 forward / 1 backward).  Partial-sum workspaces (stats, db_partials) have
+ * dgnn_tc_grid() rows. */
 int dgnn_tc_supported(int f_in, int f_out, int gather);
 int dgnn_tc_grid(void);
+int dgnn_tc_slice(int backward);
 int dgnn_tc_packed_floats(int n_rows, int seg_len, int n_segs);
-int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len, int n_segs, float* packed,
-                     void* stream);
+int dgnn_pack_b_tf32(const float* w, int n_rows, int ld, int seg_len, int n_segs, int slice,
+                     float* packed, void* stream);
 int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
                       const int32_t* nbr, const float* ea, int fe,
                       const float* w_e, const float* b_e,

@@ -34,3 +34,18 @@ def test_partitioned_training_step_matches_single_gpu():
 def test_partitioned_updated_training_step_matches_single_gpu():
     out = _torchrun("check_partition_upd.py", 29523, 6000)
     assert "PARTITIONED_UPDATED_TRAINING world=2" in out
+
+
+def test_sharded_scene_build_matches_single_gpu():
+    """Sharded build (no rank holds the whole graph), boundary-first order, overlapped exchange: inference and one
+    training step on a Delaunay scene and on the benchmark's lattice scene."""
+    out = _torchrun("check_partition_scene.py", 29524, 8000)
+    assert "PARTITIONED_SCENE world=2 ok" in out
+
+
+def test_sharded_scene_single_rank():
+    """The same sharded code path with one shard (runs on a 1-GPU box too)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "check_partition_scene.py"), "3000"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "PARTITIONED_SCENE world=1 ok" in r.stdout

@@ -103,7 +103,11 @@ def test_decoder0_hidden_features_and_gradients(golden):
     assert ok, err
     (y.square() * w.to(DEV)).sum().backward()
     refp = dict(ref.named_parameters())
+    gmax = max(float(v.grad.abs().max()) for v in refp.values())
     for k, p in net.named_parameters():
+        if k.endswith("lin_j.bias"):     # a bias in front of a BatchNorm: analytically zero, both sides are rounding noise
+            assert float(p.grad.abs().max()) <= 1e-4 * gmax and float(refp[k].grad.abs().max()) <= 1e-4 * gmax, k
+            continue
         e, tol = grad_close(p.grad, refp[k].grad)
         assert e <= tol, (k, e, tol)
 

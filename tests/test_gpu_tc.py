@@ -90,7 +90,7 @@ def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather):
         nbr = torch.randint(0, n, (n, 4), device=DEV, dtype=torch.int32)
         nbr[::5, 3] = -1
         nbr[::7, 1] = -1
-    bp = engine.pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
+    bp = engine.pack_b(w_cat.t().contiguous(), k_total, f_out, 1, backward=True)
     d_self = torch.empty(n, f_in, device=DEV)
     d_agg = torch.empty(n, f_in, device=DEV) if gather else None
     db_p = torch.empty(lib().dgnn_tc_grid(), f_out, dtype=torch.float64, device=DEV)

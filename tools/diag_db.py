@@ -12,7 +12,7 @@ for (n, f_in, f_out) in ((1000, 28, 64), (2498, 128, 128), (2498, 128, 64)):
     k_total = 2 * f_in
     w_cat = torch.randn(f_out, k_total, device=DEV) * 0.2
     nbr = torch.randint(0, n, (n, 4), device=DEV, dtype=torch.int32)
-    bp = engine.pack_b(w_cat.t().contiguous(), k_total, f_out, 1)
+    bp = engine.pack_b(w_cat.t().contiguous(), k_total, f_out, 1, backward=True)
     d_self = torch.empty(n, f_in, device=DEV); d_agg = torch.empty(n, f_in, device=DEV)
     db_p = torch.empty(lib().dgnn_tc_grid(), f_out, dtype=torch.float64, device=DEV)
     st = torch.cuda.current_stream().cuda_stream

@@ -23,7 +23,7 @@ w_cat = torch.randn(f, 2 * f, device=DEV) * 0.05; bias = torch.randn(f, device=D
 st = torch.cuda.current_stream().cuda_stream
 tcg = lib().dgnn_tc_grid()
 b_fwd = engine.pack_b(w_cat, f, f, 2)
-b_bwd = engine.pack_b(w_cat.t().contiguous(), 2 * f, f, 1)
+b_bwd = engine.pack_b(w_cat.t().contiguous(), 2 * f, f, 1, backward=True)
 stats = torch.empty((tcg, 2, f), dtype=torch.float64, device=DEV)
 db_p = torch.empty((tcg, f), dtype=torch.float64, device=DEV)
 dw_p = torch.empty((tcg, f, 2 * f), device=DEV)
