@@ -316,6 +316,11 @@ SCENE_DIMS_STRONG = (256, 256, 512)                                             
 SCENE_DIMS_PARITY = (32, 32, 32)                                                                    # 65 536 cells
 
 
+def _stage(msg):
+    if os.environ.get("DGNN_BENCH_DEBUG"):
+        print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def _maxr(v, dev, world):
     import torch.distributed as dist
     t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
@@ -433,7 +438,9 @@ def run_partitioned(args, rank, world, local_rank):
     opt = rm.Adam(net.parameters(), lr=0.005)
 
     # parity first (small scene): partitioned logits against the single-GPU path
+    _stage("parity")
     parity = partition_parity(net, rank, world, dev)
+    _stage("parity done %r" % (parity,))
 
     # ---- value: training step on the weak-scaled scene ------------------------------------------------------
     dims = SCENE_DIMS_WEAK.get(world) or SCENE_DIMS_WEAK[8]
@@ -455,6 +462,7 @@ def run_partitioned(args, rank, world, local_rank):
         opt.step()
         return loss
 
+    _stage("scene ready: own %d halo %d boundary %d" % (maps.n_own, maps.n_halo, maps.n_boundary))
     with ClockSampler(local_rank) as clocks:
         for _ in range(args.warmup):
             step()
@@ -492,9 +500,11 @@ def run_partitioned(args, rank, world, local_rank):
         pt._sup = (ys[o], ws[o])
         return step().item()
 
+    _stage("value %.3e" % value)
     e2e_steps = max(3, args.steps // 4)
     ms_e2e = _timed_region(e2e_step, e2e_steps, 1, dev, world)
     e2e_value = n_total * e2e_steps / (ms_e2e * 1e-3)
+    _stage("e2e %.3e" % e2e_value)
 
     # ---- per-kernel times of one step on this rank -> roofline of the dominant kernel
     peak, peak_src = peak_hbm()
@@ -507,7 +517,9 @@ def run_partitioned(args, rank, world, local_rank):
     roofline, table, kernel_ms = prof.summary(2, peak, peak_src)
 
     # ---- partitioned training against the single-GPU step on the small scene (loss + gradients)
+    _stage("profile done")
     train_par = partition_train_parity(clf, rank, world, dev)
+    _stage("train parity %r" % (train_par,))
 
     # free the training scene before the big inference scene
     del pt, g, x0, comm, staged
@@ -520,6 +532,7 @@ def run_partitioned(args, rank, world, local_rank):
     infer_noov = scene_inference(net, SCENE_DIMS_STRONG, rank, world, dev, iters=3, overlap=False)
     infer["ms_without_overlap"] = infer_noov["ms"]
     gc.collect(); torch.cuda.empty_cache()
+    _stage("scene inference %r" % (infer,))
 
     # ---- the round-1 data-parallel object-batch number, as an extra key
     dp = dp_objects(args, rank, world, dev, clf)
@@ -551,7 +564,9 @@ def run_partitioned(args, rank, world, local_rank):
                "partition_vs_single_max_abs": parity,
                "partition_train_vs_single": train_par,
                "dp": dp, "kernels": table, "cpu_baseline": None}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    _stage("done")
+    dist.barrier()
     dist.destroy_process_group()
 
 

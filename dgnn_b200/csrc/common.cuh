@@ -38,6 +38,19 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 
+// Loads that stay where they are written: ptxas is free to sink an ordinary read-only load down to its first use (it does,
+// under register pressure), which turns a software prefetch into a blocking load.  `asm volatile` keeps the issue point.
+__device__ __forceinline__ float4 ldg4_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ldg4i_pinned(const int32_t* p) {
+    int4 v;
+    asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 // 256-bit read-only load (LDG.E.256, sm_100+); p must be 32-byte aligned
 __device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

@@ -117,16 +117,19 @@ __device__ __forceinline__ void act8(float4& a, float4& b, const float4& sa, con
 //             count issues the 9 MMAs of PHI item n+2 (elect-by-arrival, see the file header).
 //   PHI ring  4 TMEM buffers of FP columns (item n in buffer n & 3), ready two items before they are consumed;
 //             no "free" barrier: the arrival count of item n already orders the overwrite of item n-4's buffer.
-template <int CPT, int MODE>  // CPT: features per thread = fp / 4
-__global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcArgs p) {
+// NW compute warps: 16 (4 per scheduler, 128 registers) or 32 (8 per scheduler, 64 registers; twice the warps to hide the
+// shared-memory / TMEM / mbarrier latencies with, half the strip per thread)
+template <int CPT, int MODE, int NW>  // CPT: features per thread = fp / (NW / 4)
+__global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArgs p) {
+    constexpr int G_NCW = NW, G_THREADS = NW * 32;      // shadow the file-level constants (those are the dW_e kernel's)
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t ea_empty[G_EA_STAGES];
     __shared__ uint64_t phi_full[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ int ea_count[G_EA_STAGES];                // warps that have stored their share of the stage
+    __shared__ uint64_t ea_count[G_EA_STAGES];           // counts the warps that have stored their share of the stage
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int FP = CPT * 4;
+    constexpr int FP = CPT * (NW / 4);
     constexpr int CH = CPT / 4;                          // 16-byte chunks per strip row (2, 4 or 8)
     constexpr int RPI = 32 / CH;                         // rows copied by one cp.async warp instruction
     constexpr int PITCH = CPT * 4;                       // bytes per strip row
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
     float* aff_s = reinterpret_cast<float*>(x_base + (size_t)2 * G_NCW * WSTAGE);   // MODE 0: scale[FP] | shift[FP]
 
     if (tid == 0) {
-        for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); ea_count[s] = 0; }
+        for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); mbar_init(&ea_count[s], G_NCW); }
         for (int s = 0; s < 4; ++s) mbar_init(&phi_full[s], 1);
         fence_barrier_init();
     }
@@ -202,16 +205,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             int4 nb = make_int4(-1, -1, -1, -1);
             if (tc < n_my) {
                 const int64_t t = tile_of(tc) * G_M + row;
-                if (t < p.n_rows) nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+                if (t < p.n_rows) nb = ldg4i_pinned(p.nbr + (size_t)t * 4);
             }
             return nb;
         };
         // ---- EA staging, one PHI item at a time
-        float4 ev[2];
-        int e_r[2], e_c4[2];                           // this thread's (row, first feature) of the two float4 it stages
-        uint32_t e_off[2];
+        constexpr int EU = NW >= 32 ? 1 : 2;           // float4 of an EA item per thread (128 rows x <= 7 float4)
+        float4 ev[EU];
+        int e_r[EU], e_c4[EU];                         // this thread's (row, first feature) of the float4 it stages
+        uint32_t e_off[EU];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < EU; ++u) {
             const int idx = tid + u * G_NCW * 32;
             e_r[u] = idx < G_M * fe4 ? idx / fe4 : -1;
             e_c4[u] = idx < G_M * fe4 ? (idx - e_r[u] * fe4) * 4 : 0;
@@ -220,10 +224,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
         auto ea_load = [&](uint32_t n) {               // global loads of PHI item n into registers
             const int64_t r0 = tile_of(n >> 2) * G_M;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < EU; ++u) {
                 ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (n < n_phi && e_r[u] >= 0 && r0 + e_r[u] < p.n_rows)
-                    ev[u] = ldg4(p.ea + ((size_t)(r0 + e_r[u]) * 4 + (n & 3u)) * p.fe + e_c4[u]);
+                    ev[u] = ldg4_pinned(p.ea + ((size_t)(r0 + e_r[u]) * 4 + (n & 3u)) * p.fe + e_c4[u]);
             }
         };
         auto ea_store = [&](uint32_t n) {              // registers -> (hi | lo) operand stage, then signal the MMA warp
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             uint8_t* e_lo = e_hi + G_ATOM;
             mbar_wait(&ea_empty[s], (su & 1) ^ 1);
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < EU; ++u) {
                 if (e_r[u] >= 0) {
                     float4 h, l;
                     split_tf32(ev[u].x, h.x, l.x); split_tf32(ev[u].y, h.y, l.y);
@@ -245,11 +249,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                const int arrived = atomicAdd(&ea_count[s], 1);
-                if (arrived == G_NCW - 1) {            // last warp of the stage: issue PHI item n = EA . WE^T
-                    ea_count[s] = 0;                   // next use of the stage is ordered behind ea_empty
-                    __threadfence_block();
+                if (mbar_arrive_pending(&ea_count[s]) == 1u) {   // last warp of the stage: issue PHI item n = EA . WE^T
+                    mbar_wait(&ea_count[s], su & 1);   // completed by this very arrival: acquires the other warps' stores
                     // PHI buffer n & 3 was last read for item n - 4.  Every warp stores item n at its position n - 2, i.e.
                     // after it has finished consuming item n - 3 and everything before: once the count is complete no
                     // warp can still be reading the buffer, so no further barrier is needed before overwriting it.
@@ -320,18 +321,31 @@ __global__ void __launch_bounds__(G_THREADS, 1) gather_tc_kernel(const GatherTcA
             for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
 #pragma unroll
             for (int k = 0; k < IPT; ++k, ++xi) {
-                // next item's copy goes in flight (the other stage was released by the __syncwarp below)
-                if (k + 1 < IPT) x_issue(tc, k + 1, nbv, (xi + 1) & 1);
-                else x_issue(tc + 1, 0, nbn, (xi + 1) & 1);
+                // next item's copy goes in flight (the other stage was released by the __syncwarp at the end of the last item)
+                auto issue_next = [&]() {
+                    if (k + 1 < IPT) x_issue(tc, k + 1, nbv, (xi + 1) & 1);
+                    else x_issue(tc + 1, 0, nbn, (xi + 1) & 1);
+                };
+#ifdef DGNN_XISSUE_LATE      // variant: copy issued after the operand stores' fence.proxy.async (measured: no gain, MODE 1 slower)
+                cp_async_wait<0>();
+#else
+                issue_next();
                 cp_async_wait<1>();
+#endif
                 __syncwarp();
                 const uint8_t* xs = xw + (size_t)(xi & 1) * G_NCW * WSTAGE + lane * PITCH;
+#ifdef DGNN_XISSUE_LATE
+                if (k >= 4) issue_next();
+#endif
                 if (k < 4) {
                     const uint32_t b = pn & 3u, bu = pn >> 2;
                     mbar_wait(&phi_full[b], bu & 1);
                     tc_fence_after_sync();
                     // MMA of item pn is done => EA stage (pn + 2) % 2 is free: store item pn + 2, fetch item pn + 3
                     ea_store(pn + 2);
+#ifdef DGNN_XISSUE_LATE
+                    issue_next();
+#endif
                     ea_load(pn + 3);
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)FP + (uint32_t)c0;
                     const bool valid = nbv[k] >= 0;
@@ -486,13 +500,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t p_empty[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ int p_count[4];                           // warps of the quarter that have stored their rows of the stage
+    __shared__ uint64_t p_count[4];                      // counts the warps of the quarter that have stored their rows of the stage
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int CH = CPT / 4, RPI = 32 / CH, PITCH = CPT * 4, WSTAGE = 32 * PITCH;
     uint8_t* x_base = smem + (size_t)4 * G_P_BYTES;      // [2 stages][G_NCW warps][32 rows x PITCH]
     if (tid == 0) {
-        for (int qq = 0; qq < 4; ++qq) { mbar_init(&p_empty[qq], 1); p_count[qq] = 0; }
+        for (int qq = 0; qq < 4; ++qq) { mbar_init(&p_empty[qq], 1); mbar_init(&p_count[qq], 4); }
         fence_barrier_init();
     }
     for (int i = tid; i < 4 * G_P_BYTES / 16; i += G_THREADS) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
             int4 nb = make_int4(-1, -1, -1, -1);
             if (tc < n_my) {
                 const int64_t t = tile_of(tc) * G_M + row;
-                if (t < p.n_rows) nb = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+                if (t < p.n_rows) nb = ldg4i_pinned(p.nbr + (size_t)t * 4);
             }
             return nb;
         };
@@ -573,7 +587,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int e0 = grp * 8 + h2 * 4;
                     ev[h2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (e0 < p.fe && tv && nbv[k] >= 0) ev[h2] = ldg4(p.ea + ((size_t)t * 4 + k) * p.fe + e0);
+                    if (e0 < p.fe && tv && nbv[k] >= 0) ev[h2] = ldg4_pinned(p.ea + ((size_t)t * 4 + k) * p.fe + e0);
                 }
             };
 #pragma unroll
@@ -643,11 +657,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            __threadfence_block();
-                            const int arrived = atomicAdd(&p_count[q], 1);
-                            if (arrived == 3) {            // last warp of the quarter: accumulate P^T . EA of this round
-                                p_count[q] = 0;
-                                __threadfence_block();
+                            if (mbar_arrive_pending(&p_count[q]) == 1u) {   // last warp of the quarter: accumulate P^T . EA
+                                mbar_wait(&p_count[q], it & 1);  // completed by this very arrival: acquires the other warps' stores
                                 tc_fence_after_sync();
                                 // every quarter accumulates into its own TMEM columns, its rounds in order: the sum over
                                 // cells is evaluated in a fixed order whatever the timing of the warps
@@ -723,15 +734,19 @@ template <int MODE>
 static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
     size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + (size_t)2 * G_NCW * 32 * p.fp + (size_t)8 * p.fp + 1024;
-#define LAUNCH_G(CPT)                                                                                          \
+#define LAUNCH_G(CPT, NW)                                                                                      \
     do {                                                                                                       \
-        if (int rc_ = ensure_dyn_smem((const void*)gather_tc_kernel<CPT, MODE>, 226 * 1024, what)) return rc_;    \
-        gather_tc_kernel<CPT, MODE><<<sm_count(), G_THREADS, smem, st>>>(p);                                   \
+        if (int rc_ = ensure_dyn_smem((const void*)gather_tc_kernel<CPT, MODE, NW>, 226 * 1024, what)) return rc_; \
+        gather_tc_kernel<CPT, MODE, NW><<<sm_count(), NW * 32, smem, st>>>(p);                                 \
     } while (0)
     switch (cpt) {
-        case 8: LAUNCH_G(8); break;
-        case 16: LAUNCH_G(16); break;
-        case 32: LAUNCH_G(32); break;
+        case 8: LAUNCH_G(8, 16); break;
+        case 16: LAUNCH_G(16, 16); break;
+#ifdef DGNN_GATHER_32W     // variant: 32 warps x 16 features per thread (64 registers).  Measured on B200, 128 -> 128 layer:
+        case 32: LAUNCH_G(16, 32); break;              // forward 12.1 vs 10.5 us / tile, backward 13.8 vs 12.1: the kernel is not
+#else                      // short of warps to hide latency with, it is short of issue slots (index arithmetic, barriers)
+        case 32: LAUNCH_G(32, 16); break;
+#endif
         default: return fail(what, "unsupported feature width");
     }
 #undef LAUNCH_G

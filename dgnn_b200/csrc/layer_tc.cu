@@ -565,8 +565,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                 uint8_t* a_hi = smem + (size_t)s * stage_bytes;
                 uint8_t* a_lo = a_hi + A_ATOM_BYTES;
                 if (MODE == MODE_FWD_DENSE) {
+#ifdef DGNN_RAW_LATE
+                    cp_async_wait<RAW_DEPTH - 2>();      // the oldest of the RAW_DEPTH - 1 groups in flight has landed
+#else
                     issue_next();
                     cp_async_wait<RAW_DEPTH - 1>();
+#endif
                     read_raw_fwd(raw_base + (st_i % RAW_DEPTH) * (uint32_t)A_ATOM_BYTES, warp, lane, cur);
                     ++st_i;
                 }
@@ -587,6 +591,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_full[s]);
+#ifdef DGNN_RAW_LATE     // variant: next raw atom issued after the fence.proxy.async (= MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC); measured: no gain
+                if (MODE == MODE_FWD_DENSE) issue_next();
+#endif
                 if (++s == (uint32_t)p.stages) { s = 0; ++use; }
             }
             if (prev_tile0 >= 0) {

@@ -96,6 +96,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive and report how many arrivals the phase still needed BEFORE this one (1 => this arrival completed the phase).
+// mbarrier.arrive has release semantics at CTA scope: no __threadfence_block() (MEMBAR, which also waits for the
+// thread's in-flight cp.async copies) is needed between a warp's operand stores and the count.
+__device__ __forceinline__ uint32_t mbar_arrive_pending(uint64_t* bar) {
+    uint64_t state;
+    uint32_t pending;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+    return pending;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
