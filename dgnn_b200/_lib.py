@@ -40,6 +40,8 @@ SIGNATURES = {
     "dgnn_sampler_assign": [P, L, P, P, L, P, P, P, P, P],
     "dgnn_column_moments": [P, L, I, I, I, P, P, I, P],
     "dgnn_column_affine": [P, L, I, I, I, P, P, I, P, P],
+    "dgnn_column_moments_f64": [P, L, I, I, I, P, P, I, P],
+    "dgnn_column_standardize_f64": [P, L, I, I, I, P, P, I, I, P, P],
     "dgnn_edge_relayout": [P, P, P, P, L, I, P, P, P],
     "dgnn_edge_relayout_idx": [P, P, P, P, P, L, I, P, P, P],
     "dgnn_layer_grid": [I, I],
@@ -85,6 +87,14 @@ SIGNATURES = {
     "dgnn_edge_filter_bwd": [P, P, P, I, P, P, P, P, P, I, L, L, I, P, P],
     "dgnn_adam_step": [P, P, P, P, L, F, F, F, F, I, P],
     "dgnn_adam_multi": [P, I, L, F, F, F, F, I, P],
+    "dgnn_gc_terminals": [P, L, F, P, P, P, P, P],
+    "dgnn_gc_push_relabel": [L, P, P, P, P, P, P, I, I, P],
+    "dgnn_gc_bfs_init": [L, P, P, I, P],
+    "dgnn_gc_bfs_step": [L, P, P, P, P, I, I, P, P],
+    "dgnn_gc_active": [L, P, P, I, P, P],
+    "dgnn_gc_labels": [L, P, I, P, P],
+    "dgnn_gc_energy_grid": [],
+    "dgnn_gc_energy": [L, P, F, P, I, P, P, P],
     "dgnn_argmax_labels": [P, L, I, P, P],
     "dgnn_scores": [P, L, I, P, P, P],
     "dgnn_interface_facets": [P, L, P, L, P, P],

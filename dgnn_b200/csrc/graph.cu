@@ -288,7 +288,8 @@ extern "C" int dgnn_edge_relayout_idx(const float* ea, const int64_t* e_id, cons
 // (m = NULL: zeros).  One thread per row chunk, double accumulation, per-block partials (deterministic).
 namespace dgnn {
 constexpr int STD_MAXC = 64;
-__global__ void __launch_bounds__(256) column_moments_kernel(const float* __restrict__ x, long long n, int ld, int col0,
+template <typename T>
+__global__ void __launch_bounds__(256) column_moments_kernel(const T* __restrict__ x, long long n, int ld, int col0,
                                                              int c, const double* __restrict__ m,
                                                              double* __restrict__ partials) {
     __shared__ double red[2][256];
@@ -312,15 +313,19 @@ __global__ void __launch_bounds__(256) column_moments_kernel(const float* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) column_affine_kernel(const float* __restrict__ x, long long n, int ld, int col0,
+// out = (x - shift) * k (DIVIDE = false) or (x - shift) / k (DIVIDE = true, sklearn's `X -= mean; X /= scale`), evaluated
+// in float64 and rounded to float32 once (processing/data.py:444-519: standardise in float64, then torch.float)
+template <typename T, bool DIVIDE>
+__global__ void __launch_bounds__(256) column_affine_kernel(const T* __restrict__ x, long long n, int ld, int col0,
                                                             int c, const double* __restrict__ shift,
-                                                            const double* __restrict__ inv_scale, int ld_out,
+                                                            const double* __restrict__ k, int ld_out, int col0_out,
                                                             float* __restrict__ out) {
     const long long total = n * c;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / c;
         const int j = (int)(i % c);
-        out[r * ld_out + col0 + j] = (float)(((double)x[r * ld + col0 + j] - shift[j]) * inv_scale[j]);
+        const double d = (double)x[r * ld + col0 + j] - shift[j];
+        out[r * ld_out + col0_out + j] = (float)(DIVIDE ? d / k[j] : d * k[j]);
     }
 }
 }  // namespace dgnn
@@ -330,8 +335,27 @@ extern "C" int dgnn_column_moments(const float* x, int64_t n, int ld, int col0, 
     DGNN_REQUIRE(x && partials, "null pointer");
     DGNN_REQUIRE(c > 0 && c <= dgnn::STD_MAXC && col0 >= 0 && col0 + c <= ld, "column range");
     DGNN_REQUIRE(n_blocks > 0, "n_blocks");
-    dgnn::column_moments_kernel<<<n_blocks, 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, center, partials);
+    dgnn::column_moments_kernel<float><<<n_blocks, 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, center, partials);
     return check_launch("dgnn_column_moments");
+}
+
+extern "C" int dgnn_column_moments_f64(const double* x, int64_t n, int ld, int col0, int c, const double* center,
+                                       double* partials, int n_blocks, void* stream) {
+    DGNN_REQUIRE(x && partials, "null pointer");
+    DGNN_REQUIRE(c > 0 && c <= dgnn::STD_MAXC && col0 >= 0 && col0 + c <= ld, "column range");
+    DGNN_REQUIRE(n_blocks > 0, "n_blocks");
+    dgnn::column_moments_kernel<double><<<n_blocks, 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, center, partials);
+    return check_launch("dgnn_column_moments_f64");
+}
+
+extern "C" int dgnn_column_standardize_f64(const double* x, int64_t n, int ld, int col0, int c, const double* mean,
+                                           const double* scale, int ld_out, int col0_out, float* out, void* stream) {
+    DGNN_REQUIRE(x && mean && scale && out, "null pointer");
+    DGNN_REQUIRE(c > 0 && col0 >= 0 && col0 + c <= ld && col0_out >= 0 && col0_out + c <= ld_out, "column range");
+    if (n <= 0) return 0;
+    dgnn::column_affine_kernel<double, true><<<ggrid(n * c), 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, mean, scale,
+                                                                                         ld_out, col0_out, out);
+    return check_launch("dgnn_column_standardize_f64");
 }
 
 extern "C" int dgnn_column_affine(const float* x, int64_t n, int ld, int col0, int c, const double* shift,
@@ -339,6 +363,7 @@ extern "C" int dgnn_column_affine(const float* x, int64_t n, int ld, int col0, i
     DGNN_REQUIRE(x && shift && inv_scale && out, "null pointer");
     DGNN_REQUIRE(c > 0 && col0 >= 0 && col0 + c <= ld && col0 + c <= ld_out, "column range");
     if (n <= 0) return 0;
-    dgnn::column_affine_kernel<<<ggrid(n * c), 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, shift, inv_scale, ld_out, out);
+    dgnn::column_affine_kernel<float, false><<<ggrid(n * c), 256, 0, as_stream(stream)>>>(x, n, ld, col0, c, shift, inv_scale,
+                                                                                         ld_out, col0, out);
     return check_launch("dgnn_column_affine");
 }

@@ -118,6 +118,14 @@ int dgnn_column_moments(const float* x, int64_t n, int ld, int col0, int c, cons
                         double* partials, int n_blocks, void* stream);
 int dgnn_column_affine(const float* x, int64_t n, int ld, int col0, int c, const double* shift,
                        const double* inv_scale, int ld_out, float* out, void* stream);
+/* The reference keeps the features in float64 up to the final `torch.tensor(.., dtype=torch.float)`
+ * (processing/data.py:444-519).  Same two-pass moments on a float64 matrix, and the transform as sklearn
+ * writes it, `X -= mean_; X /= scale_`, evaluated in float64 and rounded to float32 once:
+ * out[r, col0_out+j] = float((x[r, col0+j] - mean[j]) / scale[j]). */
+int dgnn_column_moments_f64(const double* x, int64_t n, int ld, int col0, int c, const double* center,
+                            double* partials, int n_blocks, void* stream);
+int dgnn_column_standardize_f64(const double* x, int64_t n, int ld, int col0, int c, const double* mean,
+                                const double* scale, int ld_out, int col0_out, float* out, void* stream);
 
 /* ---- one message-passing layer, forward (Static:66-96 + norm/ReLU of the producer) ------
  * For target row t < n_tgt (targets are the first n_tgt source rows):
@@ -351,6 +359,33 @@ int dgnn_interface_facets(const uint8_t* labels_finite, int64_t n_finite, const 
 /* ---- halo exchange staging (multi-GPU) ---------------------------------------- */
 /* buf[r,:] = x[idx[r],:] / x[base + r,:] = buf[r,:] are dgnn_gather_rows / plain copies; the
  * NCCL send/recv itself stays with the host (torch.distributed) on the same stream. */
+
+/* ---- graph-cut regularisation of the labels (processing/generate_mesh.py:15-58) --------------------------------
+ * Two labels, E(l) = sum_c D(c,l_c) + w * #{finite-finite facets with different labels}, D(c,0) =
+ * round(z[c,1]*unary_weight), D(c,1) = round(z[c,0]*unary_weight) (float32 product, round-half-even, as
+ * `(prediction*unary_weight).round()` after the column swap of :25).  gco's alpha-expansion ends in a global minimum
+ * of this submodular energy = one s-t minimum cut, computed by a lock-free push-relabel over the facet table
+ * nbr int32[n,4] (-1 = none) / rslot uint8[n,4] (nbr[nbr[c,k], rslot[c,k]] == c):
+ *   dgnn_gc_terminals    excess / sink_cap int64[n] from the logits (optionally the two cost columns d0 / d1)
+ *   dgnn_gc_bfs_init / dgnn_gc_bfs_step   global relabelling: height = residual distance to the sink, hmax = none;
+ *                        step `level` labels the cells one arc further, *changed (device int32) is set if any
+ *   dgnn_gc_push_relabel `iters` push / relabel attempts per cell; cap int32[n,4] residual facet capacities (init w)
+ *   dgnn_gc_active       adds the number of cells with excess that can still reach the sink to *count
+ *   dgnn_gc_labels       labels uint8[n]: 1 (outside) if the cell reaches the sink, else 0 (inside)
+ *   dgnn_gc_energy       per-block (data, 2 x smoothness) partial sums int64[dgnn_gc_energy_grid(), 2] */
+int dgnn_gc_terminals(const float* logits, int64_t n, float unary_weight, int64_t* excess, int64_t* sink_cap,
+                      int64_t* d0, int64_t* d1, void* stream);
+int dgnn_gc_push_relabel(int64_t n, const int32_t* nbr, const uint8_t* rslot, int32_t* cap, int64_t* excess,
+                         int64_t* sink_cap, int32_t* height, int hmax, int iters, void* stream);
+int dgnn_gc_bfs_init(int64_t n, const int64_t* sink_cap, int32_t* height, int hmax, void* stream);
+int dgnn_gc_bfs_step(int64_t n, const int32_t* nbr, const uint8_t* rslot, const int32_t* cap, int32_t* height,
+                     int level, int hmax, int32_t* changed, void* stream);
+int dgnn_gc_active(int64_t n, const int64_t* excess, const int32_t* height, int hmax, uint64_t* count,
+                   void* stream);
+int dgnn_gc_labels(int64_t n, const int32_t* height, int hmax, uint8_t* labels, void* stream);
+int dgnn_gc_energy_grid(void);
+int dgnn_gc_energy(int64_t n, const float* logits, float unary_weight, const int32_t* nbr, int binary_weight,
+                   const uint8_t* labels, int64_t* partials, void* stream);
 
 #ifdef __cplusplus
 }

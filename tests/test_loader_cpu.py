@@ -35,3 +35,45 @@ def test_edge_index_from_adjacencies_convention():
     assert ei.dtype == torch.int64 and tuple(ei.shape) == (2, 4 * n)
     assert torch.equal(ei[0], torch.arange(n).repeat_interleave(4))          # row 4i+k is owned by cell i
     assert np.array_equal(ei[1].numpy(), adj[:, 1])
+
+
+def _loader_cases():
+    import importlib.util, os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_loader_golden", os.path.join(here, "make_loader_golden.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m, dict(np.load(os.path.join(here, "loader_golden.npz")))
+
+
+def test_oracle_loader_matches_the_reference_loader_golden():
+    """oracle.loader.load_graph against the outputs of the reference's unmodified processing/data.py (column order,
+    dropped statistics, regularisation column, the three scalers)."""
+    import os
+    from oracle.loader import load_graph
+    m, gold = _loader_cases()
+    base = os.path.join(m.SCENE, "7")
+    for tag, c in m.CONFIGS.items():
+        r = load_graph(base, m.make_clf(c))
+        assert r["node_names"] == list(gold[tag + "_node_names"]), tag
+        np.testing.assert_allclose(r["features"], gold[tag + "_features"], rtol=3e-7, atol=1e-9, err_msg=tag)
+        assert np.array_equal(r["edge_lists"], gold[tag + "_edge_lists"])
+        assert np.array_equal(r["gt"], gold[tag + "_gt"]) and np.array_equal(r["infinite"], gold[tag + "_infinite"])
+        assert abs(r["mean_edge"] - float(gold[tag + "_mean_edge"])) < 1e-15
+        if c["edge_convs"]:
+            assert r["edge_names"] == list(gold[tag + "_edge_names"]), tag
+            np.testing.assert_allclose(r["edge_features"], gold[tag + "_edge_features"], rtol=3e-7, atol=1e-9, err_msg=tag)
+
+
+def test_loader_reproduces_the_reference_errors_on_cpu_side_logic():
+    """Dropping a statistic from the facet / edge features calls .drop on an NpzFile in the reference (AttributeError)."""
+    import os
+    import pytest
+    from dgnn_b200.data import _assemble, dataLoader
+    m, _ = _loader_cases()
+    base = os.path.join(m.SCENE, "7")
+    with pytest.raises(AttributeError):
+        _assemble(base, ["shape", "facet", "min", "max", "sum"], dataLoader.NODE_SPEC, "node")
+    with pytest.raises(AttributeError):
+        _assemble(base, ["shape", "vertex", "count", "min", "max"], dataLoader.EDGE_SPEC, "edge")
+    names, cols, extra = _assemble(base, ["shape", "vertex", "facet", "count", "min", "max", "sum"], dataLoader.NODE_SPEC, "node")
+    assert len(names) == 28 and names[:4] == ["radius", "vol", "longest_edge", "shortest_edge"] and "mean_edge" in extra
