@@ -75,4 +75,4 @@ def test_labels_cut_and_interface_chain():
     clf = to_attr(dict(graph_cut=dict(unary_weight=100.0, binary_weight=50, binary_type=None), temp=dict(device=DEV)))
     lab = graph_cut(lab0.cpu().numpy(), z[~inf_t.to(DEV)].cpu(), gc_edges, clf)
     ids = interface_facet_ids(torch.from_numpy(lab.astype(np.uint8)).to(DEV), nfacets).cpu().numpy()
-    assert np.array_equal(ids, np.nonzero(og.interface_facets(lab, nfacets))[0])
+    assert np.array_equal(ids, og.interface_facets(lab, nfacets))
