@@ -309,6 +309,100 @@ def parity_vs_oracle(n_objects, dev, seed0=0):
             "label_flips_off_ties": flips, "cells": int(d["n"]), "tolerance": 1e-4}
 
 
+def side_configs(net, dev, peak, args):
+    """Single-GPU measurements of the other BASELINE configs on their own graphs (N = 1 only):
+    cfg1  reconbench.yaml inference on ONE ~50 k-point scan-like graph (~330 k cells) + the CPU oracle on the same graph,
+    cfg3  synthetic_room-shaped scene: scipy Delaunay of --cfg3-points random points (1 M -> ~6.7 M cells), inference,
+    wide  the configs[1] training step at configs/modelnet.yaml:56 widths [128,256,512,1024] (tensor-pipe bound)."""
+    from dgnn_b200 import runModel as rm, synthetic as og
+    from dgnn_b200.surfaceNetStaticEdgeFilters import SurfaceNet
+    from dgnn_b200.synthetic import make_clf, to_attr
+    out = {}
+
+    def graph(points):
+        adj, infinite, cen, _ = og.delaunay_graph(points)
+        n = infinite.shape[0]
+        x, ea, y = og.synthetic_features(n, infinite, seed=5)
+        return to_attr(dict(x=torch.from_numpy(x), edge_attr=torch.from_numpy(ea), y=torch.from_numpy(y),
+                            edge_index=torch.from_numpy(adj.T.astype(np.int64)).contiguous(),
+                            pos=torch.from_numpy(cen.astype(np.float32)))), n
+
+    def infer_ms(d, iters):
+        dd = to_attr({k: v.to(dev) for k, v in d.items()})
+        net.eval()
+        with torch.no_grad():
+            ms = _timed_region(lambda: net.inference_layer(dd), iters, 3, dev, 1) / iters
+        net.train()
+        return ms
+
+    # cfg1
+    d1, n1 = graph(og.scan_like_points(50_000, seed=0))
+    ms1 = infer_ms(d1, 20)
+    out["cfg1"] = {"cells": n1, "ms": round(ms1, 4), "cells_per_s": n1 / (ms1 * 1e-3),
+                   "hbm_frac": round(n1 * 4024 / (ms1 * 1e-3) / 1e9 / peak, 4),
+                   "workload": "configs[0] reconbench.yaml StaticEdgeFilters inference_layer, one 50 k-point scan-like graph, device resident"}
+    if not args.no_cpu_baseline:
+        from oracle.static_model import SurfaceNet as OracleNet
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ref = OracleNet(make_clf(convs=WIDTHS))
+        ref.load_state_dict({k: v.detach().cpu() for k, v in net.state_dict().items()})
+        ref.eval()
+        with torch.no_grad():
+            zr = ref.inference_layer(d1)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ref.inference_layer(d1)
+            cpu_s = (time.perf_counter() - t0) / 2
+            net.eval()
+            z = net.inference_layer(to_attr({k: v.to(dev) for k, v in d1.items()})).cpu()
+            net.train()
+        scale = torch.maximum(zr.abs(), zr.abs().mean())
+        out["cfg1"]["cpu_baseline"] = {"value": n1 / cpu_s, "unit": "cells/s", "cores": cores, "kind": "port",
+                                       "sample": "the same graph, 2 passes after 1 warm-up, oracle (plain PyTorch CPU)"}
+        out["cfg1"]["parity_max_rel"] = float(((z - zr).abs() / scale).max())
+    del d1
+    # cfg3
+    t0 = time.perf_counter()
+    d3, n3 = graph(og.random_points(args.cfg3_points, seed=0))
+    gen_s = time.perf_counter() - t0
+    ms3 = infer_ms(d3, 5)
+    out["cfg3"] = {"cells": n3, "points": args.cfg3_points, "ms": round(ms3, 3), "cells_per_s": n3 / (ms3 * 1e-3),
+                   "hbm_frac": round(n3 * 4024 / (ms3 * 1e-3) / 1e9 / peak, 4), "host_delaunay_s": round(gen_s, 1),
+                   "workload": "configs[2] synthetic_room-shaped scene, scipy Delaunay of random points, inference_layer, device resident"}
+    del d3
+    # wide widths: the configs[1] batch at modelnet.yaml widths
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+    wide = (128, 256, 512, 1024)
+    host = make_objects(16, seed0=0)
+    clfw = make_clf(convs=wide, device=str(dev))
+    torch.manual_seed(0)
+    netw = SurfaceNet(clfw).to(dev).train()
+    optw = rm.Adam(netw.parameters(), lr=0.005)
+    dres = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    data = batch_of(dres, to_attr)
+
+    def stepw():
+        loss = rm.cell_loss(netw(data), data.all.y, data.all.x, clfw)
+        optw.zero_grad(set_to_none=True)
+        loss.backward()
+        optw.step()
+
+    msw = _timed_region(stepw, 5, 3, dev, 1) / 5
+    flops = 0
+    ws = [F0] + list(wide)
+    for a, b in zip(ws[:-1], ws[1:]):
+        flops += 4 * a * b + 8 * FE * a + 8 * a
+    flops += 2 * wide[-1] * (wide[-1] // 2) + 4 * (wide[-1] // 2)
+    out["wide"] = {"widths": [F0] + list(wide), "cells": host["n"], "ms_per_step": round(msw, 3),
+                   "cells_per_s": host["n"] / (msw * 1e-3),
+                   "algorithmic_tflops": round(3 * flops * host["n"] / (msw * 1e-3) / 1e12, 2),
+                   "note": "configs/modelnet.yaml:56 widths, 16 objects, fwd+loss+bwd+Adam; tensor-pipe bound: 3 x forward FLOPs per "
+                           "cell counted once (the 3xTF32 split issues 3 MMAs per product on top)"}
+    return out
+
+
 # --------------------------------------------------------------------------- partitioned scene (N > 1)
 
 SCENE_DIMS_WEAK = {1: (128, 128, 256), 2: (128, 256, 256), 4: (256, 256, 256), 8: (256, 256, 512)}   # 8.39 M cells per GPU
@@ -375,6 +469,48 @@ def scene_inference(net, dims, rank, world, dev, iters=5, overlap=True):
            "overlap": bool(overlap and world > 1)}
     net.train()
     return res
+
+
+UPD_DIMS = {1: (64, 128, 128), 2: (128, 128, 128), 4: (128, 128, 256), 8: (128, 256, 256)}   # 2.1 M cells per GPU
+
+
+def updated_training(rank, world, dev, steps=5, warmup=2):
+    """BASELINE configs[3] (cfg4): the Updated-edge-filter model (model_params [64,128,128,128], "sage+" head) trained on
+    ONE lattice scene partitioned over the ranks (2.1 M cells per GPU: the variant materialises its edge state, 4 x F_in
+    floats per cell and layer), fwd + kl loss + bwd + Adam, halo exchange forward, reverse halo exchange of the source
+    gradients backward, gradient all-reduce.  cells/s of the whole job."""
+    from dgnn_b200 import runModel as rm, scene as sc
+    from dgnn_b200.partition import PartitionedUpdatedTraining
+    from dgnn_b200.surfaceNetUpdatedEdgeFilters import SurfaceNet as UpdNet
+    from dgnn_b200.synthetic import make_clf, to_attr
+    dims = UPD_DIMS.get(world) or UPD_DIMS[8]
+    n = 2 * dims[0] * dims[1] * dims[2]
+    clf = to_attr(dict(training=dict(model_params=list(WIDTHS), model_name="sage+"),
+                       features=dict(normalization_feature=0, keep_normalization_feature=0), temp=dict(device=str(dev))))
+    loss_clf = make_clf(device=str(dev))
+    torch.manual_seed(0)
+    net = UpdNet(F0, clf).to(dev).train()
+    if world > 1:
+        import torch.distributed as dist
+        for t in net.parameters():
+            dist.broadcast(t.data, 0)
+    opt = rm.Adam(net.parameters(), lr=0.005)
+    shard = sc.lattice_scene(dims, rank, world, dev)
+    pt = PartitionedUpdatedTraining(net)
+    pt.prepare_scene(shard)
+    y, w = shard.y, shard.w
+
+    def step():
+        _, logits = pt.forward()
+        loss = rm.cell_loss(logits, y, w, loss_clf, group=None, distributed=world > 1)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        pt.allreduce_gradients()
+        opt.step()
+
+    ms = _timed_region(step, steps, warmup, dev, world) / steps
+    return {"cells": n, "dims": list(dims), "ms_per_step": round(ms, 3), "cells_per_s": n / (ms * 1e-3), "model": "Updated edge "
+            "filters, model_params %s, sage+ head, edge state materialised" % (list(WIDTHS),)}
 
 
 def partition_parity(net, rank, world, dev):
@@ -534,6 +670,10 @@ def run_partitioned(args, rank, world, local_rank):
     gc.collect(); torch.cuda.empty_cache()
     _stage("scene inference %r" % (infer,))
 
+    upd = updated_training(rank, world, dev)
+    gc.collect(); torch.cuda.empty_cache()
+    _stage("updated training %r" % (upd,))
+
     # ---- the round-1 data-parallel object-batch number, as an extra key
     dp = dp_objects(args, rank, world, dev, clf)
 
@@ -563,6 +703,7 @@ def run_partitioned(args, rank, world, local_rank):
                "scene_inference": infer,
                "partition_vs_single_max_abs": parity,
                "partition_train_vs_single": train_par,
+               "updated_training": upd,
                "dp": dp, "kernels": table, "cpu_baseline": None}
         print(json.dumps(out), flush=True)
     _stage("done")
@@ -657,6 +798,8 @@ def main():
     ap.add_argument("--objects", type=int, default=64, help="object graphs per GPU per step")
     ap.add_argument("--cpu-objects", type=int, default=4, help="objects in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the cfg1 / cfg3 / wide-width side measurements")
+    ap.add_argument("--cfg3-points", type=int, default=1_000_000, help="points of the cfg3 scene (scipy Delaunay on the host)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -826,6 +969,12 @@ def main():
         scene_inf = {"error": "out of memory on one GPU"}
     gc.collect(); torch.cuda.empty_cache()
     part_parity = partition_parity(net, 0, 1, dev)       # sharded build (1 shard) against the ordinary loader path
+    upd = updated_training(0, 1, dev)
+    gc.collect(); torch.cuda.empty_cache()
+    side = {}
+    if not args.no_side_configs:
+        side = side_configs(net, dev, peak, args)
+        gc.collect(); torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -857,6 +1006,8 @@ def main():
                          "hbm_frac": round(n_cells * 4024 / (infer_ms * 1e-3) / 1e9 / peak, 4),
                          "note": "eval-mode inference_layer on the same batch, device resident, 4 024 B/cell"},
            "scene_inference": scene_inf,
+           "updated_training": upd,
+           "cfg1_inference": side.get("cfg1"), "cfg3_inference": side.get("cfg3"), "wide_training": side.get("wide"),
            "partition_vs_single_max_abs": part_parity,
            "parity": parity,
            "parity_max_rel": parity["logits_max_rel"] if parity else None,

@@ -399,7 +399,35 @@ class PartitionedUpdatedTraining:
         self._plan = (local, maps, ids, HaloComm(maps, n, self.group))
         return self._plan
 
-    def forward(self, data_all):
+    def prepare_scene(self, scene):
+        """Sharded build from this rank's ``dgnn_b200.scene.LocalScene`` (halo maps negotiated with the peers; the edge
+        state of an edge lives with its target cell, so only ``ea_in`` is needed)."""
+        from .surfaceNetUpdatedEdgeFilters import AttrView
+        net = self.model
+        dev = torch.device(net.clf.temp.device)
+        maps = build_halo_maps_sharded(scene.nbr_gid.to(dev), scene.lo, scene.hi, partition_bounds(scene.n_global, self.world),
+                                       self.rank, self.group)
+        n_own, n_src = maps.n_own, maps.n_own + maps.n_halo
+        comm = HaloComm(maps, scene.n_global, self.group)
+        x_loc = torch.zeros((n_src, scene.x.shape[1]), dtype=torch.float32, device=dev)
+        x_loc[:n_own] = scene.x
+        if scene.x.shape[1] % 4 == 0:
+            comm.exchange(x_loc)
+        else:                                              # the row exchange moves multiples of 4 floats
+            xp = torch.zeros((n_src, (scene.x.shape[1] + 3) // 4 * 4), dtype=torch.float32, device=dev)
+            xp[:n_own, :scene.x.shape[1]] = scene.x
+            comm.exchange(xp)
+            x_loc = xp[:, :scene.x.shape[1]].contiguous()
+        tgt = torch.arange(n_own, device=dev).repeat_interleave(4)
+        ei = torch.stack([maps.local_nbr.reshape(-1).long(), tgt])
+        e_loc = 4 * n_own
+        ea_loc = scene.ea_in.reshape(e_loc, -1).contiguous()
+        adj = (ei, torch.arange(e_loc, device=dev), (n_src, n_own))
+        local = AttrView(x=x_loc, n_id=torch.arange(n_src, device=dev), adjs=[adj] * net.num_layers, edge_attr=ea_loc)
+        self._plan = (local, maps, scene.caller_ids, comm)
+        return self._plan
+
+    def forward(self, data_all=None):
         if self._plan is None:
             self.prepare(data_all)
         local, maps, ids, comm = self._plan

@@ -126,6 +126,35 @@ class AttrView:
         self.__dict__.update(kw)
 
 
+def _layer_plan(net, adj, dev, need_backward):
+    """ELL tables of one hop plus the two edge-id maps the layer kernels need: ``eid_glob[t,k]`` = row of the global edge
+    state behind the k-th in-edge of target t, ``orow[s,j]`` = row ``4t+k`` of e' behind the j-th out-edge of source s.
+    Cached on the module per (edge_index, e_id) tensor identity + version (a whole-graph batch passes the same adjacency
+    for every layer and every step; it is built once)."""
+    edge_index, e_id, size = adj[0], adj[1], adj[2]
+    key = (id(edge_index), edge_index._version, id(e_id), e_id._version, tuple(size), bool(need_backward), str(dev))
+    cache = net.__dict__.setdefault("_plans", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit[0]
+    g = build_from_edges(edge_index, None, None, size[0], size[1], dev, need_backward=need_backward)
+    eid_loc = g._eid_in
+    eid_glob = torch.where(eid_loc >= 0, e_id.to(dev)[eid_loc.clamp(min=0).long()].to(torch.int32),
+                           torch.full_like(eid_loc, -1)).contiguous()
+    orow = None
+    if need_backward:
+        row_of_edge = torch.full((max(edge_index.shape[1], 1),), -1, dtype=torch.int32, device=dev)
+        flat = eid_loc.reshape(-1)
+        ok = flat >= 0
+        row_of_edge[flat[ok].long()] = torch.arange(flat.numel(), dtype=torch.int32, device=dev)[ok]
+        eo = g._eid_out
+        orow = torch.where(eo >= 0, row_of_edge[eo.clamp(min=0).long()], torch.full_like(eo, -1)).contiguous()
+    if len(cache) > 16:
+        cache.clear()
+    cache[key] = ((g, eid_glob, orow), (edge_index, e_id))      # the entry keeps the keyed tensors alive
+    return g, eid_glob, orow
+
+
 def _forward(net, data_all, dev, sv, comm=None):
     """Forward on the device; ``sv`` (a list) receives what the backward needs, one entry per layer."""
     f = net.clf.features
@@ -138,14 +167,11 @@ def _forward(net, data_all, dev, sv, comm=None):
     relu_in = False
     for i, conv in enumerate(net.convs):
         edge_index, e_id, size = data_all.adjs[i]
-        g = build_from_edges(edge_index, None, None, size[0], size[1], dev, need_backward=sv is not None)
+        g, eid_glob, orow = _layer_plan(net, data_all.adjs[i], dev, sv is not None)
         n_tgt = size[1]
         fi, fo = pad4(conv.in_channels), conv.out_channels
         k_in = e_state.shape[1]
         # rows of the edge state for every (target, slot): global edge id = e_id[local edge id]
-        eid_loc = g._eid_in
-        eid_glob = torch.where(eid_loc >= 0, e_id.to(dev)[eid_loc.clamp(min=0).long()].to(torch.int32),
-                               torch.full_like(eid_loc, -1))
         ea = torch.empty((n_tgt * 4, k_in), dtype=torch.float32, device=dev)
         call("dgnn_gather_rows", ptr(e_state), ptr(eid_glob), n_tgt * 4, k_in, ptr(ea), _stream())
         w_e = engine._pad2(conv.lin_e.weight.detach(), fi, k_in).contiguous()
@@ -165,13 +191,7 @@ def _forward(net, data_all, dev, sv, comm=None):
             s = _Saved()
             s.g, s.eid_glob, s.ea, s.phi, s.agg, s.x_in, s.out = g, eid_glob, ea, e_new, agg, x, out
             s.relu_in, s.w_e, s.w_cat, s.fi, s.fo, s.k_in, s.e_all = relu_in, w_e, w_cat, fi, fo, k_in, e_all
-            # row 4t+k of e' for every out-edge (s,j): invert the (target,slot) -> local edge id table
-            row_of_edge = torch.full((edge_index.shape[1],), -1, dtype=torch.int32, device=dev)
-            flat = eid_loc.reshape(-1)
-            ok = flat >= 0
-            row_of_edge[flat[ok].long()] = torch.arange(flat.numel(), dtype=torch.int32, device=dev)[ok]
-            eo = g._eid_out
-            s.orow = torch.where(eo >= 0, row_of_edge[eo.clamp(min=0).long()], torch.full_like(eo, -1)).contiguous()
+            s.orow = orow          # row 4t+k of e' for every out-edge (s,j)
             sv.append(s)
         x = out
         # new edge state, indexed by global edge id; edges outside this hop stay 0 (Updated:236-238)
