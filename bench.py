@@ -183,12 +183,48 @@ def algorithmic_bytes(name, a):
     return None, ""
 
 
+_CELLS_ARG = {"dgnn_gather_tc_fwd": 9, "dgnn_dense_fwd_tc": 10, "dgnn_dense_bwd_tc": 9, "dgnn_dw_bwd_tc": 12,
+              "dgnn_gather_tc_bwd": 13, "dgnn_layer_fwd": 14, "dgnn_layer_fwd_tc": 14, "dgnn_dense_bwd": 9, "dgnn_dw_bwd": 12,
+              "dgnn_gather_bwd": 13}
+_TRAFFIC_KERNELS = {"dgnn_gather_tc_fwd": [r"gather_tc_kernel<\d+, 0\b"],
+                    "dgnn_gather_tc_bwd": [r"gather_tc_kernel<\d+, 1\b", r"dwe_tc_kernel<"],
+                    "dgnn_dense_fwd_tc": [r"layer_tc_kernel<0, 0"], "dgnn_dense_bwd_tc": [r"layer_tc_kernel<2, 0"],
+                    "dgnn_dw_bwd_tc": [r"dw_tc_kernel"]}
+
+
+def launch_cells(name, args):
+    i = _CELLS_ARG.get(name)
+    return args[i] if i is not None else 0
+
+
+def traffic_per_cell(name, tag):
+    """(DRAM bytes per cell, source file) of the kernels behind one C-ABI call from the newest committed ncu capture."""
+    import csv, glob, re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_layer_kernels.csv")))
+    pats = _TRAFFIC_KERNELS.get(name)
+    if not files or not pats:
+        return None, None
+    rows = list(csv.DictReader(open(files[-1])))
+    total, hit = 0.0, 0
+    for pat in pats:
+        for r in rows:
+            layer = r["layer"]
+            same = layer == tag or ("->" not in tag and layer.startswith(tag + "->"))
+            if same and re.search(pat, r["Kernel Name"]):
+                total += float(r["dram_bytes_per_cell"]); hit += 1
+                break
+    if hit != len(pats):
+        return None, os.path.basename(files[-1])
+    return total, os.path.basename(files[-1])
+
+
 class KernelProfile:
     """Per-launch device time of every C-ABI call, measured with CUDA events on the launching
     stream (used after the timed region to find the dominant kernel and its achieved GB/s)."""
 
     def __init__(self):
         self.rows = []
+        self.rows_cells = {}
 
     def install(self):
         from dgnn_b200 import _lib
@@ -222,25 +258,21 @@ class KernelProfile:
             k = (name, tag)
             r = agg.setdefault(k, dict(ms=0.0, launches=0, bytes=0, known=nbytes is not None))
             r["ms"] += ms; r["launches"] += 1; r["bytes"] += nbytes or 0
+            self.rows_cells[k] = launch_cells(name, args)
         total = sum(r["ms"] for r in agg.values())
         top = max((k for k in agg if agg[k]["known"]), key=lambda k: agg[k]["ms"])
         r = agg[top]
         ach = r["bytes"] / (r["ms"] * 1e-3) / 1e9
         table = sorted(((k[0] + ":" + k[1], round(v["ms"] / n_steps, 4), v["launches"] // n_steps) for k, v in agg.items()),
                        key=lambda t: -t[1])
-        # DRAM bytes per cell (dram__bytes_read.sum + dram__bytes_write.sum) of the F = 128 kernels from the committed
-        # `ncu --set full` capture (profiles/r01_ncu_full_final_kernels.csv, 604 913 cells), scaled to this launch
-        traffic_per_cell = {"dgnn_gather_tc_bwd:f128": 3720, "dgnn_gather_tc_fwd:f128": 1304,
-                            "dgnn_dense_fwd_tc:f128->128": 1480, "dgnn_dense_bwd_tc:f128->128": 2007,
-                            "dgnn_dw_bwd_tc:f128->128": 2055}
-        algo_per_cell = {"dgnn_gather_tc_bwd:f128": 2384, "dgnn_gather_tc_fwd:f128": 1360,
-                         "dgnn_dense_fwd_tc:f128->128": 1536, "dgnn_dense_bwd_tc:f128->128": 2064,
-                         "dgnn_dw_bwd_tc:f128->128": 2048}
-        tpc = traffic_per_cell.get(top[0] + ":" + top[1])
-        cells = (r["bytes"] // r["launches"]) // algo_per_cell[top[0] + ":" + top[1]] if tpc else 0
+        # measured DRAM traffic of the dominant call: dram__bytes_read.sum + dram__bytes_write.sum per cell of its kernels in
+        # the committed `ncu --set full` capture (profiles/r*_ncu_layer_kernels.csv, tools/ncu_kernels_csv.py), scaled to
+        # the cells of this launch
+        cells = int(self.rows_cells.get(top, 0))
+        tpc, tsrc = traffic_per_cell(top[0], top[1])
         roof = {"bound": "hbm", "kernel": top[0] + ":" + top[1], "achieved": round(ach, 1), "peak": peak_gbs, "unit": "GB/s",
                 "frac": round(ach / peak_gbs, 4), "peak_source": peak_src,
-                "traffic": int(tpc * cells) if tpc and cells else None,
+                "traffic": int(tpc * cells) if tpc and cells else None, "traffic_source": tsrc,
                 "kernel_ms_per_launch": round(r["ms"] / r["launches"], 4),
                 "kernel_share_of_step": round(r["ms"] / total, 4),
                 "algorithmic_bytes_per_launch": r["bytes"] // r["launches"]}
