@@ -87,6 +87,7 @@ SIGNATURES = {
     "dgnn_edge_filter_bwd": [P, P, P, I, P, P, P, P, P, I, L, L, I, P, P],
     "dgnn_adam_step": [P, P, P, P, L, F, F, F, F, I, P],
     "dgnn_adam_multi": [P, I, L, F, F, F, F, I, P],
+    "dgnn_adam_multi_dev": [P, I, L, P, P, P],
     "dgnn_gc_terminals": [P, L, F, P, P, P, P, P],
     "dgnn_gc_push_relabel": [L, P, P, P, P, P, P, I, I, P],
     "dgnn_gc_bfs_init": [L, P, P, I, P],

@@ -459,6 +459,32 @@ __global__ void adam_multi_kernel(const long long* __restrict__ table, float lr,
     }
 }
 
+// The same update with the step count and the hyper-parameters read from device memory, so that a captured CUDA graph of
+// the training step stays valid across replays: state[0] = step count (>= 1, advanced by the caller on the same stream
+// before the launch), hyper = (lr, beta1, beta2, eps).
+__global__ void adam_multi_dev_kernel(const long long* __restrict__ table, const float* __restrict__ hyper,
+                                      const long long* __restrict__ state) {
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3];
+    const double step = (double)state[0];
+    const float bc1 = (float)(1.0 - pow((double)b1, step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, step));
+    const long long* row = table + (size_t)blockIdx.y * 5;
+    float* p = reinterpret_cast<float*>(row[0]);
+    const float* g = reinterpret_cast<const float*>(row[1]);
+    float* m = reinterpret_cast<float*>(row[2]);
+    float* v = reinterpret_cast<float*>(row[3]);
+    const long long n = row[4];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float gi = g[i];
+        float mi = m[i] + (gi - m[i]) * (1.f - b1);
+        float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - (lr / bc1) * (mi / denom);
+    }
+}
+
 // dy = relu'(y) * dh, S1 = sum dy, S2 = sum dy*xhat; thread owns a 4-column group
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ z,
                                                       const float* __restrict__ sc, const float* __restrict__ sh,
@@ -719,6 +745,15 @@ extern "C" int dgnn_adam_multi(const int64_t* table, int n_tensors, int64_t max_
     dim3 grid(grid_for(max_n, 256, 64), n_tensors);
     adam_multi_kernel<<<grid, 256, 0, as_stream(stream)>>>((const long long*)table, lr, beta1, beta2, eps, bc1, bc2);
     return check_launch("dgnn_adam_multi");
+}
+
+extern "C" int dgnn_adam_multi_dev(const int64_t* table, int n_tensors, int64_t max_n, const float* hyper,
+                                   const int64_t* state, void* stream) {
+    if (n_tensors <= 0 || max_n <= 0) return 0;
+    DGNN_REQUIRE(table && hyper && state, "null pointer");
+    dim3 grid(grid_for(max_n, 256, 64), n_tensors);
+    adam_multi_dev_kernel<<<grid, 256, 0, as_stream(stream)>>>((const long long*)table, hyper, (const long long*)state);
+    return check_launch("dgnn_adam_multi_dev");
 }
 
 extern "C" int dgnn_act_bwd(const float* dh, const float* z, const float* in_scale, const float* in_shift,

@@ -247,15 +247,27 @@ class BatchPrefetcher:
 
 class Adam(torch.optim.Optimizer):
     """``torch.optim.Adam(params, lr)`` with the reference's defaults (``runModel.py:290``), all
-    parameter tensors updated by ONE kernel launch (``dgnn_adam_multi``)."""
+    parameter tensors updated by ONE kernel launch.  The step count and the hyper-parameters live in device memory
+    (``dgnn_adam_multi_dev``) and the pointer table is staged through pinned host memory, so ``step()`` can be captured
+    in a CUDA graph (``GraphedStep``) and replayed; ``lr`` may be changed between steps as the reference does
+    (``adjust_learning_rate``, ``runModel.py:95-99``)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._step = 0
 
+    def _group_state(self, group, dev):
+        gs = group.get("_dev")
+        if gs is None:
+            gs = group["_dev"] = dict(step=torch.zeros(1, dtype=torch.int64, device=dev),
+                                      hyper=torch.empty(4, dtype=torch.float32, device=dev), hyper_host=None,
+                                      table=None, table_host=None, rows=None)
+        return gs
+
     @torch.no_grad()
     def step(self, closure=None):
         self._step += 1
+        capturing = torch.cuda.is_current_stream_capturing()
         for group in self.param_groups:
             rows, max_n = [], 0
             for p in group["params"]:
@@ -273,11 +285,68 @@ class Adam(torch.optim.Optimizer):
             if not rows:
                 continue
             dev = group["params"][0].device
-            table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+            gs = self._group_state(group, dev)
             b1, b2 = group["betas"]
-            call("dgnn_adam_multi", ptr(table), len(rows), max_n, float(group["lr"]), float(b1), float(b2),
-                 float(group["eps"]), self._step, _stream())
-            group["_table"] = table
+            hyper = (float(group["lr"]), float(b1), float(b2), float(group["eps"]))
+            if gs["hyper_host"] != hyper:                      # (re)upload the hyper-parameters only when they change
+                if capturing:
+                    raise RuntimeError("Adam hyper-parameters changed during CUDA graph capture")
+                gs["hyper"].copy_(torch.tensor(hyper, dtype=torch.float32))
+                gs["hyper_host"] = hyper
+            if gs["rows"] != rows:                             # gradient buffers moved (or first step): restage the table
+                if gs["table_host"] is None or gs["table_host"].shape[0] != len(rows):
+                    gs["table_host"] = torch.empty((len(rows), 5), dtype=torch.int64).pin_memory()
+                    gs["table"] = torch.empty((len(rows), 5), dtype=torch.int64, device=dev)
+                gs["table_host"].copy_(torch.tensor(rows, dtype=torch.int64))
+                gs["table"].copy_(gs["table_host"], non_blocking=True)     # pinned -> device: a memcpy node under capture
+                gs["rows"] = rows
+            gs["step"] += 1
+            call("dgnn_adam_multi_dev", ptr(gs["table"]), len(rows), max_n, ptr(gs["hyper"]), ptr(gs["step"]), _stream())
             for p in group["params"]:           # the kernel wrote the parameters behind autograd's back: record the
                 if p.grad is not None:          # in-place update so that version-keyed caches (packed weights) notice
                     torch.autograd.graph.increment_version(p)
+
+
+class GraphedStep:
+    """One training step (forward, loss, backward, optimiser) of a FIXED device-resident batch captured into a CUDA
+    graph and replayed: the ~140 kernel launches of a step become one graph launch (no launch gaps, no Python between
+    kernels).  The reference trains for many epochs on one collated batch of all training graphs (``run.py:59-61``), so
+    the captured step is replayed as long as the batch object and its layout do not change; a different batch captures
+    a new graph.
+
+        step = GraphedStep(lambda: cell_loss(net(batch), batch.all.y, batch.all.x, clf), optimizer)
+        for epoch in ...: loss = step()          # a device scalar (updated in place by every replay)
+    """
+
+    def __init__(self, loss_fn, optimizer, post_backward=None, warmup=3):
+        self.loss_fn, self.opt, self.post_backward, self.warmup = loss_fn, optimizer, post_backward, warmup
+        self.graph = None
+        self.loss = None
+
+    def _eager(self):
+        loss = self.loss_fn()
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.post_backward is not None:
+            self.post_backward()
+        self.opt.step()
+        return loss
+
+    def __call__(self):
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                     # warm-up off the capture stream: plans, packed weights,
+                for _ in range(self.warmup):                  # optimiser state and the allocator pool settle first
+                    self._eager()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.opt.zero_grad(set_to_none=True)              # gradients are allocated inside the graph's private pool
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._eager()
+        self.graph.replay()
+        for group in self.opt.param_groups:                   # the replay rewrote the parameters: version-keyed caches
+            for p in group["params"]:                         # (packed weights of a later eval pass) must notice
+                torch.autograd.graph.increment_version(p)
+        return self.loss

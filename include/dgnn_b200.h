@@ -346,6 +346,11 @@ int dgnn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  * exp_avg_sq, numel); max_n = largest numel */
 int dgnn_adam_multi(const int64_t* table, int n_tensors, int64_t max_n, float lr, float beta1,
                     float beta2, float eps, int step, void* stream);
+/* The same update with lr / beta1 / beta2 / eps (hyper, device float[4]) and the step count (state, device int64[1], >= 1,
+ * advanced by the caller on the stream before the launch) read from device memory: a CUDA graph captured around the
+ * training step (runModel.GraphedStep) stays valid from replay to replay. */
+int dgnn_adam_multi_dev(const int64_t* table, int n_tensors, int64_t max_n, const float* hyper,
+                        const int64_t* state, void* stream);
 
 /* ---- labels / facets (generate_mesh.py:75, 94-105) --------------------------------------- */
 int dgnn_argmax_labels(const float* logits, int64_t n, int od, uint8_t* labels, void* stream);

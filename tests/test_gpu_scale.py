@@ -214,3 +214,46 @@ def test_packed_weight_cache_follows_weight_updates(kf96_state):
     z3 = net.inference_layer(d)
     fresh = cuda_net({}, {k: v.detach().cpu() for k, v in net.state_dict().items()}).eval()
     assert torch.equal(z3, fresh.inference_layer(d))
+
+
+def test_graphed_step_replays_the_eager_step_bit_exactly(kf96_state):
+    """runModel.GraphedStep: the captured CUDA graph of fwd + loss + bwd + Adam reproduces the eager steps bit for bit
+    (deterministic kernels), follows a learning-rate change without re-capture, and eval inference afterwards sees the
+    trained weights (packed-operand cache invalidated by the replays)."""
+    from dgnn_b200 import runModel as rm
+    g = make_graph(1500, seed=91)
+    d = data_all(g, with_pos=True)
+    clf = make_clf(device=DEV)
+
+    def run(graphed):
+        net = cuda_net({}, kf96_state).train()
+        opt = rm.Adam(net.parameters(), lr=0.005)
+        dd = to_attr({k: v.to(DEV) for k, v in d.items()})
+        batch = full_batch(dd)
+        batch.batch_n_id = batch.batch_n_id.to(DEV)
+        batch.batch_adjs = [(a[0], a[1].to(DEV), a[2]) for a in batch.batch_adjs]
+        fn = lambda: rm.cell_loss(net(batch), dd.y, dd.x, clf)
+        losses = []
+        if graphed:
+            step = rm.GraphedStep(fn, opt, warmup=0)
+        for i in range(6):
+            if i == 4:
+                for gp in opt.param_groups:
+                    gp["lr"] = 0.0005                      # adjust_learning_rate (runModel.py:95-99)
+            if graphed:
+                losses.append(float(step().item()))
+            else:
+                loss = fn(); opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
+                losses.append(float(loss.item()))
+        net.eval()
+        with torch.no_grad():
+            z = net.inference_layer(dd)
+        return losses, z, {k: v.clone() for k, v in net.state_dict().items()}
+
+    le, ze, se = run(False)
+    lg, zg, sg = run(True)
+    assert le == lg, (le, lg)
+    assert le[-1] < le[0]
+    for k in se:
+        assert torch.equal(se[k], sg[k]), k
+    assert torch.equal(ze, zg)
