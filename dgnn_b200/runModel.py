@@ -264,6 +264,21 @@ class Adam(torch.optim.Optimizer):
                                       table=None, table_host=None, rows=None)
         return gs
 
+    def refresh_hyper(self):
+        """Upload lr / betas / eps of every group if they changed since the last step (called by ``step`` and, before a
+        replay, by ``GraphedStep`` - a captured step never runs this Python again)."""
+        for group in self.param_groups:
+            gs = group.get("_dev")
+            if gs is None:
+                continue
+            b1, b2 = group["betas"]
+            hyper = (float(group["lr"]), float(b1), float(b2), float(group["eps"]))
+            if gs["hyper_host"] != hyper:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("Adam hyper-parameters changed during CUDA graph capture")
+                gs["hyper"].copy_(torch.tensor(hyper, dtype=torch.float32))
+                gs["hyper_host"] = hyper
+
     @torch.no_grad()
     def step(self, closure=None):
         self._step += 1
@@ -286,19 +301,15 @@ class Adam(torch.optim.Optimizer):
                 continue
             dev = group["params"][0].device
             gs = self._group_state(group, dev)
-            b1, b2 = group["betas"]
-            hyper = (float(group["lr"]), float(b1), float(b2), float(group["eps"]))
-            if gs["hyper_host"] != hyper:                      # (re)upload the hyper-parameters only when they change
-                if capturing:
-                    raise RuntimeError("Adam hyper-parameters changed during CUDA graph capture")
-                gs["hyper"].copy_(torch.tensor(hyper, dtype=torch.float32))
-                gs["hyper_host"] = hyper
+            self.refresh_hyper()
             if gs["rows"] != rows:                             # gradient buffers moved (or first step): restage the table
                 if gs["table_host"] is None or gs["table_host"].shape[0] != len(rows):
                     gs["table_host"] = torch.empty((len(rows), 5), dtype=torch.int64).pin_memory()
                     gs["table"] = torch.empty((len(rows), 5), dtype=torch.int64, device=dev)
                 gs["table_host"].copy_(torch.tensor(rows, dtype=torch.int64))
-                gs["table"].copy_(gs["table_host"], non_blocking=True)     # pinned -> device: a memcpy node under capture
+                # pinned -> device: a memcpy node under capture; blocking otherwise (the pinned buffer is rewritten by the
+                # next restaging, which must not overtake an asynchronous copy)
+                gs["table"].copy_(gs["table_host"], non_blocking=capturing)
                 gs["rows"] = rows
             gs["step"] += 1
             call("dgnn_adam_multi_dev", ptr(gs["table"]), len(rows), max_n, ptr(gs["hyper"]), ptr(gs["step"]), _stream())
@@ -322,6 +333,7 @@ class GraphedStep:
         self.loss_fn, self.opt, self.post_backward, self.warmup = loss_fn, optimizer, post_backward, warmup
         self.graph = None
         self.loss = None
+        self.calls = 0
 
     def _eager(self):
         loss = self.loss_fn()
@@ -333,18 +345,20 @@ class GraphedStep:
         return loss
 
     def __call__(self):
+        """The first ``warmup`` calls run eagerly (they are ordinary training steps: graph plans, packed weights, optimiser
+        state and the allocator settle), the next call captures the step and every call from then on replays it."""
+        if self.calls < self.warmup:
+            self.calls += 1
+            return self._eager()
         if self.graph is None:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                     # warm-up off the capture stream: plans, packed weights,
-                for _ in range(self.warmup):                  # optimiser state and the allocator pool settle first
-                    self._eager()
-            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.opt.zero_grad(set_to_none=True)              # gradients are allocated inside the graph's private pool
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph):                # records, does not execute
                 self.loss = self._eager()
+        self.calls += 1
+        if hasattr(self.opt, "refresh_hyper"):
+            self.opt.refresh_hyper()                          # e.g. the reference's adjust_learning_rate between epochs
         self.graph.replay()
         for group in self.opt.param_groups:                   # the replay rewrote the parameters: version-keyed caches
             for p in group["params"]:                         # (packed weights of a later eval pass) must notice

@@ -235,7 +235,7 @@ def test_graphed_step_replays_the_eager_step_bit_exactly(kf96_state):
         fn = lambda: rm.cell_loss(net(batch), dd.y, dd.x, clf)
         losses = []
         if graphed:
-            step = rm.GraphedStep(fn, opt, warmup=0)
+            step = rm.GraphedStep(fn, opt, warmup=2)
         for i in range(6):
             if i == 4:
                 for gp in opt.param_groups:
