@@ -21,8 +21,11 @@ namespace dgnn {
 
 using namespace umma;
 
-constexpr int DW_NPW = 12;                         // producer warps: one per 32-channel operand block at 128 -> 128
-constexpr int DW_THREADS = (DW_NPW + 1) * 32;      // 13 warps: at most 4 per scheduler => 128 registers per thread
+#ifndef DGNN_DW_NPW
+#define DGNN_DW_NPW 12
+#endif
+constexpr int DW_NPW = DGNN_DW_NPW;                // producer warps: 12 = one per 32-channel operand block at 128 -> 128 (128
+constexpr int DW_THREADS = (DW_NPW + 1) * 32;      // registers).  24 (two per block, 72 registers, spills) measured 2x slower on B200
 constexpr int DW_CELLS = 32;                       // cells (K) per stage = 8 groups of 4 cells
 constexpr int DW_A_BYTES = 128 * 128;               // M = 128 channel rows x 32 cells (one K-atom): 16 KB
 constexpr int DW_MAX_STAGES = 4;                    // narrow layers have small stages: more of them in flight
@@ -271,10 +274,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
             mbar_wait(&bar_done, 0);
             tc_fence_after_sync();
         }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c0 = (grp + 3 * j) * 32;
-            if (c0 >= p.np) break;
+#pragma unroll 1
+        for (int chunk = grp; chunk * 32 < p.np; chunk += DW_NPW / 4) {
+            const int c0 = chunk * 32;
             float v[32];
             if (my_groups > 0) {
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -304,6 +306,254 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
     if (warp == DW_NPW) tmem_dealloc(tmem_base, 256);
 }
 
+
+// -----------------------------------------------------------------------------------------------------------------------
+// dW, second formulation ("row-block" kernel) for layers whose block is the whole matrix (f_out <= 128, k_total <= 256).
+//
+// A stage is 32 consecutive cells.  Their rows of dy, z, agg and x are CONTIGUOUS in global memory (full-width rows), so
+// one warp fetches a whole raw stage with four 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) into a 2-deep shared-memory
+// ring - no per-thread global loads, no address arithmetic in the producers.  The transposition the contraction over
+// cells needs is done by ADDRESSING: producer thread = one operand row (= one channel); it reads its channel of 16 cells
+// with 16 LDS.32 (lanes = consecutive channels: conflict-free), applies the normalisation backward / the producer
+// affine + ReLU with per-thread-constant coefficients, splits hi / lo and writes four 16-byte chunks per image (swizzled:
+// conflict-free).  No shuffles, no selects.  The single operand buffer works as two half-stages of 16 cells (k-steps 0-1
+// and 2-3 of the 32-cell K-atom): while the tensor core consumes one half the producers fill the other.
+// db = column sums of dz: the thread that owns a dz channel keeps its sum in a register for the whole kernel.
+struct Dw2Args {
+    const float* dy;
+    const float* z;
+    const float* ng;
+    const float* na;
+    const float* nb;
+    const float* nmean;
+    const float* nrstd;
+    const float* agg;
+    const float* x_in;
+    const float* in_scale;
+    const float* in_shift;
+    int relu_in;
+    int64_t n_tgt;
+    int f_in, f_out, k_total, np;
+    float* partials;      // [grid][f_out][k_total]
+    double* db_partials;  // [grid][f_out], may be NULL
+};
+
+constexpr int DW2_PW = 12;                          // producer warps: thread = operand row (128 dz rows + up to 256 [agg | h] rows)
+constexpr int DW2_THREADS = (DW2_PW + 2) * 32;      // + MMA warp + bulk-copy warp
+constexpr int DW2_CELLS = 32;
+
+__global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t raw_full[2], raw_empty[2], op_full[2], op_empty[2], bar_done;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool norm = p.ng != nullptr;
+    const int b_bytes = p.np * 128;
+    // operand buffer: A hi | A lo | B hi | B lo, then the raw ring: per stage dy | z | agg | x
+    uint8_t* a_hi = smem;
+    uint8_t* b_hi = smem + 2 * DW_A_BYTES;
+    const uint32_t dy_bytes = (uint32_t)DW2_CELLS * p.f_out * 4u, x_bytes = (uint32_t)DW2_CELLS * p.f_in * 4u;
+    const uint32_t off_z = dy_bytes, off_agg = off_z + (norm ? dy_bytes : 0u), off_x = off_agg + (p.agg ? x_bytes : 0u);
+    const uint32_t raw_stage = (off_x + x_bytes + 127u) & ~127u;
+    uint8_t* raw0 = smem + 2 * DW_A_BYTES + 2 * b_bytes;
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], DW2_PW);
+            mbar_init(&op_full[i], DW2_PW); mbar_init(&op_empty[i], 1);
+        }
+        mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
+    // operand rows beyond f_out / k_total are never written but are read by the MMA: zero the whole buffer once
+    for (int i = tid; i < (2 * DW_A_BYTES + 2 * b_bytes) / 16; i += DW2_THREADS)
+        reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async_smem();
+    if (warp == DW2_PW) tmem_alloc(&tmem_slot, 256);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const int64_t n_groups = (p.n_tgt + DW2_CELLS - 1) / DW2_CELLS;
+    const int64_t per = (n_groups + gridDim.x - 1) / gridDim.x;           // contiguous range of 32-cell stages per CTA
+    const int64_t g_begin = (int64_t)blockIdx.x * per;
+    const int64_t g_end = g_begin + per < n_groups ? g_begin + per : n_groups;
+    const int64_t my = g_end > g_begin ? g_end - g_begin : 0;
+
+    if (warp == DW2_PW + 1) {
+        // ------------------------------------------------------------ bulk-copy warp: raw stages, one stage ahead
+        if (lane == 0) {
+            for (int64_t s = 0; s < my; ++s) {
+                const int rs = (int)(s & 1);
+                mbar_wait(&raw_empty[rs], (uint32_t)(((s >> 1) & 1) ^ 1));
+                const int64_t c0 = (g_begin + s) * DW2_CELLS;
+                const int64_t left = p.n_tgt - c0;
+                const uint32_t rows = (uint32_t)(left < DW2_CELLS ? left : DW2_CELLS);
+                uint8_t* dst = raw0 + (size_t)rs * raw_stage;
+                const uint32_t nd = rows * (uint32_t)p.f_out * 4u, nx = rows * (uint32_t)p.f_in * 4u;
+                mbar_arrive_expect_tx(&raw_full[rs], nd * (norm ? 2u : 1u) + nx * (p.agg ? 2u : 1u));
+                bulk_g2s(dst, p.dy + (size_t)c0 * p.f_out, nd, &raw_full[rs]);
+                if (norm) bulk_g2s(dst + off_z, p.z + (size_t)c0 * p.f_out, nd, &raw_full[rs]);
+                if (p.agg) bulk_g2s(dst + off_agg, p.agg + (size_t)c0 * p.f_in, nx, &raw_full[rs]);
+                bulk_g2s(dst + off_x, p.x_in + (size_t)c0 * p.f_in, nx, &raw_full[rs]);
+            }
+        }
+    } else if (warp == DW2_PW) {
+        // ------------------------------------------------------------ MMA warp: two half-stages (2 k-steps each) per stage
+        const uint32_t idesc = make_idesc_tf32(128, p.np);
+        if (lane == 0) {
+            const uint32_t ah = smem_u32(a_hi), al = ah + DW_A_BYTES, bh = smem_u32(b_hi), bl = bh + b_bytes;
+            for (int64_t s = 0; s < my; ++s) {
+#pragma unroll
+                for (int hs = 0; hs < 2; ++hs) {
+                    mbar_wait(&op_full[hs], (uint32_t)(s & 1));
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int kk = 2 * hs; kk < 2 * hs + 2; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bh + ko), idesc, (s > 0 || kk > 0) ? 1u : 0u);
+                        mma_tf32(tmem_base, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
+                        mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
+                    }
+                    mma_commit(&op_empty[hs]);
+                }
+                if (s == my - 1) mma_commit(&bar_done);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ producers: thread = operand row
+        const int row_a = tid;                               // dz channel (A rows) for tid < 128
+        const int row_b = tid - 128;                         // [agg | h] channel (B rows) for tid >= 128
+        const bool is_a = tid < 128;
+        const bool live = is_a ? row_a < p.f_out : row_b < p.k_total;
+        // source of this row inside a raw stage, and its coefficients (loop invariants)
+        uint32_t src_off = 0, src2_off = 0, stride = 0;
+        float c0 = 1.f, c1 = 0.f, c2 = 0.f;                  // dz = c0*dy - z*c2 - c1   |   h = relu?(x*c0 + c1)
+        int kind = -1;                                       // 0 dz, 1 agg (raw), 2 h(x)
+        if (live) {
+            if (is_a) {
+                kind = 0; stride = (uint32_t)p.f_out * 4u; src_off = (uint32_t)row_a * 4u; src2_off = off_z + (uint32_t)row_a * 4u;
+                if (norm) {
+                    const float g = __ldg(p.ng + row_a), a = __ldg(p.na + row_a), b = __ldg(p.nb + row_a);
+                    const float m = __ldg(p.nmean + row_a), rs = __ldg(p.nrstd + row_a);
+                    c0 = g; c2 = rs * b; c1 = a - m * c2;    // g*dy - (a + (z - m)*rs*b)
+                }
+            } else {
+                stride = (uint32_t)p.f_in * 4u;
+                if (p.agg != nullptr && row_b < p.f_in) { kind = 1; src_off = off_agg + (uint32_t)row_b * 4u; }
+                else {
+                    const int col = p.agg != nullptr ? row_b - p.f_in : row_b;
+                    kind = 2; src_off = off_x + (uint32_t)col * 4u;
+                    if (p.in_scale != nullptr) { c0 = __ldg(p.in_scale + col); c1 = __ldg(p.in_shift + col); }
+                }
+            }
+        }
+        const bool relu = kind == 2 && p.relu_in != 0;
+        const bool affine = kind == 2 && p.in_scale != nullptr;
+        const int row = is_a ? row_a : row_b;
+        const uint32_t dst_hi = smem_u32(is_a ? a_hi : b_hi) + (uint32_t)row * 128u;
+        const uint32_t lo_off = is_a ? (uint32_t)DW_A_BYTES : (uint32_t)b_bytes;
+        const uint32_t rsw = (uint32_t)(row & 7);
+        const uint32_t raw_u32 = smem_u32(raw0);
+        float dbsum = 0.f;
+        for (int64_t s = 0; s < my; ++s) {
+            const int rs = (int)(s & 1);
+            const int64_t cbase = (g_begin + s) * DW2_CELLS;
+            const int64_t left = p.n_tgt - cbase;
+            const int nvalid = (int)(left < DW2_CELLS ? left : DW2_CELLS);
+            mbar_wait(&raw_full[rs], (uint32_t)((s >> 1) & 1));
+            const uint32_t rbase = raw_u32 + (uint32_t)rs * raw_stage;
+#pragma unroll
+            for (int hs = 0; hs < 2; ++hs) {
+                float v[16];
+                if (live) {
+                    const uint32_t a0 = rbase + src_off + (uint32_t)(16 * hs) * stride;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float d;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(a0 + (uint32_t)i * stride));
+                        v[i] = d;
+                    }
+                    if (kind == 0 && norm) {
+                        const uint32_t z0 = rbase + src2_off + (uint32_t)(16 * hs) * stride;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float zz;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(zz) : "r"(z0 + (uint32_t)i * stride));
+                            v[i] = fmaf(c0, v[i], -fmaf(zz, c2, c1));
+                        }
+                    } else if (affine) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = act(v[i], c0, c1, relu);
+                    } else if (relu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (nvalid < 16 * hs + 16) {             // tail stage: cells beyond n_tgt contribute nothing
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (16 * hs + i >= nvalid) v[i] = 0.f;
+                    }
+                    if (kind == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dbsum += v[i];
+                    }
+                }
+                mbar_wait(&op_empty[hs], (uint32_t)((s & 1) ^ 1));
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float4 h, l;
+                        split_tf32(v[4 * c], h.x, l.x); split_tf32(v[4 * c + 1], h.y, l.y);
+                        split_tf32(v[4 * c + 2], h.z, l.z); split_tf32(v[4 * c + 3], h.w, l.w);
+                        const uint32_t a = dst_hi + ((((uint32_t)(4 * hs + c)) ^ rsw) << 4);
+                        sts128(a, h);
+                        sts128(a + lo_off, l);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&op_full[hs]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);      // every lane has read its share of the raw stage
+        }
+        // db partial of this CTA (one thread per dz channel, no reduction needed)
+        if (p.db_partials != nullptr && is_a && row_a < p.f_out)
+            p.db_partials[(size_t)blockIdx.x * p.f_out + row_a] = (double)dbsum;
+        // read this CTA's partial out of TMEM: warp w reads TMEM lanes 32 (w & 3) .., column chunks (w >> 2), + 3, ..
+        float* out = p.partials + (size_t)blockIdx.x * p.f_out * p.k_total;
+        const int q = warp & 3, grp = warp >> 2;
+        const int orow = q * 32 + lane;
+        if (my > 0) {
+            mbar_wait(&bar_done, 0);
+            tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int chunk = grp; chunk * 32 < p.np; chunk += DW2_PW / 4) {
+            const int col0 = chunk * 32;
+            float v[32];
+            if (my > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (orow < p.f_out) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int n = col0 + i;
+                    if (n >= p.k_total) continue;
+                    *reinterpret_cast<float4*>(out + (size_t)orow * p.k_total + n) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == DW2_PW) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace dgnn
 
 using namespace dgnn;
@@ -322,6 +572,24 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
     DGNN_REQUIRE(k_total == (agg ? 2 * f_in : f_in), "k_total mismatch");
     DGNN_REQUIRE(dy && x_in && partials, "null pointer");
     DGNN_REQUIRE(n_tgt < (int64_t)1 << 31, "more than 2^31 cells on one GPU");
+#ifndef DGNN_DW_OLD
+    if (f_out <= 128 && k_total <= 256 && (f_out % 4) == 0 && (f_in % 4) == 0) {
+        // row-block kernel: the block is the whole matrix, rows are fetched as contiguous bulk copies
+        Dw2Args q;
+        memset(&q, 0, sizeof(q));
+        q.dy = dy; q.z = g ? z : nullptr; q.ng = g; q.na = a; q.nb = b; q.nmean = mean; q.nrstd = rstd;
+        q.agg = agg; q.x_in = x_in; q.in_scale = in_scale; q.in_shift = in_shift; q.relu_in = relu_in;
+        q.n_tgt = n_tgt; q.f_in = f_in; q.f_out = f_out; q.k_total = k_total; q.np = ceil32i(k_total);
+        q.partials = partials; q.db_partials = db_partials;
+        const size_t raw = (((size_t)DW2_CELLS * 4 * ((size_t)f_out * (g ? 2 : 1) + (size_t)f_in * (agg ? 2 : 1))) + 127) & ~(size_t)127;
+        const size_t smem = 2 * DW_A_BYTES + 2 * (size_t)q.np * 128 + 2 * raw + 1024;
+        if (smem <= 226 * 1024) {
+            if (int rc_ = ensure_dyn_smem((const void*)dw2_tc_kernel, 226 * 1024, "dgnn_dw_bwd_tc")) return rc_;
+            dw2_tc_kernel<<<sm_count(), DW2_THREADS, smem, as_stream(stream)>>>(q);
+            return check_launch("dgnn_dw_bwd_tc");
+        }
+    }
+#endif
     if (int rc_ = ensure_dyn_smem((const void*)dw_tc_kernel, 210 * 1024, "dgnn_dw_bwd_tc")) return rc_;
     DwTcArgs p;
     memset(&p, 0, sizeof(p));
