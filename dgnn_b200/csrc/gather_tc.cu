@@ -748,7 +748,7 @@ struct Dwe2Args {
 };
 
 constexpr int E2_PW = 8;                            // P-producer warps: thread = (feature, half of the 32 cells)
-constexpr int E2_THREADS = (E2_PW + 3) * 32;        // + EA warp + MMA warp + copy warp
+constexpr int E2_THREADS = (E2_PW + 7) * 32;        // + EA warp + MMA warp + stage-copy warp + 4 gather warps
 constexpr int E2_GRING = 6;                         // ring of gathered [32 x F] blocks
 constexpr int E2_CELLS = 32;
 
@@ -772,8 +772,8 @@ __global__ void __launch_bounds__(E2_THREADS, 1) dwe2_tc_kernel(const Dwe2Args p
     uint8_t* g0 = st0 + 2 * st_bytes;
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 33);                                        // expect_tx arrival + the copy warp's 32 cp.async arrivals
-            mbar_init(&s_empty[i], E2_PW + 2);                                // P warps + EA warp + copy warp (reads nbr)
+            mbar_init(&s_full[i], 1);                                         // the stage-copy warp's expect_tx arrival
+            mbar_init(&s_empty[i], E2_PW + 5);                                // P warps + EA warp + 4 gather warps (they read nbr)
             mbar_init(&o_full[i], E2_PW + 1); mbar_init(&o_empty[i], 1);
         }
         for (int i = 0; i < E2_GRING; ++i) { mbar_init(&g_full[i], 32); mbar_init(&g_empty[i], E2_PW); }   // 32 cp.async arrivals
@@ -798,64 +798,52 @@ __global__ void __launch_bounds__(E2_THREADS, 1) dwe2_tc_kernel(const Dwe2Args p
     const int64_t my = g_end > g_begin ? g_end - g_begin : 0;
 
     if (warp == E2_PW + 2) {
-        // ------------------------------------------------------------ copy warp
-        // Rows are fetched with cp.async (one 16-byte piece per lane, 32 / lpr rows per warp instruction) whose completion
-        // is reported on the block's mbarrier by cp.async.mbarrier.arrive.noinc: a bulk copy per row was measured at
-        // ~35 ns each (160 per stage), the whole kernel 2x slower than the round-1 one.  The contiguous EA block and
-        // table rows of a stage stay bulk copies.  Stage s + 1 is requested before stage s is consumed.
+        // ------------------------------------------------------------ stage-copy warp: the contiguous parts of a stage
+        // (z_prev rows, EA block, table rows) as three bulk copies, one stage ahead of its consumers
+        if (lane == 0) {
+            for (int64_t s = 0; s < my; ++s) {
+                const int rs = (int)(s & 1);
+                const int64_t c0 = (g_begin + s) * E2_CELLS;
+                const int64_t left = p.n_rows - c0;
+                const uint32_t rows = (uint32_t)(left < E2_CELLS ? left : E2_CELLS);
+                uint8_t* dst = st0 + (size_t)rs * st_bytes;
+                mbar_wait(&s_empty[rs], (uint32_t)(((s >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&s_full[rs], rows * (row_bytes + 4u * (uint32_t)p.fe * 4u + 16u));
+                bulk_g2s(dst, p.z_prev + (size_t)c0 * p.ld, rows * row_bytes, &s_full[rs]);
+                bulk_g2s(dst + off_ea, p.ea + (size_t)c0 * 4 * p.fe, rows * 4u * (uint32_t)p.fe * 4u, &s_full[rs]);
+                bulk_g2s(dst + off_nb, p.nbr + (size_t)c0 * 4, rows * 16u, &s_full[rs]);
+            }
+        }
+    } else if (warp > E2_PW + 2) {
+        // ------------------------------------------------------------ gather warps, one per slot k: the 32 neighbour rows
+        // of d_agg of (stage, k) go global -> shared with cp.async (16 bytes per lane, 32 / lpr rows per warp instruction)
+        // into block (4 s + k) % E2_GRING of the ring; completion is reported on the block's mbarrier by
+        // cp.async.mbarrier.arrive.noinc.  (One bulk copy per row was measured at ~35 ns each; one warp issuing all four
+        // slots made the whole kernel wait for that warp.)
+        const int k = warp - (E2_PW + 3);
         const int lpr = (int)(row_bytes >> 4);                 // lanes per row
         const int rpi = 32 / lpr;                              // rows per warp instruction
         const int r_in = lane / lpr, c16 = lane - r_in * lpr;
         const bool lane_on = r_in < rpi;
-        auto rows_of = [&](int64_t s) {
-            const int64_t left = p.n_rows - (g_begin + s) * E2_CELLS;
-            return (int)(left < E2_CELLS ? left : E2_CELLS);
-        };
-        auto issue_stage = [&](int64_t s) {
-            const int rs = (int)(s & 1);
-            const int64_t c0 = (g_begin + s) * E2_CELLS;
-            const int rows = rows_of(s);
-            uint8_t* dst = st0 + (size_t)rs * st_bytes;
-            mbar_wait(&s_empty[rs], (uint32_t)(((s >> 1) & 1) ^ 1));
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&s_full[rs], (uint32_t)rows * (4u * (uint32_t)p.fe * 4u + 16u));
-                bulk_g2s(dst + off_ea, p.ea + (size_t)c0 * 4 * p.fe, (uint32_t)rows * 4u * (uint32_t)p.fe * 4u, &s_full[rs]);
-                bulk_g2s(dst + off_nb, p.nbr + (size_t)c0 * 4, (uint32_t)rows * 16u, &s_full[rs]);
-            }
-            for (int r0 = 0; r0 < rows; r0 += rpi) {
-                const int r = r0 + r_in;
-                if (lane_on && r < rows)
-                    cp_async16(dst + (size_t)r * row_bytes + c16 * 16, p.z_prev + (size_t)(c0 + r) * p.ld + c16 * 4);
-            }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[rs])) : "memory");
-        };
-        uint32_t gi = 0;                                       // gathered blocks issued so far
-        if (my > 0) issue_stage(0);
         for (int64_t s = 0; s < my; ++s) {
             const int rs = (int)(s & 1);
-            const int rows = rows_of(s);
-            if (s + 1 < my) issue_stage(s + 1);
-            uint8_t* dst = st0 + (size_t)rs * st_bytes;
-            // the table rows just fetched tell which rows of d_agg to gather
+            const int64_t left = p.n_rows - (g_begin + s) * E2_CELLS;
+            const int rows = (int)(left < E2_CELLS ? left : E2_CELLS);
             mbar_wait(&s_full[rs], (uint32_t)((s >> 1) & 1));
-            int4 nb = make_int4(-1, -1, -1, -1);
-            if (lane < rows) nb = *reinterpret_cast<const int4*>(dst + off_nb + lane * 16);
-            const int nv[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k, ++gi) {
-                const uint32_t g = gi % E2_GRING, gu = gi / E2_GRING;
-                mbar_wait(&g_empty[g], (gu & 1u) ^ 1u);
-                uint8_t* gd = g0 + (size_t)g * g_bytes;
-                for (int r0 = 0; r0 < E2_CELLS; r0 += rpi) {
-                    const int r = r0 + r_in;
-                    const int src = __shfl_sync(0xffffffffu, nv[k], r & 31);
-                    if (lane_on && src >= 0)
-                        cp_async16(gd + (size_t)r * row_bytes + c16 * 16, p.d_agg + (size_t)src * p.ld + c16 * 4);
-                }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&g_full[g])) : "memory");
-            }
+            int nb = -1;
+            if (lane < rows) nb = *reinterpret_cast<const int*>(st0 + (size_t)rs * st_bytes + off_nb + lane * 16 + k * 4);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[rs]);          // this warp's own read of the table rows is done
+            if (lane == 0) mbar_arrive(&s_empty[rs]);          // this warp's read of the table rows is done
+            const uint32_t gi = (uint32_t)(4 * s + k), g = gi % E2_GRING, gu = gi / E2_GRING;
+            mbar_wait(&g_empty[g], (gu & 1u) ^ 1u);
+            uint8_t* gd = g0 + (size_t)g * g_bytes;
+            for (int r0 = 0; r0 < E2_CELLS; r0 += rpi) {
+                const int r = r0 + r_in;
+                const int src = __shfl_sync(0xffffffffu, nb, r & 31);
+                if (lane_on && src >= 0)
+                    cp_async16(gd + (size_t)r * row_bytes + c16 * 16, p.d_agg + (size_t)src * p.ld + c16 * 4);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&g_full[g])) : "memory");
         }
     } else if (warp == E2_PW + 1) {
         // ------------------------------------------------------------ MMA warp: P_k^T . (EA_k^T hi + lo) per (stage, slot)
@@ -1054,7 +1042,7 @@ static int launch_dwe_tc(const GatherTcArgs& p, cudaStream_t st, const char* wha
         const size_t row_bytes = (size_t)p.f * 4, ea_stage = (size_t)E2_CELLS * 4 * p.fe * 4;
         const size_t st_bytes = (E2_CELLS * row_bytes + ((ea_stage + 15) & ~(size_t)15) + 512 + 127) & ~(size_t)127;
         const size_t smem = 2 * G_ATOM + 4 * 32 * 128 + 2 * st_bytes + (size_t)E2_GRING * E2_CELLS * row_bytes + 1024;
-        if (smem <= 226 * 1024) {
+        if (smem <= 226 * 1024 && p.ld == p.f) {          // the stage copies need full-width (contiguous) rows
             if (int rc_ = ensure_dyn_smem((const void*)dwe2_tc_kernel, 226 * 1024, what)) return rc_;
             dwe2_tc_kernel<<<sm_count(), E2_THREADS, smem, st>>>(q);
             return check_launch(what);

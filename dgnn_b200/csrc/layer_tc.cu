@@ -19,6 +19,8 @@
 //   * accumulators are double-buffered in TMEM (2 x N columns): the producer warps run the
 //     epilogue of tile i (tcgen05.ld -> bias / affine / ReLU / BN partials -> global) after they
 //     have produced tile i+1, and hand the buffer back through `acc_free`.
+#include <cuda.h>
+
 #include "umma.cuh"
 #include "common.cuh"
 
@@ -357,10 +359,11 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
 
 // one producer warp's share of a tile epilogue: TMEM lanes 32q..32q+31 (rows), column chunks grp, grp+4, ..
 // st_sum / st_sq: per-lane running column sums (chunk slot j = (chunk - grp)/4), kept across tiles
-template <int MODE>
+// (q = TMEM lane quarter of the calling warp, grp of NGRP = which of the warps sharing the quarter: chunks grp, grp + NGRP, ..)
+template <int MODE, int NGRP = 4>
 __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int64_t tile0, int warp, int lane,
-                                         double (&st_sum)[2], double (&st_sq)[2], const int4 nb) {
-    const int q = warp & 3, grp = warp >> 2;
+                                         double (&st_sum)[8 / NGRP], double (&st_sq)[8 / NGRP], const int4 nb) {
+    const int q = warp & 3, grp = (warp >> 2) % NGRP;
     const int r = q * 32 + lane;
     const int64_t t = tile0 + r;
     const bool tv = t < p.n_tgt;
@@ -372,8 +375,8 @@ __device__ __forceinline__ void epilogue(const TcArgs& p, uint32_t tmem_acc, int
     }
     const bool want_stats = MODE != MODE_BWD && p.stats != nullptr;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int chunk = grp + 4 * j;
+    for (int j = 0; j < 8 / NGRP; ++j) {
+        const int chunk = grp + NGRP * j;
         const int c0 = chunk * 32;
         if (c0 >= p.np) break;
         float v[32];
@@ -645,6 +648,371 @@ __global__ void __launch_bounds__(TC_THREADS, 1) layer_tc_kernel(const TcArgs p)
     if (warp == NPW) tmem_dealloc(tmem_base, 512);
 }
 
+// -----------------------------------------------------------------------------------------------------------------------
+// Dense forward / backward, second formulation: the raw atoms arrive by TMA TENSOR loads.
+//
+// The producers of layer_tc_kernel fetch every raw atom themselves (cp.async or register prefetch, one 16-byte piece per
+// thread with its own address arithmetic) and the kernels measured latency-bound on exactly those loads (ncu: long
+// scoreboard 2.6 / 6.7 stalled warps per issue).  Here one thread issues, per K-atom, ONE cp.async.bulk.tensor.2d
+// (SASS UTMALDG) of the box [128 rows x 32 floats] of agg / x / dy / z through a tensor map with the 128-byte swizzle:
+// the atom lands in shared memory already in the UMMA operand layout, rows and columns beyond the matrix zero-filled,
+// several atoms ahead of its consumers and without a single instruction in the producer warps.
+//   * The landing slot IS the hi operand: kind::tf32 reads the 19 high bits of an operand, so an atom that needs no
+//     arithmetic (the agg half of the forward) is used as it lies and the producers only add lo = v - trunc_tf32(v); atoms
+//     that need the producer affine + ReLU (forward) or the normalisation backward (dy, z -> dz) are rewritten in place
+//     (hi) and into the neighbouring slot (lo; in the backward that slot held z).
+//   * Two rings: A stages (raw -> hi | lo, 32 KB) filled by the TMA-A warp, weight-slice stages filled by the TMA-B warp
+//     from L2; the rings advance independently, so a slow weight slice does not hold back the activation stream.
+//   * MMA warp, double-buffered TMEM accumulators and the epilogue are those of layer_tc_kernel.
+constexpr int D2_NPW = 8, D2_NEW = 8;         // producer warps (operand conversion), epilogue warps (2 per TMEM lane quarter)
+constexpr int D2_WARPS = D2_NPW + D2_NEW;
+constexpr int D2_THREADS = (D2_WARPS + 3) * 32;     // + MMA warp + TMA-A warp + TMA-B warp
+constexpr int D2_MAX_A = 4, D2_MAX_B = 4;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue of dense2_tc_kernel: one warp's share (TMEM lane quarter q, column chunks grp, grp + 2, ..) of a tile goes
+// TMEM -> registers -> (bias / eval affine + ReLU / BN partials | 1/cnt) -> a 4 KB swizzled staging block in shared memory
+// -> ONE TMA tensor store of the [32 rows x 32 columns] box (SASS UTMASTG): full 128-byte lines instead of one 32-byte
+// sector per lane and instruction (the per-row stores of layer_tc_kernel's epilogue cost 4096 separate requests per
+// backward tile and bounded the kernel); rows / columns beyond the matrix are clipped by the tensor map.
+template <int MODE>
+__device__ __forceinline__ void epilogue2(const TcArgs& p, const CUtensorMap* tmo0, const CUtensorMap* tmo1, uint32_t tmem_acc,
+                                          int64_t tile0, int warp, int lane, uint32_t stage, double (&st_sum)[4],
+                                          double (&st_sq)[4], const int4 nb) {
+    const int q = warp & 3, grp = (warp >> 2) & 1;
+    const int64_t t = tile0 + q * 32 + lane;
+    const bool tv = t < p.n_tgt;
+    float icnt = 1.f;
+    if (MODE == MODE_BWD && p.nbr != nullptr && tv) {
+        int cnt = (nb.x >= 0) + (nb.y >= 0) + (nb.z >= 0) + (nb.w >= 0);
+        icnt = 1.f / (float)(cnt > 0 ? cnt : 1);
+    }
+    const bool want_stats = MODE != MODE_BWD && p.stats != nullptr;
+    const uint32_t srow = stage + (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c0 = (grp + 2 * j) * 32;
+        if (c0 >= p.np) break;
+        float v[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        const CUtensorMap* tm = tmo0;
+        int col = c0;
+        if (MODE != MODE_BWD) {
+            if (p.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (c0 + i >= p.f_out) continue;
+                    const float4 bi = ldg4(p.bias + c0 + i);
+                    v[i] += bi.x; v[i + 1] += bi.y; v[i + 2] += bi.z; v[i + 3] += bi.w;
+                }
+            }
+        } else {
+            const int ca = p.n_off + c0;               // column of the chunk inside [d_agg | d_self]
+            const bool is_agg = p.nbr != nullptr && ca < p.f_in;
+            if (is_agg) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] *= icnt;
+            } else {
+                tm = tmo1;
+                col = p.nbr != nullptr ? ca - p.f_in : ca;
+            }
+            if (is_agg) col = ca;
+        }
+        if (lane == 0) tma_store_wait_read();          // the previous box has left the staging block
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (MODE != MODE_BWD) {
+                if (p.out_scale != nullptr && c0 + i < p.f_out) {
+                    const float4 os = ldg4(p.out_scale + c0 + i), oh = ldg4(p.out_shift + c0 + i);
+                    o.x = fmaf(o.x, os.x, oh.x); o.y = fmaf(o.y, os.y, oh.y);
+                    o.z = fmaf(o.z, os.z, oh.z); o.w = fmaf(o.w, os.w, oh.w);
+                }
+                if (p.relu_out) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            }
+            sts128(srow + ((((uint32_t)i >> 2) ^ sw) << 4), o);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(tm, col, (int)(tile0 + q * 32), stage);
+        if (want_stats) {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (!tv) v[i] = 0.f;
+                sq[i] = v[i] * v[i];
+            }
+            st_sum[j] += (double)warp_colsum32(v);
+            st_sq[j] += (double)warp_colsum32(sq);
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(D2_THREADS, 1) dense2_tc_kernel(const TcArgs p, const __grid_constant__ CUtensorMap tm0,
+                                                                  const __grid_constant__ CUtensorMap tm1,
+                                                                  const __grid_constant__ CUtensorMap tmo0,
+                                                                  const __grid_constant__ CUtensorMap tmo1, int a_stages,
+                                                                  int b_stages) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[D2_MAX_A], a_ready[D2_MAX_A], a_empty[D2_MAX_A], b_full[D2_MAX_B], b_empty[D2_MAX_B];
+    __shared__ uint64_t bar_acc_full[2], bar_acc_free[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ double red_st[MODE == MODE_BWD ? 2 : 2 * 256];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int b_atom_bytes = p.np * ATOM_ROW_BYTES;
+    const uint32_t a_base = smem_u32(smem);
+    const uint32_t b_base = a_base + (uint32_t)a_stages * 2u * A_ATOM_BYTES;
+    // coefficient table behind the rings: forward (scale | shift) per column of the x segment, backward (c0 | c1 | c2)
+    // per channel with dz = c0 * dy - (z * c2 + c1); padded columns are the identity
+    // behind the rings: the epilogue warps' staging blocks (4 KB each), then the coefficient table
+    const uint32_t rings = (uint32_t)a_stages * 2u * A_ATOM_BYTES + (uint32_t)b_stages * 2u * (uint32_t)b_atom_bytes;
+    const uint32_t stage_base = a_base + rings;
+    float* tab = reinterpret_cast<float*>(smem + rings + D2_NEW * 4096);
+    const int ka_x = p.ka - p.ka_agg;
+    const int tab_n = (MODE == MODE_BWD ? p.ka : ka_x) * ATOM_K;
+    const bool norm = MODE == MODE_BWD && p.ng != nullptr;
+
+    if (tid == 0) {
+        for (int s = 0; s < D2_MAX_A; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], D2_NPW); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < D2_MAX_B; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_free[b], D2_NEW); }
+        fence_barrier_init();
+    }
+    if (MODE != MODE_BWD)
+        for (int c = tid; c < 512; c += D2_THREADS) red_st[c] = 0.0;
+    for (int c = tid; c < tab_n; c += D2_THREADS) {
+        if (MODE == MODE_BWD) {
+            float c0 = 1.f, c1 = 0.f, c2 = 0.f;
+            if (norm && c < p.f_out) {
+                const float g = __ldg(p.ng + c), a = __ldg(p.na + c), b = __ldg(p.nb + c);
+                const float m = __ldg(p.nmean + c), rs = __ldg(p.nrstd + c);
+                c0 = g; c2 = rs * b; c1 = a - m * c2;
+            }
+            tab[c] = c0; tab[tab_n + c] = c1; tab[2 * tab_n + c] = c2;
+        } else {
+            const bool on = p.in_scale != nullptr && c < p.f_in;
+            tab[c] = on ? __ldg(p.in_scale + c) : 1.f;
+            tab[tab_n + c] = on ? __ldg(p.in_shift + c) : 0.f;
+        }
+    }
+    if (warp == D2_WARPS) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const int64_t n_tiles = (p.n_tgt + TC_M - 1) / TC_M;
+
+    if (warp == D2_WARPS) {
+        // ------------------------------------------------------------------ MMA warp
+        const uint32_t idesc = make_idesc_tf32(TC_M, p.np);
+        uint32_t tile_cnt = 0, sa = 0, ua = 0, sb = 0, ub = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const uint32_t acc = tile_cnt & 1;
+            const uint32_t tmem_acc = tmem_base + acc * (uint32_t)p.np;
+            for (int a = 0; a < p.ka; ++a) {
+                if (lane == 0) {
+                    if (a == 0 && tile_cnt >= 2) mbar_wait(&bar_acc_free[acc], ((tile_cnt >> 1) - 1) & 1);
+                    mbar_wait(&b_full[sb], ub & 1);
+                    mbar_wait(&a_ready[sa], ua & 1);
+                    tc_fence_after_sync();
+                    const uint32_t ah = a_base + sa * 2u * A_ATOM_BYTES, al = ah + A_ATOM_BYTES;
+                    const uint32_t bh = b_base + sb * 2u * (uint32_t)b_atom_bytes, bl = bh + (uint32_t)b_atom_bytes;
+#pragma unroll
+                    for (int kk = 0; kk < ATOM_K / 8; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bh + ko), idesc, (a > 0 || kk > 0) ? 1u : 0u);
+                        mma_tf32(tmem_acc, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
+                        mma_tf32(tmem_acc, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
+                    }
+                    mma_commit(&a_empty[sa]);
+                    mma_commit(&b_empty[sb]);
+                    if (a == p.ka - 1) mma_commit(&bar_acc_full[acc]);
+                }
+                __syncwarp();
+                if (++sa == (uint32_t)a_stages) { sa = 0; ++ua; }
+                if (++sb == (uint32_t)b_stages) { sb = 0; ++ub; }
+            }
+        }
+    } else if (warp == D2_WARPS + 1) {
+        // ------------------------------------------------------------------ TMA-A warp: raw atoms, a ring ahead
+        if (lane == 0) {
+            uint32_t sa = 0, ua = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row0 = (int)(tile * TC_M);
+                for (int a = 0; a < p.ka; ++a) {
+                    const uint32_t slot = a_base + sa * 2u * A_ATOM_BYTES;
+                    mbar_wait(&a_empty[sa], (ua & 1) ^ 1);
+                    if (MODE == MODE_BWD) {
+                        mbar_arrive_expect_tx(&a_full[sa], norm ? 2u * A_ATOM_BYTES : (uint32_t)A_ATOM_BYTES);
+                        tma_load_2d(slot, &tm0, a * ATOM_K, row0, &a_full[sa]);
+                        if (norm) tma_load_2d(slot + A_ATOM_BYTES, &tm1, a * ATOM_K, row0, &a_full[sa]);
+                    } else {
+                        mbar_arrive_expect_tx(&a_full[sa], (uint32_t)A_ATOM_BYTES);
+                        if (a < p.ka_agg) tma_load_2d(slot, &tm0, a * ATOM_K, row0, &a_full[sa]);
+                        else tma_load_2d(slot, &tm1, (a - p.ka_agg) * ATOM_K, row0, &a_full[sa]);
+                    }
+                    if (++sa == (uint32_t)a_stages) { sa = 0; ++ua; }
+                }
+            }
+        }
+    } else if (warp == D2_WARPS + 2) {
+        // ------------------------------------------------------------------ TMA-B warp: weight slices (L2), a ring ahead
+        if (lane == 0) {
+            uint32_t sb = 0, ub = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int a = 0; a < p.ka; ++a) {
+                    uint8_t* b_hi = smem + (size_t)a_stages * 2 * A_ATOM_BYTES + (size_t)sb * 2 * b_atom_bytes;
+                    mbar_wait(&b_empty[sb], (ub & 1) ^ 1);
+#ifdef DGNN_D2_NOB      // timing experiment: weight slices loaded once per ring slot only (wrong results)
+                    if (ub > 0) { mbar_arrive(&b_full[sb]); if (++sb == (uint32_t)b_stages) { sb = 0; ++ub; } continue; }
+#endif
+                    mbar_arrive_expect_tx(&b_full[sb], 2u * (uint32_t)b_atom_bytes);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.b_packed) + (size_t)a * 2 * b_atom_bytes;
+                    bulk_g2s(b_hi, src, 2u * (uint32_t)b_atom_bytes, &b_full[sb]);
+                    if (++sb == (uint32_t)b_stages) { sb = 0; ++ub; }
+                }
+            }
+        }
+    } else if (warp >= D2_NPW) {
+        // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter warp & 3)
+        // tile i's accumulator is read out while the producers and the tensor core are busy with tile i + 1
+        double st_sum[4] = {0.0, 0.0, 0.0, 0.0}, st_sq[4] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t tile_cnt = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const int64_t tile0 = tile * TC_M;
+            int4 nb_epi = make_int4(-1, -1, -1, -1);
+            if (MODE == MODE_BWD && p.nbr != nullptr) {  // the row of the ELL table (1 / cnt of d_agg), in flight during the wait
+                const int64_t t = tile0 + (warp & 3) * 32 + lane;
+                if (t < p.n_tgt) nb_epi = __ldg(reinterpret_cast<const int4*>(p.nbr) + t);
+            }
+            const uint32_t acc = tile_cnt & 1;
+            mbar_wait(&bar_acc_full[acc], (tile_cnt >> 1) & 1);
+            tc_fence_after_sync();
+#ifndef DGNN_D2_NOEPI   // timing experiment: no epilogue at all (no results)
+            epilogue2<MODE>(p, &tmo0, &tmo1, tmem_base + acc * (uint32_t)p.np, tile0, warp, lane,
+                            stage_base + (uint32_t)(warp - D2_NPW) * 4096u, st_sum, st_sq, nb_epi);
+#endif
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_free[acc]);
+        }
+        if (lane == 0) tma_store_wait_all();
+        if (MODE != MODE_BWD && p.stats != nullptr) {
+            const int grp = (warp >> 2) & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (grp + 2 * j) * 32 + lane;
+                if (c < p.f_out) {
+                    atomicAdd(&red_st[c], st_sum[j]);
+                    atomicAdd(&red_st[256 + c], st_sq[j]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ producer warps
+        uint32_t sa = 0, ua = 0;
+        // this thread's four 16-byte pieces of every atom: rows 16 warp + (lane >> 3) + 4 i, chunk lane & 7
+        const uint32_t r0 = (uint32_t)(warp * 16 + (lane >> 3)), ch = (uint32_t)(lane & 7);
+        uint32_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) off[i] = (r0 + 4u * i) * 128u + ((ch ^ ((r0 + 4u * i) & 7u)) << 4);
+        const uint32_t tab_u32 = smem_u32(tab) + ch * 16u;
+        const bool relu = p.relu_in != 0;
+        const bool affine = p.in_scale != nullptr;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int a = 0; a < p.ka; ++a) {
+                const uint32_t hi = a_base + sa * 2u * A_ATOM_BYTES, lo = hi + A_ATOM_BYTES;
+                mbar_wait(&a_full[sa], ua & 1);
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = lds128(hi + off[i]);
+                if (MODE == MODE_BWD) {
+                    if (norm) {
+                        const uint32_t t = tab_u32 + (uint32_t)a * 128u;
+                        const float4 c0 = lds128(t), c1 = lds128(t + (uint32_t)tab_n * 4u), c2 = lds128(t + (uint32_t)tab_n * 8u);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 z = lds128(lo + off[i]);
+                            v[i].x = fmaf(c0.x, v[i].x, -fmaf(z.x, c2.x, c1.x)); v[i].y = fmaf(c0.y, v[i].y, -fmaf(z.y, c2.y, c1.y));
+                            v[i].z = fmaf(c0.z, v[i].z, -fmaf(z.z, c2.z, c1.z)); v[i].w = fmaf(c0.w, v[i].w, -fmaf(z.w, c2.w, c1.w));
+                        }
+                    }
+                } else if (a >= p.ka_agg) {
+                    if (affine) {
+                        const uint32_t t = tab_u32 + (uint32_t)(a - p.ka_agg) * 128u;
+                        const float4 sc = lds128(t), sh = lds128(t + (uint32_t)tab_n * 4u);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            v[i].x = act(v[i].x, sc.x, sh.x, relu); v[i].y = act(v[i].y, sc.y, sh.y, relu);
+                            v[i].z = act(v[i].z, sc.z, sh.z, relu); v[i].w = act(v[i].w, sc.w, sh.w, relu);
+                        }
+                    } else if (relu) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f);
+                        }
+                    }
+                }
+                const bool in_place = MODE != MODE_BWD ? (a < p.ka_agg || (!affine && !relu)) : !norm;
+                if (in_place) {
+                    // the raw atom is the hi operand (the tensor core drops the 13 low mantissa bits): only lo is written
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 l;
+                        // lo = v - trunc_tf32(v) is up to 2^-10 |v|: rounded (not truncated by the tensor core) to TF32, so the
+                        // pair carries v to 2^-21 like the hi = rna_tf32(v) split does
+                        l.x = tf32_rna(v[i].x - __uint_as_float(__float_as_uint(v[i].x) & 0xffffe000u));
+                        l.y = tf32_rna(v[i].y - __uint_as_float(__float_as_uint(v[i].y) & 0xffffe000u));
+                        l.z = tf32_rna(v[i].z - __uint_as_float(__float_as_uint(v[i].z) & 0xffffe000u));
+                        l.w = tf32_rna(v[i].w - __uint_as_float(__float_as_uint(v[i].w) & 0xffffe000u));
+                        sts128(lo + off[i], l);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 h, l;
+                        split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
+                        sts128(hi + off[i], h);
+                        sts128(lo + off[i], l);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[sa]);
+                if (++sa == (uint32_t)a_stages) { sa = 0; ++ua; }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (MODE != MODE_BWD && p.stats != nullptr) {
+        double* my = p.stats + (size_t)blockIdx.x * 2 * p.stats_ld;
+        for (int c = tid; c < p.f_out; c += D2_THREADS) {
+            my[c] = red_st[c];
+            my[p.stats_ld + c] = red_st[256 + c];
+        }
+    }
+    if (warp == D2_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- weight packing: w[n, k] (row stride ld) -> per K-atom swizzled hi / lo images ---------------
 // Rows are packed in slices of `slice` rows (= one launch's N): slice s holds [KA][2][np_s][32] with np_s = its padded rows.
 constexpr int TC_NSLICE = 256;      // backward: N = columns of [d_agg | d_self] per launch (2 stages of 96 KB)
@@ -746,6 +1114,93 @@ static int fwd_slices(TcArgs p, int f_out, bool gather, int raw_ring, cudaStream
     return 0;
 }
 
+// ---- tensor maps for the raw atoms (driver entry point resolved through the runtime: the library does not link libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encode_fn() {
+    static TmapEncodeFn fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TmapEncodeFn>(ptr);
+    }
+    return fn;
+}
+// fp32 matrix [rows x cols], row stride ld floats; box = one K-atom of a 128-row tile, 128-byte swizzle, zero fill
+static int make_tmap_atoms(CUtensorMap* tm, const float* base, int64_t rows, int cols, int ld, const char* what,
+                           int box_rows = TC_M) {
+    TmapEncodeFn enc = tmap_encode_fn();
+    if (enc == nullptr) return fail(what, "cuTensorMapEncodeTiled is not available from this driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0) return fail(what, "matrix not 16-byte aligned");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)ATOM_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(what, "cuTensorMapEncodeTiled failed");
+    return 0;
+}
+
+// ring depths of dense2_tc_kernel: as many raw (A) stages as fit next to >= 2 weight-slice stages (and the staging blocks)
+static int d2_stage_config(int np, int tab_floats, int static_bytes, int staging, int* a_stages, int* b_stages, size_t* smem) {
+    const int budget = 227 * 1024 - static_bytes - 1024 - tab_floats * 4 - staging;
+    const int a_bytes = 2 * A_ATOM_BYTES, b_bytes = 2 * np * ATOM_ROW_BYTES;
+    int a = D2_MAX_A, b = 0;
+    for (; a >= 2; --a) {
+        b = (budget - a * a_bytes) / b_bytes;
+        if (b >= 2) break;
+    }
+    if (a < 2) { a = 2; b = (budget - a * a_bytes) / b_bytes; }
+    if (b < 1) return 1;
+    if (b > D2_MAX_B) b = D2_MAX_B;
+    if (b > a) b = a;
+    *a_stages = a; *b_stages = b;
+    *smem = (size_t)a * a_bytes + (size_t)b * b_bytes + (size_t)tab_floats * 4 + staging + 1024;
+    return 0;
+}
+
+// tmo0 / tmo1: tensor maps of the outputs (forward: the z slice; backward: d_agg, d_self)
+template <int MODE>
+static int launch_d2(const TcArgs& p, const CUtensorMap& tm0, const CUtensorMap& tm1, const CUtensorMap& tmo0,
+                     const CUtensorMap& tmo1, cudaStream_t st, const char* what) {
+    const int tab = (MODE == MODE_BWD ? 3 * p.ka : 2 * (p.ka - p.ka_agg)) * ATOM_K;
+    int a_st, b_st;
+    size_t smem;
+    if (d2_stage_config(p.np, tab, MODE == MODE_BWD ? 512 : 4608, D2_NEW * 4096, &a_st, &b_st, &smem))
+        return fail(what, "tile does not fit shared memory");
+    if (int rc_ = ensure_dyn_smem((const void*)dense2_tc_kernel<MODE>, 227 * 1024 - (MODE == MODE_BWD ? 512 : 4608), what)) return rc_;
+    dense2_tc_kernel<MODE><<<sm_count(), D2_THREADS, smem, st>>>(p, tm0, tm1, tmo0, tmo1, a_st, b_st);
+    return check_launch(what);
+}
+
+// dense forward through dense2_tc_kernel, one launch per slice of <= TC_FWD_SLICE output columns
+static int fwd_slices_d2(TcArgs p, int f_out, cudaStream_t st, const char* what) {
+    CUtensorMap tm_agg, tm_x;
+    if (int rc = make_tmap_atoms(&tm_x, p.x_in, p.n_tgt, p.f_in, p.f_in, what)) return rc;
+    if (p.agg_in != nullptr) { if (int rc = make_tmap_atoms(&tm_agg, p.agg_in, p.n_tgt, p.f_in, p.f_in, what)) return rc; }
+    else tm_agg = tm_x;
+    const float* bias = p.bias; const float* osc = p.out_scale; const float* osh = p.out_shift;
+    float* out = p.out; double* stats = p.stats; const float* bp = p.b_packed;
+    p.out_ld = f_out; p.stats_ld = f_out;
+    for (int n0 = 0; n0 < f_out; n0 += TC_FWD_SLICE) {
+        const int w = f_out - n0 < TC_FWD_SLICE ? f_out - n0 : TC_FWD_SLICE;
+        p.f_out = w; p.np = ceil32(w);
+        p.bias = bias ? bias + n0 : nullptr;
+        p.out_scale = osc ? osc + n0 : nullptr; p.out_shift = osh ? osh + n0 : nullptr;
+        p.out = out + n0; p.stats = stats ? stats + n0 : nullptr;
+        p.b_packed = bp + (size_t)(n0 / TC_FWD_SLICE) * p.ka * 2 * TC_FWD_SLICE * ATOM_K;
+        CUtensorMap tm_out;                            // the slice's columns of z: [n_tgt x w], row stride f_out
+        if (int rc = make_tmap_atoms(&tm_out, p.out, p.n_tgt, w, f_out, what, 32)) return rc;
+        if (int rc = launch_d2<MODE_FWD_DENSE>(p, tm_agg, tm_x, tm_out, tm_out, st, what)) return rc;
+    }
+    return 0;
+}
+
 extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
                                  const int32_t* nbr, const float* ea, int fe, const float* w_e, const float* b_e,
                                  const float* b_packed, const float* bias, const float* out_scale,
@@ -767,6 +1222,9 @@ extern "C" int dgnn_layer_fwd_tc(const float* x_in, const float* in_scale, const
     p.out = out; p.agg_save = agg_save; p.stats = stats;
     cudaStream_t st = as_stream(stream);
     const char* what = "dgnn_layer_fwd_tc";
+#ifndef DGNN_DENSE_OLD
+    if (nbr == nullptr) return fwd_slices_d2(p, f_out, st, what);
+#endif
     if (nbr == nullptr) return fwd_slices<MODE_FWD_DENSE, 0>(p, f_out, false, RAW_DEPTH * A_ATOM_BYTES, st, what);
     switch (fe) {
         case 0: return fwd_slices<MODE_FWD_GATHER, 0>(p, f_out, true, 0, st, what);
@@ -799,6 +1257,9 @@ extern "C" int dgnn_dense_fwd_tc(const float* agg, const float* x_in, const floa
     p.n_tgt = n_tgt; p.f_in = f_in;
     p.bias = bias; p.out_scale = out_scale; p.out_shift = out_shift; p.relu_out = relu_out;
     p.out = out; p.stats = stats;
+#ifndef DGNN_DENSE_OLD
+    return fwd_slices_d2(p, f_out, as_stream(stream), "dgnn_dense_fwd_tc");
+#endif
     return fwd_slices<MODE_FWD_DENSE, 0>(p, f_out, false, RAW_DEPTH * A_ATOM_BYTES, as_stream(stream), "dgnn_dense_fwd_tc");
 }
 
@@ -819,11 +1280,31 @@ extern "C" int dgnn_dense_bwd_tc(const float* dy, const float* z, const float* g
     p.d_agg = d_agg; p.d_self = d_self;
     p.n_total = n_real;
     cudaStream_t st = as_stream(stream);
+#ifndef DGNN_DENSE_OLD
+    // dense2_tc_kernel: the column sums of dz (db) come from the dW kernel, and the 32-column chunks of [d_agg | d_self] must
+    // not straddle the two matrices (tensor-store epilogue); everything else stays on layer_tc_kernel
+    const bool use_d2 = db_partials == nullptr && (f_in % 32 == 0 || nbr == nullptr);
+#else
+    const bool use_d2 = false;
+#endif
+    CUtensorMap tm_dy, tm_z, tm_dagg, tm_dself;
+    if (use_d2) {
+        if (int rc = make_tmap_atoms(&tm_dy, dy, n_tgt, f_out, f_out, "dgnn_dense_bwd_tc")) return rc;
+        if (g != nullptr) { if (int rc = make_tmap_atoms(&tm_z, z, n_tgt, f_out, f_out, "dgnn_dense_bwd_tc")) return rc; }
+        else tm_z = tm_dy;
+        if (int rc = make_tmap_atoms(&tm_dself, d_self, n_tgt, f_in, f_in, "dgnn_dense_bwd_tc", 32)) return rc;
+        if (nbr != nullptr) { if (int rc = make_tmap_atoms(&tm_dagg, d_agg, n_tgt, f_in, f_in, "dgnn_dense_bwd_tc", 32)) return rc; }
+        else tm_dagg = tm_dself;
+    }
     for (int n0 = 0; n0 < n_real; n0 += TC_NSLICE) {
         const int w = n_real - n0 < TC_NSLICE ? n_real - n0 : TC_NSLICE;
         p.np = ceil32(w); p.n_off = n0;
         p.b_packed = b_packed + (size_t)(n0 / TC_NSLICE) * p.ka * 2 * TC_NSLICE * ATOM_K;
         p.db_partials = n0 == 0 ? db_partials : nullptr;
+        if (use_d2) {
+            if (int rc = launch_d2<MODE_BWD>(p, tm_dy, tm_z, tm_dagg, tm_dself, st, "dgnn_dense_bwd_tc")) return rc;
+            continue;
+        }
         size_t smem;
         DGNN_REQUIRE(tc_stage_config(p.np, false, &p.stages, &smem) == 0, "tile does not fit shared memory");
         if (int rc = launch_tc<MODE_BWD, 0>(p, smem, st, "dgnn_dense_bwd_tc")) return rc;
