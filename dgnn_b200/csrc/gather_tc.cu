@@ -35,6 +35,10 @@ constexpr int G_M = 128;
 constexpr int G_EA_STAGES = 2;                       // EA operand ring (hi | lo per stage)
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
 constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
+#ifndef DGNN_PF_AHEAD
+#define DGNN_PF_AHEAD 2
+#endif
+constexpr int G_PF_AHEAD = DGNN_PF_AHEAD;              // L2 prefetch distance in tiles of this CTA
 constexpr int DWE_ROUNDS = 1;                        // dW_e: 1 = P rounded to TF32 once, 2 = P split hi / lo (see dwe_tc_kernel)
 
 struct GatherTcArgs {
@@ -101,6 +105,15 @@ __device__ __forceinline__ void act8(float4& a, float4& b, const float4& sa, con
         a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
         b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
     }
+}
+
+// L2 prefetch of a contiguous byte range, one 128-byte line per thread and instruction (no register result, nothing to wait
+// for): the tile after next is pulled from DRAM into L2 while this one is computed, so the register / cp.async loads that
+// feed the pipeline one item ahead see L2 latency instead of DRAM latency.
+__device__ __forceinline__ void l2_prefetch_range(const void* base, size_t bytes, int tid, int nthreads) {
+    const char* b = reinterpret_cast<const char*>(base);
+    for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)nthreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -314,6 +327,21 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
             const bool tv = t < p.n_rows;
             const int4 nbn4 = load_nbr(tc + 1);        // neighbours of the next tile (its first copy is issued in this one)
             const int nbn[4] = {nbn4.x, nbn4.y, nbn4.z, nbn4.w};
+#ifdef DGNN_L2_PREFETCH        // measured on B200: slower (10.9 vs 10.4 us forward, 14.8 vs 12.2 us backward): the loads are not DRAM-latency bound
+            if (tc + G_PF_AHEAD < n_my) {              // this CTA's tile G_PF_AHEAD tiles on: DRAM -> L2 now
+                const int64_t r0 = tile_of(tc + G_PF_AHEAD) * G_M;
+                const int64_t left = p.n_rows - r0;
+                const size_t rows = (size_t)(left < G_M ? left : G_M);
+                l2_prefetch_range(p.ea + (size_t)r0 * 4 * p.fe, rows * 4 * p.fe * 4, tid, G_THREADS);
+                l2_prefetch_range(p.nbr + (size_t)r0 * 4, rows * 16, tid, G_THREADS);
+                if (p.ld == p.f) {                     // full-width rows are contiguous
+                    l2_prefetch_range(p.x + (size_t)r0 * p.ld, rows * p.ld * 4, tid, G_THREADS);
+                    if (MODE == 1 && p.z_prev != nullptr) l2_prefetch_range(p.z_prev + (size_t)r0 * p.ld, rows * p.ld * 4, tid, G_THREADS);
+                    if (MODE == 1 && p.addend != nullptr && r0 + (int64_t)rows <= p.n_add_rows)
+                        l2_prefetch_range(p.addend + (size_t)r0 * p.ld, rows * p.ld * 4, tid, G_THREADS);
+                }
+            }
+#endif
             const int cnt = (nbv[0] >= 0) + (nbv[1] >= 0) + (nbv[2] >= 0) + (nbv[3] >= 0);
             const float rcnt = cnt > 1 ? (cnt == 2 ? 0.5f : (cnt == 3 ? (1.0f / 3.0f) : 0.25f)) : 1.0f;   // 1 / max(cnt, 1)
             float acc[CPT];
@@ -492,6 +520,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
 
 // ---------------------------------------------------------------------------------------------------
 // dW_e / db_e = P^T . EA over all edges, P[edge, f] = h(s)[f] * d_agg[onbr[s,k]][f], 3xTF32 (P and EA both split).
+// (A row-block formulation like dw2_tc_kernel - bulk-copied z / EA stages, dedicated gather warps filling a ring of
+// [32 x F] blocks, transposition by addressing - measured 16 - 23 us per 128 cells against 11.3 us here, independent of F:
+// four operand hand-offs per 32-cell stage through the tensor core and back bound it, not the bytes.  Not kept.)
 // Per row quarter q one operand stage (P^T [128 features x 32 cells], hi then lo | EA^T hi | EA^T lo); the strips a warp
 // needs (its rows' z_prev strip, then the four gathered d_agg strips) arrive through the same warp-private
 // cp.async ring as in gather_tc_kernel, one item ahead, so no load is waited for in registers.
@@ -580,6 +611,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
             const bool tv = t < p.n_rows;
             const int4 nbn4 = load_nbr(tc + 1);
             const int nbn[4] = {nbn4.x, nbn4.y, nbn4.z, nbn4.w};
+#ifdef DGNN_L2_PREFETCH        // measured on B200: slower (10.9 vs 10.4 us forward, 14.8 vs 12.2 us backward): the loads are not DRAM-latency bound
+            if (tc + G_PF_AHEAD < n_my) {              // this CTA's tile G_PF_AHEAD tiles on: DRAM -> L2 now
+                const int64_t r0 = tile_of(tc + G_PF_AHEAD) * G_M;
+                const int64_t left = p.n_rows - r0;
+                const size_t rows = (size_t)(left < G_M ? left : G_M);
+                l2_prefetch_range(p.ea + (size_t)r0 * 4 * p.fe, rows * 4 * p.fe * 4, tid, G_THREADS);
+                l2_prefetch_range(p.nbr + (size_t)r0 * 4, rows * 16, tid, G_THREADS);
+                if (p.ld == p.f) {
+                    l2_prefetch_range(p.x + (size_t)r0 * p.ld, rows * p.ld * 4, tid, G_THREADS);
+                    l2_prefetch_range(p.z_prev + (size_t)r0 * p.ld, rows * p.ld * 4, tid, G_THREADS);
+                }
+            }
+#endif
             float h[CPT];
             float4 ev[2];
             auto load_ev = [&](int k) {                // this warp's share of the EA row of slot k (global, one item ahead)
@@ -719,283 +763,6 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
 }
 
 
-// -----------------------------------------------------------------------------------------------------------------------
-// dW_e / db_e, second formulation ("row-block" kernel, same idea as dw2_tc_kernel in dw_tc.cu).
-//
-// A stage is 32 consecutive source cells.  A copy warp fetches with bulk copies (cp.async.bulk -> UBLKCP) the stage's
-// z_prev rows, its EA block (32 cells x 4 slots x fe floats, contiguous) and its rows of the out-edge table, reads the
-// table back and gathers, slot by slot, the 32 neighbour rows of d_agg (one bulk copy per row) into a ring of
-// [32 cells x F] blocks.  The operands of  dW_e[f, e] += sum_cells P_k[cell, f] * EA_k[cell, e]  need the cell index
-// contiguous; the transposition is done by addressing: a P-producer thread owns one feature f and 16 cells - it reads
-// its feature of the 16 gathered rows with LDS.32 (lanes = consecutive features: conflict-free), multiplies by h(cell)[f]
-// (kept in registers for the four slots), rounds to TF32 and writes four 16-byte chunks of operand row f; one more warp
-// does the same for EA^T (thread = edge feature e, hi / lo).  No shuffles, no scattered 4-byte stores.
-// One accumulator [128 x 32] in TMEM, stages and slots accumulated in order: bitwise reproducible.
-struct Dwe2Args {
-    const float* d_agg;     // rows to gather (row stride ld)
-    const int32_t* nbr;     // [n_rows,4] out-edge table
-    const float* ea;        // [n_rows,4,fe]
-    const float* z_prev;    // [n_rows, ld]
-    const float* p_scale;   // producer norm affine, may be NULL
-    const float* p_shift;
-    int p_relu;
-    int fe;
-    int64_t n_rows;
-    int f;                  // feature width of this slice (<= 128, multiple of 4)
-    int ld;                 // row stride of d_agg / z_prev
-    int s_ld;               // rows of the dW_e partials per CTA (full width)
-    float* dwe_partials;    // [grid, s_ld, 32]
-};
-
-constexpr int E2_PW = 8;                            // P-producer warps: thread = (feature, half of the 32 cells)
-constexpr int E2_THREADS = (E2_PW + 7) * 32;        // + EA warp + MMA warp + stage-copy warp + 4 gather warps
-constexpr int E2_GRING = 6;                         // ring of gathered [32 x F] blocks
-constexpr int E2_CELLS = 32;
-
-__global__ void __launch_bounds__(E2_THREADS, 1) dwe2_tc_kernel(const Dwe2Args p) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t s_full[2], s_empty[2], g_full[E2_GRING], g_empty[E2_GRING], o_full[2], o_empty[2], bar_done;
-    __shared__ uint32_t tmem_slot;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t row_bytes = (uint32_t)p.f * 4u;
-    const uint32_t ea_stage = (uint32_t)E2_CELLS * 4u * (uint32_t)p.fe * 4u;
-    // operands: P^T [2][128 x 128 B] | EA^T hi [2][32 x 128 B] | EA^T lo [2][32 x 128 B]
-    uint8_t* op_p = smem;
-    uint8_t* op_eh = op_p + 2 * G_ATOM;
-    uint8_t* op_el = op_eh + 2 * 32 * 128;
-    // stage ring: z rows | EA block | nbr rows
-    const uint32_t off_ea = (uint32_t)E2_CELLS * row_bytes, off_nb = off_ea + ((ea_stage + 15u) & ~15u);
-    const uint32_t st_bytes = (off_nb + 512u + 127u) & ~127u;
-    uint8_t* st0 = op_el + 2 * 32 * 128;
-    const uint32_t g_bytes = (uint32_t)E2_CELLS * row_bytes;
-    uint8_t* g0 = st0 + 2 * st_bytes;
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&s_full[i], 1);                                         // the stage-copy warp's expect_tx arrival
-            mbar_init(&s_empty[i], E2_PW + 5);                                // P warps + EA warp + 4 gather warps (they read nbr)
-            mbar_init(&o_full[i], E2_PW + 1); mbar_init(&o_empty[i], 1);
-        }
-        for (int i = 0; i < E2_GRING; ++i) { mbar_init(&g_full[i], 32); mbar_init(&g_empty[i], E2_PW); }   // 32 cp.async arrivals
-        mbar_init(&bar_done, 1);
-        fence_barrier_init();
-    }
-    for (int i = tid; i < (2 * G_ATOM + 4 * 32 * 128) / 16; i += E2_THREADS)
-        reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // row fe of both EA^T hi buffers is all ones: column fe of the accumulator collects db_e = sum of P
-    if (tid < 64) *reinterpret_cast<float*>(op_eh + (size_t)(tid >> 5) * 32 * 128 + atom_off(p.fe, tid & 31)) = 1.0f;
-    fence_proxy_async_smem();
-    if (warp == E2_PW + 1) tmem_alloc(&tmem_slot, 32);
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = tmem_slot;
-    const int64_t n_groups = (p.n_rows + E2_CELLS - 1) / E2_CELLS;
-    const int64_t per = (n_groups + gridDim.x - 1) / gridDim.x;
-    const int64_t g_begin = (int64_t)blockIdx.x * per;
-    const int64_t g_end = g_begin + per < n_groups ? g_begin + per : n_groups;
-    const int64_t my = g_end > g_begin ? g_end - g_begin : 0;
-
-    if (warp == E2_PW + 2) {
-        // ------------------------------------------------------------ stage-copy warp: the contiguous parts of a stage
-        // (z_prev rows, EA block, table rows) as three bulk copies, one stage ahead of its consumers
-        if (lane == 0) {
-            for (int64_t s = 0; s < my; ++s) {
-                const int rs = (int)(s & 1);
-                const int64_t c0 = (g_begin + s) * E2_CELLS;
-                const int64_t left = p.n_rows - c0;
-                const uint32_t rows = (uint32_t)(left < E2_CELLS ? left : E2_CELLS);
-                uint8_t* dst = st0 + (size_t)rs * st_bytes;
-                mbar_wait(&s_empty[rs], (uint32_t)(((s >> 1) & 1) ^ 1));
-                mbar_arrive_expect_tx(&s_full[rs], rows * (row_bytes + 4u * (uint32_t)p.fe * 4u + 16u));
-                bulk_g2s(dst, p.z_prev + (size_t)c0 * p.ld, rows * row_bytes, &s_full[rs]);
-                bulk_g2s(dst + off_ea, p.ea + (size_t)c0 * 4 * p.fe, rows * 4u * (uint32_t)p.fe * 4u, &s_full[rs]);
-                bulk_g2s(dst + off_nb, p.nbr + (size_t)c0 * 4, rows * 16u, &s_full[rs]);
-            }
-        }
-    } else if (warp > E2_PW + 2) {
-        // ------------------------------------------------------------ gather warps, one per slot k: the 32 neighbour rows
-        // of d_agg of (stage, k) go global -> shared with cp.async (16 bytes per lane, 32 / lpr rows per warp instruction)
-        // into block (4 s + k) % E2_GRING of the ring; completion is reported on the block's mbarrier by
-        // cp.async.mbarrier.arrive.noinc.  (One bulk copy per row was measured at ~35 ns each; one warp issuing all four
-        // slots made the whole kernel wait for that warp.)
-        const int k = warp - (E2_PW + 3);
-        const int lpr = (int)(row_bytes >> 4);                 // lanes per row
-        const int rpi = 32 / lpr;                              // rows per warp instruction
-        const int r_in = lane / lpr, c16 = lane - r_in * lpr;
-        const bool lane_on = r_in < rpi;
-        for (int64_t s = 0; s < my; ++s) {
-            const int rs = (int)(s & 1);
-            const int64_t left = p.n_rows - (g_begin + s) * E2_CELLS;
-            const int rows = (int)(left < E2_CELLS ? left : E2_CELLS);
-            mbar_wait(&s_full[rs], (uint32_t)((s >> 1) & 1));
-            int nb = -1;
-            if (lane < rows) nb = *reinterpret_cast<const int*>(st0 + (size_t)rs * st_bytes + off_nb + lane * 16 + k * 4);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[rs]);          // this warp's read of the table rows is done
-            const uint32_t gi = (uint32_t)(4 * s + k), g = gi % E2_GRING, gu = gi / E2_GRING;
-            mbar_wait(&g_empty[g], (gu & 1u) ^ 1u);
-            uint8_t* gd = g0 + (size_t)g * g_bytes;
-            for (int r0 = 0; r0 < E2_CELLS; r0 += rpi) {
-                const int r = r0 + r_in;
-                const int src = __shfl_sync(0xffffffffu, nb, r & 31);
-                if (lane_on && src >= 0)
-                    cp_async16(gd + (size_t)r * row_bytes + c16 * 16, p.d_agg + (size_t)src * p.ld + c16 * 4);
-            }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&g_full[g])) : "memory");
-        }
-    } else if (warp == E2_PW + 1) {
-        // ------------------------------------------------------------ MMA warp: P_k^T . (EA_k^T hi + lo) per (stage, slot)
-        const uint32_t idesc = make_idesc_tf32(G_M, 32);
-        if (lane == 0) {
-            uint32_t oi = 0;
-            for (int64_t s = 0; s < my; ++s) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k, ++oi) {
-                    const uint32_t o = oi & 1u;
-                    mbar_wait(&o_full[o], (oi >> 1) & 1u);
-                    tc_fence_after_sync();
-                    const uint32_t ph = smem_u32(op_p) + o * G_ATOM, eh = smem_u32(op_eh) + o * 32 * 128, el = smem_u32(op_el) + o * 32 * 128;
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t ko = kk * 32;
-                        mma_tf32(tmem_base, make_desc(ph + ko), make_desc(eh + ko), idesc, (oi > 0 || kk > 0) ? 1u : 0u);
-                        mma_tf32(tmem_base, make_desc(ph + ko), make_desc(el + ko), idesc, 1u);
-                    }
-                    mma_commit(&o_empty[o]);
-                }
-            }
-            if (my > 0) mma_commit(&bar_done);
-        }
-    } else if (warp == E2_PW) {
-        // ------------------------------------------------------------ EA^T producer: thread = edge feature e, 32 cells
-        const int e = lane;
-        const bool live = e < p.fe;
-        const uint32_t rsw = (uint32_t)(e & 7);
-        uint32_t oi = 0;
-        for (int64_t s = 0; s < my; ++s) {
-            const int rs = (int)(s & 1);
-            const int64_t left = p.n_rows - (g_begin + s) * E2_CELLS;
-            const int rows = (int)(left < E2_CELLS ? left : E2_CELLS);
-            mbar_wait(&s_full[rs], (uint32_t)((s >> 1) & 1));
-            const uint32_t base = smem_u32(st0) + (uint32_t)rs * st_bytes;
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k, ++oi) {
-                const uint32_t o = oi & 1u;
-                float v[32];
-                if (live) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        float d;
-                        int nbk;
-                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(base + off_ea + (uint32_t)((c * 4 + k) * p.fe + e) * 4u));
-                        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(nbk) : "r"(base + off_nb + (uint32_t)(c * 4 + k) * 4u));
-                        v[c] = (c < rows && nbk >= 0) ? d : 0.f;
-                    }
-                }
-                mbar_wait(&o_empty[o], ((oi >> 1) & 1u) ^ 1u);
-                if (live) {
-                    const uint32_t dh = smem_u32(op_eh) + o * 32 * 128 + (uint32_t)e * 128u, dl = smem_u32(op_el) + o * 32 * 128 + (uint32_t)e * 128u;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float4 h, l;
-                        split_tf32(v[4 * c], h.x, l.x); split_tf32(v[4 * c + 1], h.y, l.y);
-                        split_tf32(v[4 * c + 2], h.z, l.z); split_tf32(v[4 * c + 3], h.w, l.w);
-                        const uint32_t off = (((uint32_t)c) ^ rsw) << 4;
-                        sts128(dh + off, h);
-                        sts128(dl + off, l);
-                    }
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&o_full[o]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[rs]);
-        }
-    } else {
-        // ------------------------------------------------------------ P producers: thread = (feature f, 16 cells)
-        const int f = tid & 127, half = tid >> 7;              // warps 0-3: cells 0-15, warps 4-7: cells 16-31
-        const bool live = f < p.f;
-        float sc = 1.f, sh = 0.f;
-        if (live && p.p_scale != nullptr) { sc = __ldg(p.p_scale + f); sh = __ldg(p.p_shift + f); }
-        const bool relu = p.p_relu != 0;
-        const uint32_t rsw = (uint32_t)(f & 7);
-        uint32_t oi = 0, gi = 0;
-        for (int64_t s = 0; s < my; ++s) {
-            const int rs = (int)(s & 1);
-            const int64_t left = p.n_rows - (g_begin + s) * E2_CELLS;
-            const int rows = (int)(left < E2_CELLS ? left : E2_CELLS);
-            mbar_wait(&s_full[rs], (uint32_t)((s >> 1) & 1));
-            const uint32_t base = smem_u32(st0) + (uint32_t)rs * st_bytes;
-            float h[16];
-            uint32_t okm[4] = {0u, 0u, 0u, 0u};               // bit c of okm[k]: edge (cell 16 half + c, slot k) exists
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const int cell = 16 * half + c;
-                float zz = 0.f;
-                if (live) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(zz) : "r"(base + (uint32_t)cell * row_bytes + (uint32_t)f * 4u));
-                h[c] = act(zz, sc, sh, relu);
-                int4 nb;
-                asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(nb.x), "=r"(nb.y), "=r"(nb.z), "=r"(nb.w) : "r"(base + off_nb + (uint32_t)cell * 16u));
-                const bool in = cell < rows;
-                okm[0] |= (uint32_t)(in && nb.x >= 0) << c; okm[1] |= (uint32_t)(in && nb.y >= 0) << c;
-                okm[2] |= (uint32_t)(in && nb.z >= 0) << c; okm[3] |= (uint32_t)(in && nb.w >= 0) << c;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[rs]);          // z and the table rows are in registers now
-#pragma unroll
-            for (int k = 0; k < 4; ++k, ++oi, ++gi) {
-                const uint32_t o = oi & 1u, g = gi % E2_GRING, gu = gi / E2_GRING;
-                mbar_wait(&g_full[g], gu & 1u);
-                const uint32_t gb = smem_u32(g0) + g * g_bytes + (uint32_t)(16 * half) * row_bytes + (uint32_t)f * 4u;
-                float v[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float d = 0.f;
-                    if (live) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(d) : "r"(gb + (uint32_t)c * row_bytes));
-                    v[c] = ((okm[k] >> c) & 1u) ? tf32_rna(h[c] * d) : 0.f;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&g_empty[g]);       // the gathered block may be refilled
-                mbar_wait(&o_empty[o], ((oi >> 1) & 1u) ^ 1u);
-                if (live) {
-                    const uint32_t dst = smem_u32(op_p) + o * G_ATOM + (uint32_t)f * 128u;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        sts128(dst + ((((uint32_t)(4 * half + c)) ^ rsw) << 4), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&o_full[o]);
-            }
-        }
-        // read-out: warps 0-3 own the TMEM lanes (= feature rows) 32 w .. 32 w + 31
-        if (warp < 4) {
-            float v[32];
-            if (my > 0) {
-                mbar_wait(&bar_done, 0);
-                tc_fence_after_sync();
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            }
-            const int row = warp * 32 + lane;
-            float* outp = p.dwe_partials + (size_t)blockIdx.x * p.s_ld * 32;
-            if (row < p.f) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(outp + (size_t)row * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-        }
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    if (warp == E2_PW + 1) tmem_dealloc(tmem_base, 32);
-}
-
 }  // namespace dgnn
 
 using namespace dgnn;
@@ -1032,23 +799,6 @@ static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* 
 }
 
 static int launch_dwe_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
-#ifdef DGNN_DWE_ROWBLOCK
-    {
-        Dwe2Args q;
-        memset(&q, 0, sizeof(q));
-        q.d_agg = p.x; q.nbr = p.nbr; q.ea = p.ea; q.z_prev = p.z_prev; q.p_scale = p.p_scale; q.p_shift = p.p_shift;
-        q.p_relu = p.p_relu; q.fe = p.fe; q.n_rows = p.n_rows; q.f = p.f; q.ld = p.ld; q.s_ld = p.s_ld;
-        q.dwe_partials = p.dwe_partials;
-        const size_t row_bytes = (size_t)p.f * 4, ea_stage = (size_t)E2_CELLS * 4 * p.fe * 4;
-        const size_t st_bytes = (E2_CELLS * row_bytes + ((ea_stage + 15) & ~(size_t)15) + 512 + 127) & ~(size_t)127;
-        const size_t smem = 2 * G_ATOM + 4 * 32 * 128 + 2 * st_bytes + (size_t)E2_GRING * E2_CELLS * row_bytes + 1024;
-        if (smem <= 226 * 1024 && p.ld == p.f) {          // the stage copies need full-width (contiguous) rows
-            if (int rc_ = ensure_dyn_smem((const void*)dwe2_tc_kernel, 226 * 1024, what)) return rc_;
-            dwe2_tc_kernel<<<sm_count(), E2_THREADS, smem, st>>>(q);
-            return check_launch(what);
-        }
-    }
-#endif
     const int cpt = p.fp / 4;
     size_t smem = (size_t)4 * G_P_BYTES + (size_t)2 * G_NCW * 32 * p.fp + 1024;
 #define LAUNCH_D(CPT)                                                                                          \
