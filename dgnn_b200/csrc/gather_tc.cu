@@ -33,6 +33,7 @@ constexpr int G_NCW = 16;
 constexpr int G_THREADS = G_NCW * 32;                // no dedicated MMA warp: the last warp to finish a stage issues its MMAs
 constexpr int G_M = 128;
 constexpr int G_EA_STAGES = 2;                       // EA operand ring (hi | lo per stage)
+constexpr int G_EAW = 4;                             // gather_tc_kernel: EA warps (two per operand stage, 64 rows each)
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
 constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
 #ifndef DGNN_PF_AHEAD
@@ -133,13 +134,13 @@ __device__ __forceinline__ void l2_prefetch_range(const void* base, size_t bytes
 // NW compute warps: 16 (4 per scheduler, 128 registers) or 32 (8 per scheduler, 64 registers; twice the warps to hide the
 // shared-memory / TMEM / mbarrier latencies with, half the strip per thread)
 template <int CPT, int MODE, int NW>  // CPT: features per thread = fp / (NW / 4)
-__global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArgs p) {
-    constexpr int G_NCW = NW, G_THREADS = NW * 32;      // shadow the file-level constants (those are the dW_e kernel's)
+__global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const GatherTcArgs p) {
+    constexpr int G_NCW = NW, G_THREADS = NW * 32;      // compute warps / threads (shadow the file-level constants of the dW_e kernel)
+    constexpr int NT = (NW + G_EAW) * 32;               // all threads: + the EA warps
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t ea_empty[G_EA_STAGES];
-    __shared__ uint64_t phi_full[4];
+    __shared__ uint64_t ea_empty[G_EA_STAGES], ea_ready[G_EA_STAGES];
+    __shared__ uint64_t phi_full[4], phi_free[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ uint64_t ea_count[G_EA_STAGES];           // counts the warps that have stored their share of the stage
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int FP = CPT * (NW / 4);
@@ -155,15 +156,15 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
     float* aff_s = reinterpret_cast<float*>(x_base + (size_t)2 * G_NCW * WSTAGE);   // MODE 0: scale[FP] | shift[FP]
 
     if (tid == 0) {
-        for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); mbar_init(&ea_count[s], G_NCW); }
-        for (int s = 0; s < 4; ++s) mbar_init(&phi_full[s], 1);
+        for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); mbar_init(&ea_ready[s], 2); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&phi_full[s], 1); mbar_init(&phi_free[s], G_NCW); }
         fence_barrier_init();
     }
     // zero the operands (K padding stays zero), then WE[n][e] = w_e[n][e] (e < fe), WE[n][fe] = b_e[n]
-    for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM) / 16; i += G_THREADS)
+    for (int i = tid; i < (2 * FP * 128 + G_EA_STAGES * 2 * G_ATOM) / 16; i += NT)
         reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    for (int i = tid; i < p.f * (p.fe + 1); i += G_THREADS) {
+    for (int i = tid; i < p.f * (p.fe + 1); i += NT) {
         const int n = i / (p.fe + 1), e = i % (p.fe + 1);
         float v = e < p.fe ? __ldg(p.w_e + (size_t)n * p.fe + e) : __ldg(p.b_e + n);
         float hi, lo;
@@ -172,12 +173,12 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
         *reinterpret_cast<float*>(we_hi + off) = hi;
         *reinterpret_cast<float*>(we_lo + off) = lo;
     }
-    for (int i = tid; i < G_EA_STAGES * G_M; i += G_THREADS) {   // bias column of every EA stage
+    for (int i = tid; i < G_EA_STAGES * G_M; i += NT) {   // bias column of every EA stage
         const int s = i / G_M, r = i % G_M;
         *reinterpret_cast<float*>(ea_base + (size_t)s * 2 * G_ATOM + atom_off(r, p.fe)) = 1.0f;
     }
     if (MODE == 0) {                                             // producer norm affine, identity when absent / padded
-        for (int i = tid; i < FP; i += G_THREADS) {
+        for (int i = tid; i < FP; i += NT) {
             const bool on = p.scale != nullptr && i < p.f;
             aff_s[i] = on ? __ldg(p.scale + i) : 1.0f;
             aff_s[FP + i] = on ? __ldg(p.shift + i) : 0.0f;
@@ -194,18 +195,80 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
     const uint32_t n_my = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     const uint32_t n_phi = n_my * 4u;
 
-    {
+    if (warp >= NW) {
+        // ---------------------------------------------------------------- EA warps: warp e owns operand stage e and the PHI
+        // items n = e, e + 2, ..: EA rows of (tile n >> 2, slot n & 3) global -> registers (all of them in flight at once,
+        // issued BEFORE the waits on the stage / PHI buffer), split hi / lo -> swizzled operand stage, then the same warp
+        // issues PHI item n = EA . WE^T into TMEM buffer n & 3.  The compute warps only consume PHI: they never meet each
+        // other at a barrier (elect-by-arrival made all 16 of them rendezvous once per item), and a slow warp delays the
+        // others only through the 4-deep PHI ring.
+        const int e = (warp - NW) & 1, half = (warp - NW) >> 1;   // operand stage, half of the tile's rows
+        const uint32_t idesc = make_idesc_tf32(G_M, FP);
+        const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
+        const int ksteps = (p.fe + 1 + 7) >> 3;        // fe features + bias column, 8 per k-step (3 for fe = 20)
+        const int fe4 = p.fe >> 2;
+        const int n_f4 = (G_M / 2) * fe4;              // float4 pieces of this warp's 64 rows
+        const uint32_t ah = smem_u32(ea_base) + (uint32_t)e * 2u * G_ATOM, al = ah + G_ATOM;
+        constexpr int EV = 10;                         // pieces per lane and batch (one batch covers fe <= 20)
+        for (uint32_t n = (uint32_t)e; n < n_phi; n += 2) {
+            const uint32_t b = n & 3u;
+            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)(n >> 2) * gridDim.x) * G_M + half * (G_M / 2);
+            const float* src = p.ea + ((size_t)r0 * 4 + (n & 3u)) * p.fe;
+            for (int base = 0; base < n_f4; base += 32 * EV) {
+                float4 ev[EV];
+#pragma unroll
+                for (int j = 0; j < EV; ++j) {
+                    const int idx = base + lane + 32 * j;
+                    const int r = idx / fe4, c4 = idx - r * fe4;
+                    ev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < n_f4 && r0 + r < p.n_rows) ev[j] = ldg4_pinned(src + (size_t)r * 4 * p.fe + c4 * 4);
+                }
+                if (base == 0) {
+                    mbar_wait(&ea_empty[e], ((n >> 1) & 1u) ^ 1u);           // this stage's previous MMAs have read it
+                    mbar_wait(&phi_free[b], ((n >> 2) & 1u) ^ 1u);           // every compute warp is done with item n - 4
+                }
+#pragma unroll
+                for (int j = 0; j < EV; ++j) {
+                    const int idx = base + lane + 32 * j;
+                    if (idx < n_f4) {
+                        const int r = idx / fe4, c4 = idx - r * fe4;
+                        float4 h, l;
+                        split_tf32(ev[j].x, h.x, l.x); split_tf32(ev[j].y, h.y, l.y);
+                        split_tf32(ev[j].z, h.z, l.z); split_tf32(ev[j].w, h.w, l.w);
+                        const uint32_t off = atom_off(half * (G_M / 2) + r, c4 * 4);
+                        sts128(ah + off, h);
+                        sts128(al + off, l);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&ea_ready[e]);
+                if (half == 1) {                       // the second-half warp issues the item once both halves are stored
+                    mbar_wait(&ea_ready[e], (n >> 1) & 1u);
+                    tc_fence_after_sync();
+                    const uint32_t d = tmem_base + b * (uint32_t)FP;
+                    for (int kk = 0; kk < ksteps; ++kk) {
+                        const uint32_t ko = kk * 32;
+                        mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
+                        mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
+                        mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
+                    }
+                    mma_commit(&ea_empty[e]);
+                    mma_commit(&phi_full[b]);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
         // ---------------------------------------------------------------- compute warps
         const int q = warp & 3, grp = warp >> 2;
         const int row = q * 32 + lane;
         const int c0 = grp * CPT;                      // first feature of this thread's strip
-        const uint32_t idesc = make_idesc_tf32(G_M, FP);
-        const uint32_t wh = smem_u32(we_hi), wl = smem_u32(we_lo);
-        const int ksteps = (p.fe + 1 + 7) >> 3;        // fe features + bias column, 8 per k-step (3 for fe = 20)
         const bool relu = (p.relu & 1) != 0;
         const bool affine = p.scale != nullptr;
         const bool al8 = ((p.f | p.ld) & 7) == 0;
-        const int fe4 = p.fe >> 2;
         uint8_t* xw = x_base + (size_t)warp * WSTAGE;                  // + stage * G_NCW * WSTAGE
         const uint32_t swz_l = ((uint32_t)lane / (8 / CH)) & (CH - 1); // chunk swizzle of this thread's row
         const int c_row = lane / CH, c_ch = lane % CH;                 // copy role: row within an instruction, chunk
@@ -221,67 +284,6 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
                 if (t < p.n_rows) nb = ldg4i_pinned(p.nbr + (size_t)t * 4);
             }
             return nb;
-        };
-        // ---- EA staging, one PHI item at a time
-        constexpr int EU = NW >= 32 ? 1 : 2;           // float4 of an EA item per thread (128 rows x <= 7 float4)
-        float4 ev[EU];
-        int e_r[EU], e_c4[EU];                         // this thread's (row, first feature) of the float4 it stages
-        uint32_t e_off[EU];
-#pragma unroll
-        for (int u = 0; u < EU; ++u) {
-            const int idx = tid + u * G_NCW * 32;
-            e_r[u] = idx < G_M * fe4 ? idx / fe4 : -1;
-            e_c4[u] = idx < G_M * fe4 ? (idx - e_r[u] * fe4) * 4 : 0;
-            e_off[u] = atom_off(e_r[u] < 0 ? 0 : e_r[u], e_c4[u]);
-        }
-        auto ea_load = [&](uint32_t n) {               // global loads of PHI item n into registers
-            const int64_t r0 = tile_of(n >> 2) * G_M;
-#pragma unroll
-            for (int u = 0; u < EU; ++u) {
-                ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < n_phi && e_r[u] >= 0 && r0 + e_r[u] < p.n_rows)
-                    ev[u] = ldg4_pinned(p.ea + ((size_t)(r0 + e_r[u]) * 4 + (n & 3u)) * p.fe + e_c4[u]);
-            }
-        };
-        auto ea_store = [&](uint32_t n) {              // registers -> (hi | lo) operand stage, then signal the MMA warp
-            if (n >= n_phi) return;
-            const uint32_t s = n % G_EA_STAGES, su = n / G_EA_STAGES;
-            uint8_t* e_hi = ea_base + (size_t)s * 2 * G_ATOM;
-            uint8_t* e_lo = e_hi + G_ATOM;
-            mbar_wait(&ea_empty[s], (su & 1) ^ 1);
-#pragma unroll
-            for (int u = 0; u < EU; ++u) {
-                if (e_r[u] >= 0) {
-                    float4 h, l;
-                    split_tf32(ev[u].x, h.x, l.x); split_tf32(ev[u].y, h.y, l.y);
-                    split_tf32(ev[u].z, h.z, l.z); split_tf32(ev[u].w, h.w, l.w);
-                    sts128(smem_u32(e_hi) + e_off[u], h);
-                    sts128(smem_u32(e_lo) + e_off[u], l);
-                }
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                if (mbar_arrive_pending(&ea_count[s]) == 1u) {   // last warp of the stage: issue PHI item n = EA . WE^T
-                    mbar_wait(&ea_count[s], su & 1);   // completed by this very arrival: acquires the other warps' stores
-                    // PHI buffer n & 3 was last read for item n - 4.  Every warp stores item n at its position n - 2, i.e.
-                    // after it has finished consuming item n - 3 and everything before: once the count is complete no
-                    // warp can still be reading the buffer, so no further barrier is needed before overwriting it.
-                    const uint32_t b = n & 3u;
-                    tc_fence_after_sync();
-                    const uint32_t ah = smem_u32(e_hi), al = ah + G_ATOM;
-                    const uint32_t d = tmem_base + b * (uint32_t)FP;
-                    for (int kk = 0; kk < ksteps; ++kk) {
-                        const uint32_t ko = kk * 32;
-                        mma_tf32(d, make_desc(ah + ko), make_desc(wh + ko), idesc, kk > 0 ? 1u : 0u);
-                        mma_tf32(d, make_desc(al + ko), make_desc(wh + ko), idesc, 1u);
-                        mma_tf32(d, make_desc(ah + ko), make_desc(wl + ko), idesc, 1u);
-                    }
-                    mma_commit(&ea_empty[s]);
-                    mma_commit(&phi_full[b]);
-                }
-            }
-            __syncwarp();
         };
         // ---- x ring: cp.async of item (tile count tc, slot k) into stage `st`
         auto x_issue = [&](uint32_t tc, int k, const int (&nbv)[4], uint32_t st) {
@@ -316,9 +318,6 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
         // ---- prologue
         int4 nb4 = load_nbr(0);
         int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-        ea_load(0); ea_store(0);
-        ea_load(1); ea_store(1);
-        ea_load(2);
         uint32_t xi = 0;                               // x items consumed so far (stage = xi & 1)
         x_issue(0, 0, nbv, 0);
         uint32_t pn = 0;                               // PHI items consumed so far
@@ -369,12 +368,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
                     const uint32_t b = pn & 3u, bu = pn >> 2;
                     mbar_wait(&phi_full[b], bu & 1);
                     tc_fence_after_sync();
-                    // MMA of item pn is done => EA stage (pn + 2) % 2 is free: store item pn + 2, fetch item pn + 3
-                    ea_store(pn + 2);
 #ifdef DGNN_XISSUE_LATE
                     issue_next();
 #endif
-                    ea_load(pn + 3);
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)FP + (uint32_t)c0;
                     const bool valid = nbv[k] >= 0;
 #pragma unroll
@@ -404,7 +400,9 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
                             acc[j + 7] = fmaf(xb.w, __uint_as_float(ph[7]), acc[j + 7]);
                         }
                     }
-                    tc_fence_before_sync();             // orders these TMEM reads before the warp's next ea_count arrival
+                    tc_fence_before_sync();             // orders these TMEM reads before the buffer is handed back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&phi_free[b]);
                     ++pn;
                     if (MODE == 0 && k == 3) {
 #pragma unroll
@@ -501,7 +499,7 @@ __global__ void __launch_bounds__(NW * 32, 1) gather_tc_kernel(const GatherTcArg
     __syncthreads();
     if (MODE == 1 && p.s_partials != nullptr) {
         double* my = p.s_partials + (size_t)blockIdx.x * 2 * p.s_ld;
-        for (int c = tid; c < p.f; c += G_THREADS) {
+        for (int c = tid; c < p.f; c += NT) {
             const int g = c / CPT, cl = c % CPT;
             double a = 0.0, b2 = 0.0;
             for (int qq = 0; qq < 4; ++qq) {           // the four row quadrants of feature group g, fixed order
@@ -782,7 +780,7 @@ static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* 
 #define LAUNCH_G(CPT, NW)                                                                                      \
     do {                                                                                                       \
         if (int rc_ = ensure_dyn_smem((const void*)gather_tc_kernel<CPT, MODE, NW>, 226 * 1024, what)) return rc_; \
-        gather_tc_kernel<CPT, MODE, NW><<<sm_count(), NW * 32, smem, st>>>(p);                                 \
+        gather_tc_kernel<CPT, MODE, NW><<<sm_count(), (NW + G_EAW) * 32, smem, st>>>(p);                       \
     } while (0)
     switch (cpt) {
         case 8: LAUNCH_G(8, 16); break;
