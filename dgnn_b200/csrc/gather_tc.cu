@@ -33,6 +33,10 @@ constexpr int G_NCW = 16;
 constexpr int G_THREADS = G_NCW * 32;                // no dedicated MMA warp: the last warp to finish a stage issues its MMAs
 constexpr int G_M = 128;
 constexpr int G_EA_STAGES = 2;                       // EA operand ring (hi | lo per stage)
+#ifndef DGNN_NST_NARROW
+#define DGNN_NST_NARROW 4
+#endif
+constexpr int G_NST_NARROW = DGNN_NST_NARROW;          // x-ring stages of the gather / dW_e kernels at F <= 64
 constexpr int G_EAW = 4;                             // gather_tc_kernel: EA warps (two per operand stage, 64 rows each)
 constexpr int G_ATOM = G_M * 128;                    // 16 KB
 constexpr int G_P_BYTES = G_ATOM + 2 * 32 * 128;     // P_hi [128 x 32 cells] + EA^T hi / lo [32 x 32 cells]
@@ -133,7 +137,7 @@ __device__ __forceinline__ void l2_prefetch_range(const void* base, size_t bytes
 //             no "free" barrier: the arrival count of item n already orders the overwrite of item n-4's buffer.
 // NW compute warps: 16 (4 per scheduler, 128 registers) or 32 (8 per scheduler, 64 registers; twice the warps to hide the
 // shared-memory / TMEM / mbarrier latencies with, half the strip per thread)
-template <int CPT, int MODE, int NW>  // CPT: features per thread = fp / (NW / 4)
+template <int CPT, int MODE, int NW, int NST>  // CPT: features per thread = fp / (NW / 4); NST: x-ring stages (power of 2)
 __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const GatherTcArgs p) {
     constexpr int G_NCW = NW, G_THREADS = NW * 32;      // compute warps / threads (shadow the file-level constants of the dW_e kernel)
     constexpr int NT = (NW + G_EAW) * 32;               // all threads: + the EA warps
@@ -152,8 +156,9 @@ __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const G
     uint8_t* we_hi = smem;                               // [FP rows x 128 B]
     uint8_t* we_lo = we_hi + FP * 128;
     uint8_t* ea_base = we_lo + FP * 128;                 // stages of (hi 16 KB | lo 16 KB)
-    uint8_t* x_base = ea_base + (size_t)G_EA_STAGES * 2 * G_ATOM;   // [2 stages][G_NCW warps][32 rows x PITCH]
-    float* aff_s = reinterpret_cast<float*>(x_base + (size_t)2 * G_NCW * WSTAGE);   // MODE 0: scale[FP] | shift[FP]
+    uint8_t* x_base = ea_base + (size_t)G_EA_STAGES * 2 * G_ATOM;   // [NST stages][G_NCW warps][32 rows x PITCH]
+    float* aff_s = reinterpret_cast<float*>(x_base + (size_t)NST * G_NCW * WSTAGE);   // MODE 0: scale[FP] | shift[FP]
+    static_assert(NST >= 2 && (NST & (NST - 1)) == 0 && NST - 1 <= IPT, "x ring: 2 or 4 stages");
 
     if (tid == 0) {
         for (int s = 0; s < G_EA_STAGES; ++s) { mbar_init(&ea_empty[s], 1); mbar_init(&ea_ready[s], 2); }
@@ -210,22 +215,66 @@ __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const G
         const int n_f4 = (G_M / 2) * fe4;              // float4 pieces of this warp's 64 rows
         const uint32_t ah = smem_u32(ea_base) + (uint32_t)e * 2u * G_ATOM, al = ah + G_ATOM;
         constexpr int EV = 10;                         // pieces per lane and batch (one batch covers fe <= 20)
+        // piece j of this lane in batch 0: global offset (floats from the item's first row) and operand offset (bytes) are
+        // the same for every item - formed once (a runtime division per piece and item made these warps the slowest)
+        uint32_t goff[EV], soff[EV];
+#pragma unroll
+        for (int j = 0; j < EV; ++j) {
+            const int idx = lane + 32 * j;
+            const int r = idx / fe4, c4 = idx - r * fe4;
+            goff[j] = idx < n_f4 ? (uint32_t)(r * 4 * p.fe + c4 * 4) : 0xffffffffu;
+            soff[j] = atom_off(half * (G_M / 2) + r, c4 * 4);                      // row = soff >> 7
+        }
         for (uint32_t n = (uint32_t)e; n < n_phi; n += 2) {
             const uint32_t b = n & 3u;
-            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)(n >> 2) * gridDim.x) * G_M + half * (G_M / 2);
+            const int64_t t0 = ((int64_t)blockIdx.x + (int64_t)(n >> 2) * gridDim.x) * G_M;   // first row of the tile
+            const int64_t r0 = t0 + half * (G_M / 2);
             const float* src = p.ea + ((size_t)r0 * 4 + (n & 3u)) * p.fe;
-            for (int base = 0; base < n_f4; base += 32 * EV) {
-                float4 ev[EV];
+            const uint32_t row_lim = (uint32_t)(p.n_rows - t0 < G_M ? p.n_rows - t0 : G_M);   // rows of the tile that exist
+#ifndef DGNN_NO_EA_PREFETCH
+            // The four slots of a row share its 4 fe floats of EA, so only the first item of a tile misses L2; pull the
+            // NEXT tile's rows (this warp's half of them, split with the other stage's warp) into L2 now, so that an
+            // item costs this warp an L2 round trip, not a DRAM one (the EA warps set the pace of the kernel at F <= 64).
+            if ((n & 3u) == (uint32_t)e && (n >> 2) + 1 < n_my) {
+                const int64_t rn = r0 + (int64_t)gridDim.x * G_M;
+                const int64_t left = p.n_rows - rn;
+                const int64_t rows = left < G_M / 2 ? left : G_M / 2;
+                const char* blk = reinterpret_cast<const char*>(p.ea + (size_t)rn * 4 * p.fe);
+                const int64_t bytes = rows * 4 * p.fe * 4;
+                for (int64_t o = ((int64_t)e * 32 + lane) * 128; o < bytes; o += 64 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + o));
+            }
+#endif
+            float4 ev[EV];
+#pragma unroll
+            for (int j = 0; j < EV; ++j) {
+                ev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef DGNN_G_NOEALOAD   // timing experiment: no EA loads (wrong results)
+                if (goff[j] != 0xffffffffu && (soff[j] >> 7) < row_lim) ev[j] = ldg4_pinned(src + goff[j]);
+#endif
+            }
+            mbar_wait(&ea_empty[e], ((n >> 1) & 1u) ^ 1u);           // this stage's previous MMAs have read it
+            mbar_wait(&phi_free[b], ((n >> 2) & 1u) ^ 1u);           // every compute warp is done with item n - 4
+#pragma unroll
+            for (int j = 0; j < EV; ++j) {
+#ifdef DGNN_G_NOEASTORE   // timing experiment: no EA operand stores (wrong results)
+                if (false)
+#endif
+                if (goff[j] != 0xffffffffu) {
+                    float4 h, l;
+                    split_tf32(ev[j].x, h.x, l.x); split_tf32(ev[j].y, h.y, l.y);
+                    split_tf32(ev[j].z, h.z, l.z); split_tf32(ev[j].w, h.w, l.w);
+                    sts128(ah + soff[j], h);
+                    sts128(al + soff[j], l);
+                }
+            }
+            for (int base = 32 * EV; base < n_f4; base += 32 * EV) {   // wide edge features (fe > 20): further batches
 #pragma unroll
                 for (int j = 0; j < EV; ++j) {
                     const int idx = base + lane + 32 * j;
                     const int r = idx / fe4, c4 = idx - r * fe4;
                     ev[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (idx < n_f4 && r0 + r < p.n_rows) ev[j] = ldg4_pinned(src + (size_t)r * 4 * p.fe + c4 * 4);
-                }
-                if (base == 0) {
-                    mbar_wait(&ea_empty[e], ((n >> 1) & 1u) ^ 1u);           // this stage's previous MMAs have read it
-                    mbar_wait(&phi_free[b], ((n >> 2) & 1u) ^ 1u);           // every compute warp is done with item n - 4
                 }
 #pragma unroll
                 for (int j = 0; j < EV; ++j) {
@@ -318,8 +367,9 @@ __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const G
         // ---- prologue
         int4 nb4 = load_nbr(0);
         int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
-        uint32_t xi = 0;                               // x items consumed so far (stage = xi & 1)
-        x_issue(0, 0, nbv, 0);
+        uint32_t xi = 0;                               // x items consumed so far (stage = xi & (NST - 1))
+#pragma unroll
+        for (int j = 0; j < NST - 1; ++j) x_issue(0, j, nbv, (uint32_t)j);
         uint32_t pn = 0;                               // PHI items consumed so far
         for (uint32_t tc = 0; tc < n_my; ++tc) {
             const int64_t t = tile_of(tc) * G_M + row;
@@ -348,19 +398,22 @@ __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const G
             for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
 #pragma unroll
             for (int k = 0; k < IPT; ++k, ++xi) {
-                // next item's copy goes in flight (the other stage was released by the __syncwarp at the end of the last item)
+                // the copy of the item NST - 1 ahead goes in flight (its stage was released by the __syncwarp at the end of the
+                // last item).  Two stages = one item ahead is all that fits at F = 128; at F <= 64 the items are short (the
+                // arithmetic of an item takes less than the round trip of its rows) and four stages keep three in flight.
                 auto issue_next = [&]() {
-                    if (k + 1 < IPT) x_issue(tc, k + 1, nbv, (xi + 1) & 1);
-                    else x_issue(tc + 1, 0, nbn, (xi + 1) & 1);
+                    constexpr int D = NST - 1;
+                    if (k + D < IPT) x_issue(tc, k + D, nbv, (xi + D) & (NST - 1));
+                    else x_issue(tc + 1, k + D - IPT, nbn, (xi + D) & (NST - 1));
                 };
 #ifdef DGNN_XISSUE_LATE      // variant: copy issued after the operand stores' fence.proxy.async (measured: no gain, MODE 1 slower)
-                cp_async_wait<0>();
+                cp_async_wait<NST - 2>();
 #else
                 issue_next();
-                cp_async_wait<1>();
+                cp_async_wait<NST - 1>();
 #endif
                 __syncwarp();
-                const uint8_t* xs = xw + (size_t)(xi & 1) * G_NCW * WSTAGE + lane * PITCH;
+                const uint8_t* xs = xw + (size_t)(xi & (NST - 1)) * G_NCW * WSTAGE + lane * PITCH;
 #ifdef DGNN_XISSUE_LATE
                 if (k >= 4) issue_next();
 #endif
@@ -479,7 +532,7 @@ __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const G
                         }
                     }
                 }
-                __syncwarp();                          // every lane is done with stage xi & 1 before it is refilled
+                __syncwarp();                          // every lane is done with this item's stage before it is refilled
             }
             nbv[0] = nbn[0]; nbv[1] = nbn[1]; nbv[2] = nbn[2]; nbv[3] = nbn[3];
         }
@@ -524,7 +577,7 @@ __global__ void __launch_bounds__((NW + G_EAW) * 32, 1) gather_tc_kernel(const G
 // Per row quarter q one operand stage (P^T [128 features x 32 cells], hi then lo | EA^T hi | EA^T lo); the strips a warp
 // needs (its rows' z_prev strip, then the four gathered d_agg strips) arrive through the same warp-private
 // cp.async ring as in gather_tc_kernel, one item ahead, so no load is waited for in registers.
-template <int CPT>
+template <int CPT, int NST>    // NST: x-ring stages (2 at F = 128, 4 below: see gather_tc_kernel)
 __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t p_empty[4];
@@ -603,7 +656,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
         int4 nb4 = load_nbr(0);
         int nbv[4] = {nb4.x, nb4.y, nb4.z, nb4.w};
         uint32_t xi = 0, it = 0;
-        x_issue(0, 0, nbv, 0);
+        static_assert(NST >= 2 && (NST & (NST - 1)) == 0 && NST - 1 <= 5, "x ring: 2 or 4 stages");
+#pragma unroll
+        for (int j = 0; j < NST - 1; ++j) x_issue(0, j, nbv, (uint32_t)j);
         for (uint32_t tc = 0; tc < n_my; ++tc) {
             const int64_t t = tile_of(tc) * G_M + row;
             const bool tv = t < p.n_rows;
@@ -634,11 +689,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
             };
 #pragma unroll
             for (int m = 0; m < 5; ++m, ++xi) {
-                if (m + 1 < 5) x_issue(tc, m + 1, nbv, (xi + 1) & 1);
-                else x_issue(tc + 1, 0, nbn, (xi + 1) & 1);
-                cp_async_wait<1>();
+                {
+                    constexpr int D = NST - 1;             // copies run D items ahead of their use
+                    if (m + D < 5) x_issue(tc, m + D, nbv, (xi + D) & (NST - 1));
+                    else x_issue(tc + 1, m + D - 5, nbn, (xi + D) & (NST - 1));
+                }
+                cp_async_wait<NST - 1>();
                 __syncwarp();
-                const uint8_t* xs = xw + (size_t)(xi & 1) * G_NCW * WSTAGE + lane * PITCH;
+                const uint8_t* xs = xw + (size_t)(xi & (NST - 1)) * G_NCW * WSTAGE + lane * PITCH;
                 if (m == 0) {
                     load_ev(0);
 #pragma unroll
@@ -776,20 +834,19 @@ static int fp_of(int f) { return f <= 32 ? 32 : (f <= 64 ? 64 : 128); }
 template <int MODE>
 static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
-    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + (size_t)2 * G_NCW * 32 * p.fp + (size_t)8 * p.fp + 1024;
-#define LAUNCH_G(CPT, NW)                                                                                      \
+    const int nst = cpt == 32 ? 2 : G_NST_NARROW;  // x-ring stages: what fits at F = 128, deeper below
+    size_t smem = (size_t)2 * p.fp * 128 + (size_t)G_EA_STAGES * 2 * G_ATOM + (size_t)nst * G_NCW * 32 * p.fp + (size_t)8 * p.fp + 1024;
+#define LAUNCH_G(CPT, NW, NST)                                                                                 \
     do {                                                                                                       \
-        if (int rc_ = ensure_dyn_smem((const void*)gather_tc_kernel<CPT, MODE, NW>, 226 * 1024, what)) return rc_; \
-        gather_tc_kernel<CPT, MODE, NW><<<sm_count(), (NW + G_EAW) * 32, smem, st>>>(p);                       \
+        if (int rc_ = ensure_dyn_smem((const void*)gather_tc_kernel<CPT, MODE, NW, NST>, 226 * 1024, what)) return rc_; \
+        gather_tc_kernel<CPT, MODE, NW, NST><<<sm_count(), (NW + G_EAW) * 32, smem, st>>>(p);                  \
     } while (0)
     switch (cpt) {
-        case 8: LAUNCH_G(8, 16); break;
-        case 16: LAUNCH_G(16, 16); break;
-#ifdef DGNN_GATHER_32W     // variant: 32 warps x 16 features per thread (64 registers).  Measured on B200, 128 -> 128 layer:
-        case 32: LAUNCH_G(16, 32); break;              // forward 12.1 vs 10.5 us / tile, backward 13.8 vs 12.1: the kernel is not
-#else                      // short of warps to hide latency with, it is short of issue slots (index arithmetic, barriers)
-        case 32: LAUNCH_G(32, 16); break;
-#endif
+        case 8: LAUNCH_G(8, 16, G_NST_NARROW); break;
+        case 16: LAUNCH_G(16, 16, G_NST_NARROW); break;
+        // (a 32-warp variant, 16 features per thread and 64 registers, measured 12.1 vs 10.5 us forward and 13.8 vs 12.1 us
+        // backward at F = 128 on B200)
+        case 32: LAUNCH_G(32, 16, 2); break;
         default: return fail(what, "unsupported feature width");
     }
 #undef LAUNCH_G
@@ -798,16 +855,17 @@ static int launch_gather_tc(const GatherTcArgs& p, cudaStream_t st, const char* 
 
 static int launch_dwe_tc(const GatherTcArgs& p, cudaStream_t st, const char* what) {
     const int cpt = p.fp / 4;
-    size_t smem = (size_t)4 * G_P_BYTES + (size_t)2 * G_NCW * 32 * p.fp + 1024;
-#define LAUNCH_D(CPT)                                                                                          \
+    const int nst = cpt == 32 ? 2 : G_NST_NARROW;
+    size_t smem = (size_t)4 * G_P_BYTES + (size_t)nst * G_NCW * 32 * p.fp + 1024;
+#define LAUNCH_D(CPT, NST)                                                                                     \
     do {                                                                                                       \
-        if (int rc_ = ensure_dyn_smem((const void*)dwe_tc_kernel<CPT>, 226 * 1024, what)) return rc_;             \
-        dwe_tc_kernel<CPT><<<sm_count(), G_THREADS, smem, st>>>(p);                                            \
+        if (int rc_ = ensure_dyn_smem((const void*)dwe_tc_kernel<CPT, NST>, 226 * 1024, what)) return rc_;        \
+        dwe_tc_kernel<CPT, NST><<<sm_count(), G_THREADS, smem, st>>>(p);                                       \
     } while (0)
     switch (cpt) {
-        case 8: LAUNCH_D(8); break;
-        case 16: LAUNCH_D(16); break;
-        case 32: LAUNCH_D(32); break;
+        case 8: LAUNCH_D(8, G_NST_NARROW); break;
+        case 16: LAUNCH_D(16, G_NST_NARROW); break;
+        case 32: LAUNCH_D(32, 2); break;
         default: return fail(what, "unsupported feature width");
     }
 #undef LAUNCH_D
