@@ -311,13 +311,14 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_tc_kernel(const DwTcArgs p) 
 // dW, second formulation ("row-block" kernel) for layers whose block is the whole matrix (f_out <= 128, k_total <= 256).
 //
 // A stage is 32 consecutive cells.  Their rows of dy, z, agg and x are CONTIGUOUS in global memory (full-width rows), so
-// one warp fetches a whole raw stage with four 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) into a 2-deep shared-memory
+// one warp fetches a whole raw stage with four 1-D bulk copies (cp.async.bulk -> SASS UBLKCP) into a shared-memory
 // ring - no per-thread global loads, no address arithmetic in the producers.  The transposition the contraction over
 // cells needs is done by ADDRESSING: producer thread = one operand row (= one channel); it reads its channel of 16 cells
 // with 16 LDS.32 (lanes = consecutive channels: conflict-free), applies the normalisation backward / the producer
 // affine + ReLU with per-thread-constant coefficients, splits hi / lo and writes four 16-byte chunks per image (swizzled:
 // conflict-free).  No shuffles, no selects.  The single operand buffer works as two half-stages of 16 cells (k-steps 0-1
 // and 2-3 of the 32-cell K-atom): while the tensor core consumes one half the producers fill the other.
+// The raw ring is as deep as the shared memory allows (2 stages of 64 KB at 128 -> 128, 3 - 4 for the narrower layers).
 // db = column sums of dz: the thread that owns a dz channel keeps its sum in a register for the whole kernel.
 struct Dw2Args {
     const float* dy;
@@ -336,15 +337,22 @@ struct Dw2Args {
     int f_in, f_out, k_total, np;
     float* partials;      // [grid][f_out][k_total]
     double* db_partials;  // [grid][f_out], may be NULL
+    int ring;             // raw stages in flight: 2 at 128 -> 128 (64 KB each), up to DW2_MAX_RING for narrower layers
 };
 
+constexpr int DW2_MAX_RING = 8;
 constexpr int DW2_PW = 12;                          // producer warps: thread = operand row (128 dz rows + up to 256 [agg | h] rows)
 constexpr int DW2_THREADS = (DW2_PW + 2) * 32;      // + MMA warp + bulk-copy warp
 constexpr int DW2_CELLS = 32;
 
+// FULL = 0: ONE operand buffer worked as two half-stages of 16 cells (all that fits next to the raw ring at 128 -> 128).
+// FULL = 1: TWO whole operand buffers, one hand-off per 32-cell stage: a hand-off (operand stores -> fence -> MMA ->
+// commit -> producers) measures ~0.6 us whatever the operand size, and at two per stage it, not the bytes, set the pace
+// of the narrower layers (5 - 5.7 us per 128 cells at 64 -> 128 and 28 -> 64 against 7.5 us at 128 -> 128).
+template <int FULL>
 __global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t raw_full[2], raw_empty[2], op_full[2], op_empty[2], bar_done;
+    __shared__ uint64_t raw_full[DW2_MAX_RING], raw_empty[DW2_MAX_RING], op_full[2], op_empty[2], bar_done;
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -356,17 +364,16 @@ __global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p)
     const uint32_t dy_bytes = (uint32_t)DW2_CELLS * p.f_out * 4u, x_bytes = (uint32_t)DW2_CELLS * p.f_in * 4u;
     const uint32_t off_z = dy_bytes, off_agg = off_z + (norm ? dy_bytes : 0u), off_x = off_agg + (p.agg ? x_bytes : 0u);
     const uint32_t raw_stage = (off_x + x_bytes + 127u) & ~127u;
-    uint8_t* raw0 = smem + 2 * DW_A_BYTES + 2 * b_bytes;
+    const uint32_t opb = 2u * DW_A_BYTES + 2u * (uint32_t)b_bytes;       // one operand buffer
+    uint8_t* raw0 = smem + (FULL ? 2u : 1u) * opb;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], DW2_PW);
-            mbar_init(&op_full[i], DW2_PW); mbar_init(&op_empty[i], 1);
-        }
+        for (int i = 0; i < DW2_MAX_RING; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], DW2_PW); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&op_full[i], DW2_PW); mbar_init(&op_empty[i], 1); }
         mbar_init(&bar_done, 1);
         fence_barrier_init();
     }
     // operand rows beyond f_out / k_total are never written but are read by the MMA: zero the whole buffer once
-    for (int i = tid; i < (2 * DW_A_BYTES + 2 * b_bytes) / 16; i += DW2_THREADS)
+    for (int i = tid; i < (int)((FULL ? 2u : 1u) * opb / 16u); i += DW2_THREADS)
         reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async_smem();
     if (warp == DW2_PW) tmem_alloc(&tmem_slot, 256);
@@ -384,8 +391,8 @@ __global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p)
         // ------------------------------------------------------------ bulk-copy warp: raw stages, one stage ahead
         if (lane == 0) {
             for (int64_t s = 0; s < my; ++s) {
-                const int rs = (int)(s & 1);
-                mbar_wait(&raw_empty[rs], (uint32_t)(((s >> 1) & 1) ^ 1));
+                const int rs = (int)(s % p.ring);
+                mbar_wait(&raw_empty[rs], (uint32_t)(((s / p.ring) & 1) ^ 1));
                 const int64_t c0 = (g_begin + s) * DW2_CELLS;
                 const int64_t left = p.n_tgt - c0;
                 const uint32_t rows = (uint32_t)(left < DW2_CELLS ? left : DW2_CELLS);
@@ -404,18 +411,32 @@ __global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p)
         if (lane == 0) {
             const uint32_t ah = smem_u32(a_hi), al = ah + DW_A_BYTES, bh = smem_u32(b_hi), bl = bh + b_bytes;
             for (int64_t s = 0; s < my; ++s) {
-#pragma unroll
-                for (int hs = 0; hs < 2; ++hs) {
-                    mbar_wait(&op_full[hs], (uint32_t)(s & 1));
+                if (FULL) {
+                    const uint32_t o = (uint32_t)(s & 1), ob = o * opb;
+                    mbar_wait(&op_full[o], (uint32_t)((s >> 1) & 1));
                     tc_fence_after_sync();
 #pragma unroll
-                    for (int kk = 2 * hs; kk < 2 * hs + 2; ++kk) {
-                        const uint32_t ko = kk * 32;
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t ko = ob + kk * 32;
                         mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bh + ko), idesc, (s > 0 || kk > 0) ? 1u : 0u);
                         mma_tf32(tmem_base, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
                         mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
                     }
-                    mma_commit(&op_empty[hs]);
+                    mma_commit(&op_empty[o]);
+                } else {
+#pragma unroll
+                    for (int hs = 0; hs < 2; ++hs) {
+                        mbar_wait(&op_full[hs], (uint32_t)(s & 1));
+                        tc_fence_after_sync();
+#pragma unroll
+                        for (int kk = 2 * hs; kk < 2 * hs + 2; ++kk) {
+                            const uint32_t ko = kk * 32;
+                            mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bh + ko), idesc, (s > 0 || kk > 0) ? 1u : 0u);
+                            mma_tf32(tmem_base, make_desc(al + ko), make_desc(bh + ko), idesc, 1u);
+                            mma_tf32(tmem_base, make_desc(ah + ko), make_desc(bl + ko), idesc, 1u);
+                        }
+                        mma_commit(&op_empty[hs]);
+                    }
                 }
                 if (s == my - 1) mma_commit(&bar_done);
             }
@@ -457,11 +478,11 @@ __global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p)
         const uint32_t raw_u32 = smem_u32(raw0);
         float dbsum = 0.f;
         for (int64_t s = 0; s < my; ++s) {
-            const int rs = (int)(s & 1);
+            const int rs = (int)(s % p.ring);
             const int64_t cbase = (g_begin + s) * DW2_CELLS;
             const int64_t left = p.n_tgt - cbase;
             const int nvalid = (int)(left < DW2_CELLS ? left : DW2_CELLS);
-            mbar_wait(&raw_full[rs], (uint32_t)((s >> 1) & 1));
+            mbar_wait(&raw_full[rs], (uint32_t)((s / p.ring) & 1));
             const uint32_t rbase = raw_u32 + (uint32_t)rs * raw_stage;
 #pragma unroll
             for (int hs = 0; hs < 2; ++hs) {
@@ -499,21 +520,25 @@ __global__ void __launch_bounds__(DW2_THREADS, 1) dw2_tc_kernel(const Dw2Args p)
                         for (int i = 0; i < 16; ++i) dbsum += v[i];
                     }
                 }
-                mbar_wait(&op_empty[hs], (uint32_t)((s & 1) ^ 1));
+                const uint32_t ob = FULL ? (uint32_t)(s & 1) * opb : 0u;
+                if (FULL) { if (hs == 0) mbar_wait(&op_empty[s & 1], (uint32_t)(((s >> 1) & 1) ^ 1)); }
+                else mbar_wait(&op_empty[hs], (uint32_t)((s & 1) ^ 1));
                 if (live) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float4 h, l;
                         split_tf32(v[4 * c], h.x, l.x); split_tf32(v[4 * c + 1], h.y, l.y);
                         split_tf32(v[4 * c + 2], h.z, l.z); split_tf32(v[4 * c + 3], h.w, l.w);
-                        const uint32_t a = dst_hi + ((((uint32_t)(4 * hs + c)) ^ rsw) << 4);
+                        const uint32_t a = dst_hi + ob + ((((uint32_t)(4 * hs + c)) ^ rsw) << 4);
                         sts128(a, h);
                         sts128(a + lo_off, l);
                     }
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&op_full[hs]);
+                if (!FULL || hs == 1) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&op_full[FULL ? (int)(s & 1) : hs]);
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);      // every lane has read its share of the raw stage
@@ -582,10 +607,26 @@ extern "C" int dgnn_dw_bwd_tc(const float* dy, const float* z, const float* g, c
         q.n_tgt = n_tgt; q.f_in = f_in; q.f_out = f_out; q.k_total = k_total; q.np = ceil32i(k_total);
         q.partials = partials; q.db_partials = db_partials;
         const size_t raw = (((size_t)DW2_CELLS * 4 * ((size_t)f_out * (g ? 2 : 1) + (size_t)f_in * (agg ? 2 : 1))) + 127) & ~(size_t)127;
-        const size_t smem = 2 * DW_A_BYTES + 2 * (size_t)q.np * 128 + 2 * raw + 1024;
-        if (smem <= 226 * 1024) {
-            if (int rc_ = ensure_dyn_smem((const void*)dw2_tc_kernel, 226 * 1024, "dgnn_dw_bwd_tc")) return rc_;
-            dw2_tc_kernel<<<sm_count(), DW2_THREADS, smem, as_stream(stream)>>>(q);
+        // the kernel runs at (bytes in flight) / (copy round trip): as many raw stages as the shared memory holds
+        const size_t opb = 2 * DW_A_BYTES + 2 * (size_t)q.np * 128;
+#ifndef DGNN_DW2_HALF_ONLY
+        const bool full = 2 * opb + 2 * raw + 1024 <= 226 * 1024;         // two whole operand buffers + >= 2 raw stages fit
+#else
+        const bool full = false;
+#endif
+        const size_t fixed = (full ? 2 : 1) * opb + 1024;
+        int ring = fixed + 2 * raw <= 226 * 1024 ? (int)((226 * 1024 - fixed) / raw) : 0;
+        if (ring > DW2_MAX_RING) ring = DW2_MAX_RING;
+        q.ring = ring;
+        const size_t smem = fixed + (size_t)ring * raw;
+        if (ring >= 2) {
+            if (full) {
+                if (int rc_ = ensure_dyn_smem((const void*)dw2_tc_kernel<1>, 226 * 1024, "dgnn_dw_bwd_tc")) return rc_;
+                dw2_tc_kernel<1><<<sm_count(), DW2_THREADS, smem, as_stream(stream)>>>(q);
+            } else {
+                if (int rc_ = ensure_dyn_smem((const void*)dw2_tc_kernel<0>, 226 * 1024, "dgnn_dw_bwd_tc")) return rc_;
+                dw2_tc_kernel<0><<<sm_count(), DW2_THREADS, smem, as_stream(stream)>>>(q);
+            }
             return check_launch("dgnn_dw_bwd_tc");
         }
     }
