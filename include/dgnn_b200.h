@@ -160,7 +160,11 @@ int dgnn_layer_fwd(const float* x_in, const float* in_scale, const float* in_shi
  *             seg_len = f_out, n_segs = 1
  * packed holds dgnn_tc_packed_floats(n_rows, seg_len, n_segs) floats, rows grouped in slices of
  * `slice` = dgnn_tc_slice(0 forward / 1 backward).  Partial-sum workspaces (stats, db_partials) have
- * dgnn_tc_grid() rows. */
+ * dgnn_tc_grid() rows.
+ * dgnn_dense_fwd_tc / dgnn_dense_bwd_tc (and dgnn_layer_fwd_tc without a table) move their activations with TMA tensor
+ * maps (cp.async.bulk.tensor loads of [128 x 32] atoms, [32 x 32] tensor stores): agg / x_in / dy / z / out / d_agg /
+ * d_self must be 16-byte aligned, row-contiguous float32 matrices.  With db_partials != NULL, or f_in not a multiple of
+ * 32 next to a table, dgnn_dense_bwd_tc takes the older per-thread-load kernel (same results). */
 int dgnn_tc_supported(int f_in, int f_out, int gather);
 int dgnn_tc_grid(void);
 int dgnn_tc_slice(int backward);
