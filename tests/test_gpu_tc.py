@@ -15,7 +15,10 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max()).item()
 
 
-@pytest.mark.parametrize("n,f_in,f_out", [(1000, 28, 64), (129, 64, 128), (4096, 128, 128), (777, 128, 64), (50, 32, 32)])
+@pytest.mark.parametrize("n,f_in,f_out", [(1000, 28, 64), (129, 64, 128), (4096, 128, 128), (777, 128, 64), (50, 32, 32),
+                                          # tensor-map edge cases: one row, rows / columns beyond the boxes, several
+                                          # output slices, a ring longer than a tile
+                                          (1, 4, 4), (127, 36, 132), (128, 100, 260), (31, 256, 40), (20000, 128, 128)])
 def test_dense_forward_tc_matches_fp64(n, f_in, f_out):
     from dgnn_b200 import engine
     torch.manual_seed(0)
@@ -33,7 +36,9 @@ def test_dense_forward_tc_matches_fp64(n, f_in, f_out):
     assert _rel(out, ref) < 2e-6
     # per-channel (sum, sum^2) partials
     st = stats.sum(0)
-    np.testing.assert_allclose(st[0].cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5, atol=1e-3)
+    # a column sum cancels: its error is measured against the sum of magnitudes (fp32 per-tile partials, doubles after)
+    np.testing.assert_allclose(st[0].cpu().numpy(), ref.sum(0).cpu().numpy(), rtol=1e-5,
+                               atol=max(1e-3, 2e-6 * ref.abs().sum(0).max().item()))
     np.testing.assert_allclose(st[1].cpu().numpy(), (ref * ref).sum(0).cpu().numpy(), rtol=1e-5)
     # eval epilogue: affine + relu fused
     osc = torch.rand(f_out, device=DEV) + 0.5
@@ -72,9 +77,11 @@ def test_gather_forward_tc_matches_generic_kernel(f_in, f_out, fe):
     np.testing.assert_allclose(s2.sum(0).cpu().numpy(), s1.sum(0).cpu().numpy(), rtol=2e-5, atol=1e-2)
 
 
+@pytest.mark.parametrize("with_db", [True, False], ids=["db", "nodb"])   # nodb: the TMA tensor-map kernel (db from dW)
 @pytest.mark.parametrize("n,f_in,f_out,gather", [(1000, 28, 64, True), (3000, 128, 128, True), (515, 128, 64, False),
-                                                  (640, 64, 128, True)])
-def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather):
+                                                  (640, 64, 128, True), (1, 32, 4, True), (127, 64, 36, True),
+                                                  (129, 100, 132, False), (130, 160, 300, True), (20000, 128, 128, True)])
+def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather, with_db):
     from dgnn_b200 import engine
     from dgnn_b200._lib import call, lib, ptr
     torch.manual_seed(2)
@@ -93,7 +100,9 @@ def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather):
     bp = engine.pack_b(w_cat.t().contiguous(), k_total, f_out, 1, backward=True)
     d_self = torch.empty(n, f_in, device=DEV)
     d_agg = torch.empty(n, f_in, device=DEV) if gather else None
-    db_p = torch.empty(lib().dgnn_tc_grid(), f_out, dtype=torch.float64, device=DEV)
+    if with_db and f_out > 256:
+        pytest.skip("the shared column sums cover f_out <= 256")
+    db_p = torch.empty(lib().dgnn_tc_grid(), f_out, dtype=torch.float64, device=DEV) if with_db else None
     st = torch.cuda.current_stream().cuda_stream
     call("dgnn_dense_bwd_tc", ptr(dy), ptr(z), ptr(gq), ptr(aq), ptr(bq), ptr(mean), ptr(rstd), ptr(bp), ptr(nbr), n,
          f_in, f_out, ptr(d_agg), ptr(d_self), ptr(db_p), st)
@@ -105,11 +114,13 @@ def test_dense_backward_tc_matches_fp64(n, f_in, f_out, gather):
         assert _rel(d_self, dA[:, f_in:]) < 3e-6
     else:
         assert _rel(d_self, dA) < 3e-6
-    np.testing.assert_allclose(db_p.sum(0).cpu().numpy(), dz.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
+    if with_db:
+        np.testing.assert_allclose(db_p.sum(0).cpu().numpy(), dz.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("n,f_in,f_out,gather", [(1000, 28, 64, True), (5000, 128, 128, True), (515, 128, 64, False),
-                                                  (31, 64, 128, True), (40000, 64, 128, True)])
+                                                  (31, 64, 128, True), (40000, 64, 128, True), (1, 4, 4, False),
+                                                  (33, 28, 64, True), (100, 128, 64, False), (30000, 36, 100, True)])
 def test_dw_tc_matches_fp64(n, f_in, f_out, gather):
     from dgnn_b200._lib import call, lib, ptr
     torch.manual_seed(3)
