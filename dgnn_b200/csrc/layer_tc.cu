@@ -20,6 +20,7 @@
 //     epilogue of tile i (tcgen05.ld -> bias / affine / ReLU / BN partials -> global) after they
 //     have produced tile i+1, and hand the buffer back through `acc_free`.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "umma.cuh"
 #include "common.cuh"
@@ -1013,6 +1014,265 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_tc_kernel(const TcArgs p
     if (warp == D2_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
+// -----------------------------------------------------------------------------------------------------------------------
+// Dense forward, third formulation: the A operand lives in TENSOR MEMORY.  (Built with -DDGNN_DENSE3; not the default.)
+//
+// Measured on B200 (128 -> 128, 604 913 cells): 7.9 us per 128-cell tile against 8.2 us for dense2_tc_kernel, and the
+// knock-out runs of THIS kernel (macros below) say why it is not more: no raw-atom loads 7.9 us, no weight-slice loads
+// 7.9 us, no epilogue 7.1 us, ONE tcgen05.mma per K-atom instead of twelve 5.0 us.  The MMA stream itself is the bound:
+// the 96 kind::tf32 MMAs of a tile (M = 128, N = 128, K = 8) take ~82 ns each, the 48 of the backward (N = 256) ~168 ns,
+// i.e. ~1.27 cycles per accumulator column - 2.5x the nominal 128 N / 256 cycles: with K = 8 per instruction every MMA
+// reads and rewrites the whole fp32 accumulator tile.  So neither shared-memory operand bandwidth (this kernel removes
+// the A reads) nor HBM sets the pace of the 3xTF32 dense kernels, and the same holds for the dW kernel (12 MMAs of
+// N = 256 per 32-cell stage = 2.0 us of its 1.9 us stage time) and for ~3 us per tile of the gather kernels (PHI).
+//
+// dense2_tc_kernel is bound by shared-memory bandwidth: a tf32 MMA with both operands in shared memory reads 128 B/clk at
+// N = 128 - all there is - and 3xTF32 triples those reads.  tcgen05.mma takes A from TMEM instead: the producers read the
+// TMA-landed raw atom once (thread = one row of the atom and half of its 32 columns), apply the affine + ReLU, split hi / lo
+// and write both with tcgen05.st (lane = row, column = k).  The raw slot is released as soon as the producers hold it in
+// registers, the MMAs read only the weight slice from shared memory, nothing is written back to it.
+//   TMEM (512 columns): two accumulators of <= 128 columns, then a ring of 4 A stages of 64 columns (hi | lo).
+//   Shared memory: raw landing ring (16 KB per atom), weight-slice ring, epilogue staging, coefficient table.
+constexpr int D3_TSTAGES = 4;                  // A stages in TMEM
+constexpr int D3_MAX_RAW = 8;
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T, one K = 8 step; single thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(D2_THREADS, 1) dense3_fwd_kernel(const TcArgs p, const __grid_constant__ CUtensorMap tm0,
+                                                                   const __grid_constant__ CUtensorMap tm1,
+                                                                   const __grid_constant__ CUtensorMap tmo0, int raw_stages,
+                                                                   int b_stages) {
+    constexpr int MODE = MODE_FWD_DENSE;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t raw_full[D3_MAX_RAW], raw_empty[D3_MAX_RAW], at_full[D3_TSTAGES], at_empty[D3_TSTAGES];
+    __shared__ uint64_t b_full[D2_MAX_B], b_empty[D2_MAX_B], bar_acc_full[2], bar_acc_free[2];
+    __shared__ uint32_t tmem_slot;
+    __shared__ double red_st[2 * 256];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int b_atom_bytes = p.np * ATOM_ROW_BYTES;
+    const uint32_t raw_base = smem_u32(smem);
+    const uint32_t b_base = raw_base + (uint32_t)raw_stages * A_ATOM_BYTES;
+    const uint32_t rings = (uint32_t)raw_stages * A_ATOM_BYTES + (uint32_t)b_stages * 2u * (uint32_t)b_atom_bytes;
+    const uint32_t stage_base = raw_base + rings;
+    float* tab = reinterpret_cast<float*>(smem + rings + D2_NEW * 4096);
+    const int ka_x = p.ka - p.ka_agg;
+    const int tab_n = ka_x * ATOM_K;
+
+    if (tid == 0) {
+        for (int s = 0; s < D3_MAX_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], D2_NPW); }
+        for (int s = 0; s < D3_TSTAGES; ++s) { mbar_init(&at_full[s], D2_NPW); mbar_init(&at_empty[s], 1); }
+        for (int s = 0; s < D2_MAX_B; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_free[b], D2_NEW); }
+        fence_barrier_init();
+    }
+    for (int c = tid; c < 512; c += D2_THREADS) red_st[c] = 0.0;
+    for (int c = tid; c < tab_n; c += D2_THREADS) {
+        const bool on = p.in_scale != nullptr && c < p.f_in;
+        tab[c] = on ? __ldg(p.in_scale + c) : 1.f;
+        tab[tab_n + c] = on ? __ldg(p.in_shift + c) : 0.f;
+    }
+    if (warp == D2_WARPS) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_a0 = tmem_base + 256u;                 // A stages behind the two accumulators
+    const int64_t n_tiles = (p.n_tgt + TC_M - 1) / TC_M;
+
+    if (warp == D2_WARPS) {
+        // ------------------------------------------------------------------ MMA warp
+        const uint32_t idesc = make_idesc_tf32(TC_M, p.np);
+        uint32_t tile_cnt = 0, ts = 0, ut = 0, sb = 0, ub = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const uint32_t acc = tile_cnt & 1;
+            const uint32_t tmem_acc = tmem_base + acc * 128u;
+            for (int a = 0; a < p.ka; ++a) {
+                if (lane == 0) {
+                    if (a == 0 && tile_cnt >= 2) mbar_wait(&bar_acc_free[acc], ((tile_cnt >> 1) - 1) & 1);
+                    mbar_wait(&b_full[sb], ub & 1);
+                    mbar_wait(&at_full[ts], ut & 1);
+                    tc_fence_after_sync();
+                    const uint32_t ah = tmem_a0 + ts * 64u, al = ah + 32u;
+                    const uint32_t bh = b_base + sb * 2u * (uint32_t)b_atom_bytes, bl = bh + (uint32_t)b_atom_bytes;
+#ifdef DGNN_D3_NOMMA    // timing experiment: one MMA per atom instead of twelve (wrong results)
+                    for (int kk = 0; kk < 1; ++kk) {
+                        const uint32_t ko = kk * 32, kc = kk * 8;
+                        mma_tf32_ts(tmem_acc, ah + kc, make_desc(bh + ko), idesc, (a > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    if (false)
+#endif
+#pragma unroll
+                    for (int kk = 0; kk < ATOM_K / 8; ++kk) {
+                        const uint32_t ko = kk * 32, kc = kk * 8;
+                        mma_tf32_ts(tmem_acc, ah + kc, make_desc(bh + ko), idesc, (a > 0 || kk > 0) ? 1u : 0u);
+                        mma_tf32_ts(tmem_acc, al + kc, make_desc(bh + ko), idesc, 1u);
+                        mma_tf32_ts(tmem_acc, ah + kc, make_desc(bl + ko), idesc, 1u);
+                    }
+                    mma_commit(&at_empty[ts]);
+                    mma_commit(&b_empty[sb]);
+                    if (a == p.ka - 1) mma_commit(&bar_acc_full[acc]);
+                }
+                __syncwarp();
+                if (++ts == D3_TSTAGES) { ts = 0; ++ut; }
+                if (++sb == (uint32_t)b_stages) { sb = 0; ++ub; }
+            }
+        }
+    } else if (warp == D2_WARPS + 1) {
+        // ------------------------------------------------------------------ TMA-A warp: raw atoms, a ring ahead
+        if (lane == 0) {
+            uint32_t rs = 0, ur = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int row0 = (int)(tile * TC_M);
+                for (int a = 0; a < p.ka; ++a) {
+                    mbar_wait(&raw_empty[rs], (ur & 1) ^ 1);
+#ifdef DGNN_D3_NOA      // timing experiment: no raw atoms loaded (wrong results)
+                    mbar_arrive(&raw_full[rs]);
+#else
+                    mbar_arrive_expect_tx(&raw_full[rs], (uint32_t)A_ATOM_BYTES);
+                    if (a < p.ka_agg) tma_load_2d(raw_base + rs * A_ATOM_BYTES, &tm0, a * ATOM_K, row0, &raw_full[rs]);
+                    else tma_load_2d(raw_base + rs * A_ATOM_BYTES, &tm1, (a - p.ka_agg) * ATOM_K, row0, &raw_full[rs]);
+#endif
+                    if (++rs == (uint32_t)raw_stages) { rs = 0; ++ur; }
+                }
+            }
+        }
+    } else if (warp == D2_WARPS + 2) {
+        // ------------------------------------------------------------------ TMA-B warp: weight slices (L2), a ring ahead
+        if (lane == 0) {
+            uint32_t sb = 0, ub = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int a = 0; a < p.ka; ++a) {
+                    uint8_t* b_hi = smem + (size_t)raw_stages * A_ATOM_BYTES + (size_t)sb * 2 * b_atom_bytes;
+                    mbar_wait(&b_empty[sb], (ub & 1) ^ 1);
+#ifdef DGNN_D3_NOB      // timing experiment: no weight slices loaded (wrong results)
+                    mbar_arrive(&b_full[sb]); (void)b_hi;
+#else
+                    mbar_arrive_expect_tx(&b_full[sb], 2u * (uint32_t)b_atom_bytes);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.b_packed) + (size_t)a * 2 * b_atom_bytes;
+                    bulk_g2s(b_hi, src, 2u * (uint32_t)b_atom_bytes, &b_full[sb]);
+#endif
+                    if (++sb == (uint32_t)b_stages) { sb = 0; ++ub; }
+                }
+            }
+        }
+    } else if (warp >= D2_NPW) {
+        // ------------------------------------------------------------------ epilogue warps (TMEM lane quarter warp & 3)
+        double st_sum[4] = {0.0, 0.0, 0.0, 0.0}, st_sq[4] = {0.0, 0.0, 0.0, 0.0};
+        uint32_t tile_cnt = 0;
+        const int4 nb_epi = make_int4(-1, -1, -1, -1);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_cnt) {
+            const int64_t tile0 = tile * TC_M;
+            const uint32_t acc = tile_cnt & 1;
+            mbar_wait(&bar_acc_full[acc], (tile_cnt >> 1) & 1);
+            tc_fence_after_sync();
+#ifndef DGNN_D3_NOEPI   // timing experiment: no epilogue (no results)
+            epilogue2<MODE>(p, &tmo0, &tmo0, tmem_base + acc * 128u, tile0, warp, lane,
+                            stage_base + (uint32_t)(warp - D2_NPW) * 4096u, st_sum, st_sq, nb_epi);
+#endif
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_free[acc]);
+        }
+        if (lane == 0) tma_store_wait_all();
+        if (p.stats != nullptr) {
+            const int grp = (warp >> 2) & 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (grp + 2 * j) * 32 + lane;
+                if (c < p.f_out) {
+                    atomicAdd(&red_st[c], st_sum[j]);
+                    atomicAdd(&red_st[256 + c], st_sq[j]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ producer warps: raw atom -> TMEM (hi | lo)
+        // thread = row 32 q + lane of the atom (q = warp & 3 = the TMEM lane quarter this warp may touch) and the 16 columns
+        // of half = warp >> 2
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t r = (uint32_t)(q * 32 + lane);
+        uint32_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) off[i] = r * 128u + ((((uint32_t)(4 * half + i)) ^ (r & 7u)) << 4);
+        const uint32_t tab_u32 = smem_u32(tab) + (uint32_t)half * 64u;
+        const bool relu = p.relu_in != 0;
+        const bool affine = p.in_scale != nullptr;
+        const uint32_t t_lane = tmem_a0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * half);
+        uint32_t rs = 0, ur = 0, ts = 0, ut = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int a = 0; a < p.ka; ++a) {
+                const uint32_t slot = raw_base + rs * A_ATOM_BYTES;
+                mbar_wait(&raw_full[rs], ur & 1);
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 x4 = lds128(slot + off[i]);
+                    v[4 * i] = x4.x; v[4 * i + 1] = x4.y; v[4 * i + 2] = x4.z; v[4 * i + 3] = x4.w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[rs]);          // the atom is in registers: the slot may be refilled
+                if (a >= p.ka_agg) {
+                    if (affine) {
+                        const uint32_t t = tab_u32 + (uint32_t)(a - p.ka_agg) * 128u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 sc = lds128(t + 16u * i), sh = lds128(t + (uint32_t)tab_n * 4u + 16u * i);
+                            v[4 * i] = act(v[4 * i], sc.x, sh.x, relu); v[4 * i + 1] = act(v[4 * i + 1], sc.y, sh.y, relu);
+                            v[4 * i + 2] = act(v[4 * i + 2], sc.z, sh.z, relu); v[4 * i + 3] = act(v[4 * i + 3], sc.w, sh.w, relu);
+                        }
+                    } else if (relu) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                }
+                float lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split_tf32(v[i], v[i], lo[i]);
+                mbar_wait(&at_empty[ts], (ut & 1) ^ 1);               // the MMAs that read this TMEM stage are done
+                tc_fence_after_sync();
+                tmem_st16(t_lane + ts * 64u, v);
+                tmem_st16(t_lane + ts * 64u + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&at_full[ts]);
+                if (++rs == (uint32_t)raw_stages) { rs = 0; ++ur; }
+                if (++ts == D3_TSTAGES) { ts = 0; ++ut; }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (p.stats != nullptr) {
+        double* my = p.stats + (size_t)blockIdx.x * 2 * p.stats_ld;
+        for (int c = tid; c < p.f_out; c += D2_THREADS) {
+            my[c] = red_st[c];
+            my[p.stats_ld + c] = red_st[256 + c];
+        }
+    }
+    if (warp == D2_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
 // ---- weight packing: w[n, k] (row stride ld) -> per K-atom swizzled hi / lo images ---------------
 // Rows are packed in slices of `slice` rows (= one launch's N): slice s holds [KA][2][np_s][32] with np_s = its padded rows.
 constexpr int TC_NSLICE = 256;      // backward: N = columns of [d_agg | d_self] per launch (2 stages of 96 KB)
@@ -1196,6 +1456,23 @@ static int fwd_slices_d2(TcArgs p, int f_out, cudaStream_t st, const char* what)
         p.b_packed = bp + (size_t)(n0 / TC_FWD_SLICE) * p.ka * 2 * TC_FWD_SLICE * ATOM_K;
         CUtensorMap tm_out;                            // the slice's columns of z: [n_tgt x w], row stride f_out
         if (int rc = make_tmap_atoms(&tm_out, p.out, p.n_tgt, w, f_out, what, 32)) return rc;
+#ifdef DGNN_DENSE3
+        {   // A operand in tensor memory (dense3_fwd_kernel): np <= 128 always holds for a forward slice
+            const int tab = 2 * (p.ka - p.ka_agg) * ATOM_K;
+            const int budget = 227 * 1024 - 4608 - 1024 - tab * 4 - D2_NEW * 4096;
+            const int b_bytes = 2 * p.np * ATOM_ROW_BYTES;
+            static const int b_env = getenv("DGNN_D3_B") ? atoi(getenv("DGNN_D3_B")) : 3;
+            int b_st = b_env, raw_st = (budget - b_st * b_bytes) / A_ATOM_BYTES;
+            if (raw_st > D3_MAX_RAW) raw_st = D3_MAX_RAW;
+            if (raw_st >= 2) {
+                const size_t smem = (size_t)raw_st * A_ATOM_BYTES + (size_t)b_st * b_bytes + (size_t)tab * 4 + D2_NEW * 4096 + 1024;
+                if (int rc_ = ensure_dyn_smem((const void*)dense3_fwd_kernel, 227 * 1024 - 4608, what)) return rc_;
+                dense3_fwd_kernel<<<sm_count(), D2_THREADS, smem, st>>>(p, tm_agg, tm_x, tm_out, raw_st, b_st);
+                if (int rc = check_launch(what)) return rc;
+                continue;
+            }
+        }
+#endif
         if (int rc = launch_d2<MODE_FWD_DENSE>(p, tm_agg, tm_x, tm_out, tm_out, st, what)) return rc;
     }
     return 0;
