@@ -1019,12 +1019,11 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_tc_kernel(const TcArgs p
 //
 // Measured on B200 (128 -> 128, 604 913 cells): 7.9 us per 128-cell tile against 8.2 us for dense2_tc_kernel, and the
 // knock-out runs of THIS kernel (macros below) say why it is not more: no raw-atom loads 7.9 us, no weight-slice loads
-// 7.9 us, no epilogue 7.1 us, ONE tcgen05.mma per K-atom instead of twelve 5.0 us.  The MMA stream itself is the bound:
-// the 96 kind::tf32 MMAs of a tile (M = 128, N = 128, K = 8) take ~82 ns each, the 48 of the backward (N = 256) ~168 ns,
-// i.e. ~1.27 cycles per accumulator column - 2.5x the nominal 128 N / 256 cycles: with K = 8 per instruction every MMA
-// reads and rewrites the whole fp32 accumulator tile.  So neither shared-memory operand bandwidth (this kernel removes
-// the A reads) nor HBM sets the pace of the 3xTF32 dense kernels, and the same holds for the dW kernel (12 MMAs of
-// N = 256 per 32-cell stage = 2.0 us of its 1.9 us stage time) and for ~3 us per tile of the gather kernels (PHI).
+// 7.9 us, no epilogue 7.1 us, ONE tcgen05.mma per K-atom instead of twelve 5.0 us.  The MMA stream of the one issuing
+// thread is the bound: tools/bench_umma measures 216 - 245 cycles per tcgen05.mma issued from one thread whatever N, data
+// type, swizzle or A source (122 / 61 from two / four issuing warps), and a tile needs 96 of them.  Several issuing warps
+// were tried in dense2_tc_kernel (7.7 us) and dropped: MMAs of different threads are unordered, so the fp32 accumulation
+// order - and the last bits of the result - changed from run to run, and the repo guarantees bit-identical launches.
 //
 // dense2_tc_kernel is bound by shared-memory bandwidth: a tf32 MMA with both operands in shared memory reads 128 B/clk at
 // N = 128 - all there is - and 3xTF32 triples those reads.  tcgen05.mma takes A from TMEM instead: the producers read the
