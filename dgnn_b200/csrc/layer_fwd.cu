@@ -47,7 +47,8 @@ __device__ __forceinline__ void gather_tile(const LayerFwdArgs& p, float* a_s, i
     const int ipw = 32 / lpc;                                       // items per warp pass
     const int sub = lane / lpc, li = lane % lpc;
     const int nch = (F + 63) >> 6;
-    const bool relu = p.relu_in != 0;
+    const bool relu = (p.relu_in & 1) != 0;
+    const bool self_loop = (p.relu_in & 2) != 0;   // run.py:70-71,215-216: add_self_loops (edge_convs == 0 only)
     for (int c = 0; c < nch; ++c) {
         const int f = c * 64 + li * 2;
         const bool fv = f < F;
@@ -104,11 +105,14 @@ __device__ __forceinline__ void gather_tile(const LayerFwdArgs& p, float* a_s, i
                 a1 = fmaf(h1, ph1, a1);
             }
             if (fv) {
+                float s0 = tv ? act(self.x, sc0, sh0, relu) : 0.f;
+                float s1 = tv ? act(self.y, sc1, sh1, relu) : 0.f;
+                if (self_loop && tv) {                 // the cell is its own fifth in-neighbour (no edge filter: phi = 1)
+                    a0 += s0; a1 += s1; ++cnt;
+                }
                 float d = (float)(cnt > 0 ? cnt : 1);
                 a0 = a0 / d;
                 a1 = a1 / d;
-                float s0 = tv ? act(self.x, sc0, sh0, relu) : 0.f;
-                float s1 = tv ? act(self.y, sc1, sh1, relu) : 0.f;
                 *reinterpret_cast<float2*>(a_s + cell * p.lda + f) = make_float2(a0, a1);
                 *reinterpret_cast<float2*>(a_s + cell * p.lda + F + f) = make_float2(s0, s1);
                 if (p.agg_save != nullptr && tv)
@@ -122,7 +126,7 @@ __device__ __forceinline__ void gather_tile(const LayerFwdArgs& p, float* a_s, i
 __device__ __forceinline__ void load_tile_dense(const LayerFwdArgs& p, float* a_s, int64_t tile0) {
     const int F = p.f_in;
     const int f4 = F >> 2;
-    const bool relu = p.relu_in != 0;
+    const bool relu = (p.relu_in & 1) != 0;
     for (int idx = threadIdx.x; idx < TM * f4; idx += NT) {
         int r = idx / f4, c = (idx % f4) * 4;
         int64_t t = tile0 + r;
@@ -294,6 +298,7 @@ extern "C" int dgnn_layer_fwd(const float* x_in, const float* in_scale, const fl
     if (w_e == nullptr) fe = 0;
     DGNN_REQUIRE(fe % 4 == 0 && fe <= 32, "edge feature width must be a multiple of 4 and <= 32");
     DGNN_REQUIRE(nbr != nullptr || agg_save == nullptr, "agg_save needs a gather layer");
+    DGNN_REQUIRE((relu_in & 2) == 0 || (fe == 0 && nbr != nullptr), "self loops (relu_in bit 1) need a gather layer without an edge filter");
     DGNN_REQUIRE(fe == 0 || (ea != nullptr && b_e != nullptr), "edge filter needs ea and b_e");
     LayerFwdArgs p;
     p.x_in = x_in; p.in_scale = in_scale; p.in_shift = in_shift; p.relu_in = relu_in;

@@ -205,6 +205,12 @@ def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGra
                out_aff: Optional[Affine], relu_out: bool, n_tgt, f_in, f_out, want_agg, want_stats, b_packed=None,
                out_rows=None):
     dev = x_in.device
+    loops = g is not None and g.self_loops
+    if loops:
+        # add_self_loops (run.py:70-71, edge_convs == 0): the generic kernel takes the flag as bit 1 of relu_in
+        if fe:
+            raise DgnnError("self loops are only defined without an edge filter (model.edge_convs == 0)")
+        b_packed = None
     out = torch.empty((out_rows or n_tgt, f_out), dtype=torch.float32, device=dev)
     agg = torch.empty((n_tgt, f_in), dtype=torch.float32, device=dev) if want_agg else None
     stats = None
@@ -212,7 +218,8 @@ def _layer_fwd(x_in, in_aff: Optional[Affine], relu_in: bool, g: Optional[EllGra
         grid = lib().dgnn_tc_grid() if b_packed is not None else lib().dgnn_layer_grid(f_in, f_out)
         stats = torch.empty((grid, 2, f_out), dtype=torch.float64, device=dev)
     call("dgnn_layer_fwd_tc" if b_packed is not None else "dgnn_layer_fwd", ptr(x_in), ptr(in_aff.scale) if in_aff else None, ptr(in_aff.shift) if in_aff else None,
-         int(relu_in), ptr(g.nbr) if g is not None else None, ptr(g.ea_in) if (g is not None and fe) else None, fe,
+         int(relu_in) | (2 if loops else 0), ptr(g.nbr) if g is not None else None,
+         ptr(g.ea_in) if (g is not None and fe) else None, fe,
          ptr(w_e), ptr(b_e), ptr(b_packed) if b_packed is not None else ptr(pk_wt), ptr(pk_bias),
          ptr(out_aff.scale) if out_aff else None, ptr(out_aff.shift) if out_aff else None, int(relu_out),
          n_tgt, f_in, f_out, ptr(out), ptr(agg), ptr(stats), _stream())
@@ -589,6 +596,14 @@ def backward(spec: NetSpec, sv: Saved, dout: torch.Tensor, comm=None):
         relu_in = l > 0
         d_agg, d_self, db, dw = _dense_and_dw(dy, sv.z[l], coeffs, aff, pk.w_cat, g, sv.agg[l], x_in, in_aff, relu_in,
                                               g.n_tgt, pk.f_in, pk.f_out, agg_rows=g.n_src if comm else None)
+        if g.self_loops:
+            # the self edge t -> t: the mean runs over cnt + 1 rows (the kernel scaled d_agg by 1 / max(cnt, 1)), and the
+            # cell's own activation receives d_agg[t] like any other source of t
+            if comm is not None:
+                raise DgnnError("self loops on a partitioned scene are not supported")
+            cnt = (g.nbr >= 0).sum(1, dtype=torch.float32)
+            d_agg[:g.n_tgt] *= (cnt.clamp(min=1.0) / (cnt + 1.0)).unsqueeze(1)
+            d_self += d_agg[:g.n_tgt]
         # sources whose gradient this rank produces: all of them, or (partitioned) the owned rows only, with the
         # d_agg rows of halo targets fetched from their owners
         n_srcs = g.n_src

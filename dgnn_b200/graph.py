@@ -19,7 +19,7 @@ centroid when positions are known, reverse Cuthill-McKee of the adjacency otherw
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
@@ -60,6 +60,7 @@ class EllGraph:
     _eid_out: Optional[torch.Tensor] = None  # int32[n_src,4]: local edge id of every (source, out-slot), -1 = none
     ea_edges: Optional[torch.Tensor] = None  # float32[E, fe]: edge attributes in edge-list order (edge_convs == 2)
     _orow: Optional[torch.Tensor] = None     # int32[n_src,4]: row 4t+k (incoming order) of every out-edge, -1 = none
+    self_loops: bool = False                 # every target is also its own in-neighbour (edge_convs == 0, run.py:70-71)
 
     def orow(self) -> torch.Tensor:
         """Row of the incoming-order edge matrix [n_tgt*4, .] that holds the out-edge (s, j): inverts _eid_in."""
@@ -123,6 +124,23 @@ def locality_order(edge_index_cpu: Optional[torch.Tensor], n: int, pos: Optional
     return None
 
 
+def strip_self_loops(edge_index: torch.Tensor, n_tgt: int, edge_attr) -> Tuple[torch.Tensor, bool]:
+    """``add_self_loops`` (``run.py:70-71,215-216``, only when ``model.edge_convs == 0``) appends one edge ``t -> t`` per
+    node.  The ELL-4 table keeps the four facet neighbours; the self edge becomes a flag of the layout (the kernels add
+    ``h(t)`` to the sum and 1 to the count).  Returns the edge list without self edges and whether there were any; a
+    graph where only SOME targets carry a self edge, or one with edge attributes, is rejected."""
+    loops = edge_index[0] == edge_index[1]
+    n_loops = int(loops.sum().item())
+    if n_loops == 0:
+        return edge_index, False
+    if edge_attr is not None:
+        raise _lib.DgnnError("self loops are only defined without edge attributes (model.edge_convs == 0, run.py:70)")
+    tg = edge_index[1][loops]
+    if n_loops != n_tgt or int(torch.unique(tg).numel()) != n_tgt or int(tg.max().item()) >= n_tgt:
+        raise _lib.DgnnError("self loops must cover every target exactly once (add_self_loops)")
+    return edge_index[:, ~loops].contiguous(), True
+
+
 def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor], n: int, device,
                      pos: Optional[torch.Tensor] = None, order: str = "auto",
                      need_backward: bool = True, e_id: Optional[torch.Tensor] = None) -> EllGraph:
@@ -134,6 +152,11 @@ def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor]
     """
     dev = torch.device(device)
     _lib.check_device(dev.index or 0)
+    edge_index, loops = strip_self_loops(edge_index, n, edge_attr)
+    if loops:
+        g = build_full_graph(edge_index, None, n, device, pos, order, need_backward, None)
+        g.self_loops = True
+        return g
     fe = 0 if edge_attr is None else pad4(edge_attr.shape[1])
     if e_id is not None and edge_attr is not None and (edge_attr.shape[1] % 4 or not edge_attr.is_contiguous()
                                                        or edge_attr.dtype != torch.float32):
@@ -192,6 +215,11 @@ def build_from_edges(edge_index: torch.Tensor, e_id: Optional[torch.Tensor], edg
     ``edge_attr`` rows are selected by ``e_id`` (all edges in order when ``e_id`` is None)."""
     dev = torch.device(device)
     _lib.check_device(dev.index or 0)
+    edge_index, loops = strip_self_loops(edge_index, n_tgt, edge_attr)
+    if loops:
+        g = build_from_edges(edge_index, None, None, n_src, n_tgt, device, need_backward)
+        g.self_loops = True
+        return g
     st = _stream()
     ei = edge_index.to(dev, dtype=torch.int64).contiguous()
     E = ei.shape[1]

@@ -70,6 +70,15 @@ class NeighborSampler:
             num_nodes = node_idx.numel()                       # PyG: a mask fixes the node count
         n = (int(ei.max().item()) + 1 if ei.numel() else 0) if num_nodes is None else int(num_nodes)
         self.num_nodes = n
+        # add_self_loops (run.py:70-71, edge_convs == 0): one edge i -> i per node behind the E facet edges.  The table keeps
+        # the facet edges; every hop's Adj gets the self edges of its targets back (ids E + node, as add_self_loops numbers them)
+        loops = ei[0] == ei[1]
+        self.self_loops = bool(loops.any().item()) if ei.numel() else False
+        if self.self_loops:
+            if int(loops.sum().item()) != n or torch.unique(ei[0][loops]).numel() != n:
+                raise DgnnError("self loops must cover every node exactly once (add_self_loops)")
+            ei = ei[:, ~loops].contiguous()
+        self._n_facet_edges = ei.shape[1]
         e = ei.shape[1]
         with torch.cuda.device(self.device):
             self.in_src = torch.empty((n, 4), dtype=torch.int32, device=self.device)
@@ -142,6 +151,10 @@ class NeighborSampler:
                 new_ids = torch.empty(n_new, dtype=torch.int64, device=dev)
                 call("dgnn_sampler_assign", ptr(src_g), n_e, ptr(flag), ptr(rank), n_tgt, ptr(self._loc), ptr(self._first),
                      ptr(new_ids), ptr(edge_local[0]), st)
+                if self.self_loops:
+                    own = torch.arange(n_tgt, dtype=torch.int64, device=dev)
+                    edge_local = torch.cat([edge_local, torch.stack([own, own])], dim=1)
+                    e_id = torch.cat([e_id, self._n_facet_edges + n_id[:n_tgt]])
                 n_id = torch.cat([n_id, new_ids]) if n_new else n_id
                 adjs.append(Adj(edge_local, e_id if self.return_e_id else None, (n_id.numel(), n_tgt)))
             call("dgnn_sampler_set_loc", ptr(n_id), n_id.numel(), -1, ptr(self._loc), st)   # scratch back to "absent"

@@ -138,7 +138,8 @@ int dgnn_column_standardize_f64(const double* x, int64_t n, int ld, int col0, in
  * With nbr == NULL the gather is skipped (dense layer: z = h(t) . wt_cat + bias, k_total = f_in).
  * agg_save (nullable) receives agg (training).  stats (nullable) = double[grid, 2, f_out]
  * per-CTA partial (sum z, sum z^2) over valid rows; grid = dgnn_layer_grid().
- * ea_stride = floats per edge row in `ea` (>= fe).  */
+ * ea_stride = floats per edge row in `ea` (>= fe).   * relu_in: bit 0 = ReLU on load; bit 1 (dgnn_layer_fwd only, fe == 0) = self loops: every target is its own fifth
+ * in-neighbour, agg = (sum_k h(nbr_k) + h(t)) / (cnt + 1)  (run.py:70-71,215-216 add_self_loops when edge_convs == 0). */
 int dgnn_layer_grid(int f_in, int f_out);
 int dgnn_layer_fwd(const float* x_in, const float* in_scale, const float* in_shift, int relu_in,
                    const int32_t* nbr, const float* ea, int fe,

@@ -326,3 +326,57 @@ def test_tiny_graphs(n_points):
         z, zr = net.inference_layer(d), ref.inference_layer(d)
     err, ok = logits_close(z.cpu().numpy(), zr.numpy())
     assert ok, err
+
+
+def _with_self_loops(d):
+    """``add_self_loops(edge_index)[0]`` (run.py:70-71,215-216): one edge i -> i per node behind the facet edges."""
+    n = d.x.shape[0]
+    own = torch.arange(n, dtype=torch.int64)
+    # edge_attr keeps its 4 N rows: the reference samples with return_e_id = model.edge_convs = 0 and never reads it
+    return to_attr(dict(x=d.x, y=d.y, edge_attr=d.edge_attr,
+                        edge_index=torch.cat([d.edge_index, torch.stack([own, own])], dim=1)))
+
+
+def _full_batch_no_eid(d, n_layers_plus=5):
+    n = d.x.shape[0]
+    return to_attr(dict(all=d, batch_n_id=torch.arange(n), batch_adjs=[(d.edge_index, None, (n, n))] * n_layers_plus))
+
+
+SL_KW = dict(convs=(16, 32, 32, 32), edge_convs=0, decoder=1, n_edge_feat=None)
+
+
+def test_self_loops_whole_graph_train_step_and_inference():
+    """``graph.self_loops: 1`` with ``model.edge_convs: 0`` (run.py:70-71,215-216): every cell is its own fifth
+    in-neighbour.  Whole-graph train step (logits, loss, every gradient) and inference against the oracle."""
+    g = make_graph(700, seed=33)
+    d = _with_self_loops(data_all(g))
+    net, ref = _train_compare(SL_KW, _full_batch_no_eid(d), d, d.x.shape[0])
+    net.eval(); ref.eval()
+    with torch.no_grad():
+        z, zr = net.inference_layer(d).cpu().numpy(), ref.inference_layer(d).numpy()
+    err, ok = logits_close(z, zr)
+    assert ok, err
+
+
+def test_self_loops_sampled_closure_and_device_sampler():
+    """Seed-batch training on a self-looped graph: the closure sampled by the oracle's restatement of PyG's sampler
+    (five in-edges per target), and the device sampler yielding the same nodes and the same edges per hop."""
+    from dgnn_b200.sampler import NeighborSampler as DeviceSampler
+    g = make_graph(500, seed=34)
+    d = _with_self_loops(data_all(g))
+    L = len(SL_KW["convs"])
+    seeds = torch.arange(30, 126)
+    smp = NeighborSampler(d.edge_index, [-1] * (L + 1), 96, node_idx=seeds, num_nodes=d.x.shape[0])
+    bs, n_id, adjs = next(iter(smp))
+    adjs = [(a[0], None, a[2]) for a in adjs]              # return_e_id = model.edge_convs = 0 (run.py:74)
+    data = to_attr(dict(all=d, batch_n_id=n_id, batch_adjs=adjs))
+    _train_compare(SL_KW, data, d, adjs[L - 1][2][1])
+    dsm = DeviceSampler(d.edge_index, [-1] * (L + 1), node_idx=seeds, num_nodes=d.x.shape[0], batch_size=96,
+                        return_e_id=False, device=DEV)
+    assert dsm.self_loops
+    bs2, n_id2, adjs2 = next(iter(dsm))
+    assert bs2 == bs and torch.equal(n_id2.cpu(), n_id)
+    for a, b in zip(adjs, adjs2):
+        assert tuple(a[2]) == tuple(b.size)
+        ka = sorted(map(tuple, a[0].t().tolist())); kb = sorted(map(tuple, b.edge_index.t().cpu().tolist()))
+        assert ka == kb

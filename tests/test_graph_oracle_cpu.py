@@ -106,3 +106,22 @@ def test_product_generator_matches_oracle_generator():
         fb = og.synthetic_features(gb[1].shape[0], gb[1], seed=9)
         for u, v in zip(fa, fb):
             assert np.array_equal(u, v)
+
+
+def test_strip_self_loops_contract():
+    """``add_self_loops`` lists (run.py:70-71): the self edges become a flag, partial or attributed self loops are rejected."""
+    import pytest
+    import torch
+    from dgnn_b200._lib import DgnnError
+    from dgnn_b200.graph import strip_self_loops
+    ei = torch.tensor([[1, 2, 0, 2, 0, 1], [0, 0, 1, 1, 2, 2]])
+    out, loops = strip_self_loops(ei, 3, None)
+    assert not loops and out is ei
+    own = torch.arange(3)
+    sl = torch.cat([ei, torch.stack([own, own])], dim=1)
+    out, loops = strip_self_loops(sl, 3, None)
+    assert loops and torch.equal(out, ei)
+    with pytest.raises(DgnnError):
+        strip_self_loops(sl[:, :-1], 3, None)            # a target without its self edge
+    with pytest.raises(DgnnError):
+        strip_self_loops(sl, 3, torch.zeros(9, 4))       # self loops next to edge attributes (edge_convs != 0)
