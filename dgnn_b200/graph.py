@@ -129,6 +129,8 @@ def strip_self_loops(edge_index: torch.Tensor, n_tgt: int, edge_attr) -> Tuple[t
     node.  The ELL-4 table keeps the four facet neighbours; the self edge becomes a flag of the layout (the kernels add
     ``h(t)`` to the sum and 1 to the count).  Returns the edge list without self edges and whether there were any; a
     graph where only SOME targets carry a self edge, or one with edge attributes, is rejected."""
+    if edge_index.shape[1] < n_tgt:                 # add_self_loops appends one edge per node: fewer edges, no self loops
+        return edge_index, False
     loops = edge_index[0] == edge_index[1]
     n_loops = int(loops.sum().item())
     if n_loops == 0:
@@ -152,7 +154,10 @@ def build_full_graph(edge_index: torch.Tensor, edge_attr: Optional[torch.Tensor]
     """
     dev = torch.device(device)
     _lib.check_device(dev.index or 0)
-    edge_index, loops = strip_self_loops(edge_index, n, edge_attr)
+    # (4 n edges = the facet list of the reference's files, where a cell never neighbours itself: no scan, no sync)
+    loops = False
+    if edge_index.shape[1] != 4 * n:
+        edge_index, loops = strip_self_loops(edge_index, n, edge_attr)
     if loops:
         g = build_full_graph(edge_index, None, n, device, pos, order, need_backward, None)
         g.self_loops = True
