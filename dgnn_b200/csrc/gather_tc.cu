@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
     for (int i = tid; i < 4 * 32; i += G_THREADS)
         *reinterpret_cast<float*>(smem + (size_t)(i >> 5) * G_P_BYTES + G_ATOM + atom_off(p.fe, i & 31)) = 1.0f;
     fence_proxy_async_smem();
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);        // one [128 x 32] accumulator per row quarter
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);        // one [128 x 64] accumulator (P . EA_hi | P . EA_lo) per row quarter
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
     const uint32_t n_my = (int64_t)blockIdx.x < n_tiles ? (uint32_t)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
 
     {
-        const uint32_t idesc = make_idesc_tf32(G_M, 32);
+        const uint32_t idesc = make_idesc_tf32(G_M, DWE_ROUNDS == 1 ? 64 : 32);
         // row quarter q = warp >> 2: the four warps of a quarter sit on four different schedulers, so a quarter that waits
         // for its MMAs does not idle a whole scheduler (TMEM is only touched in the read-out below)
         const int q = warp >> 2, grp = warp & 3;
@@ -767,13 +767,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                                 // every quarter accumulates into its own TMEM columns, its rounds in order: the sum over
                                 // cells is evaluated in a fixed order whatever the timing of the warps
                                 const uint32_t ph = smem_u32(pq), ehh = ph + G_ATOM, ell = ehh + 32 * 128;
-                                const uint32_t dq = tmem_base + (uint32_t)(q * 32);
+                                const uint32_t dq = tmem_base + (uint32_t)(q * 64);
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk) {
                                     const uint32_t ko = kk * 32;
-                                    mma_tf32(dq, make_desc(ph + ko), make_desc(ehh + ko), idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                                    if (rnd == 0) mma_tf32(dq, make_desc(ph + ko), make_desc(ell + ko), idesc, 1u);
+                                    if (DWE_ROUNDS == 1) {
+                                        // EA^T lo lies right behind EA^T hi: ONE MMA of N = 64 gives P . EA_hi | P . EA_lo in the
+                                        // two column halves (4 instructions per stage instead of 8; the halves are added at the end)
+                                        mma_tf32(dq, make_desc(ph + ko), make_desc(ehh + ko), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                                    } else {
+                                        mma_tf32(dq, make_desc(ph + ko), make_desc(ehh + ko), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                                        if (rnd == 0) mma_tf32(dq, make_desc(ph + ko), make_desc(ell + ko), idesc, 1u);
+                                    }
                                 }
+                                (void)ell;
                                 mma_commit(&p_empty[q]);
                             }
                         }
@@ -798,11 +805,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
                 // quarter is the only one nobody has waited for yet
                 for (int qq = 0; qq < 4; ++qq) mbar_wait(&p_empty[qq], (it - 1) & 1);
                 tc_fence_after_sync();
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);       // quarter 0, then + 1, 2, 3 in order
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);       // quarter 0 (hi, then lo half), then 1, 2, 3 in order
 #pragma unroll 1
-                for (int qq = 1; qq < 4; ++qq) {
+                for (int hq = 1; hq < 8; ++hq) {
+                    if (DWE_ROUNDS != 1 && (hq & 1)) continue;                 // two rounds: 32-column accumulators in the even slots
                     float w[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(qq * 32), w);
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(hq * 32), w);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += w[i];
                 }
@@ -819,7 +827,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) dwe_tc_kernel(const GatherTcArgs
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 128);
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 
