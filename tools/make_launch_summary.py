@@ -7,7 +7,7 @@ inf = run("profiles/r02_launches_infer_steps3_objects64.csv")
 d = json.load(open(root + "profiles/r02_bench_n1.json"))
 lt = open(root + "profiles/r02_layer_times.txt").read()
 md = ["# Round 2 launch summary (B200, final build)\n"]
-md.append("Sources: `profiles/r02_launches_train_steps3_objects64.csv` / `r02_launches_infer_steps3_objects64.csv` = `ncu --metrics gpu__time_duration.sum --clock-control none --csv` of `tools/step_once.py 64 3 [infer]` (3 eager steps of the bench's configs[1] batch, 1 208 829 cells, incl. the one-off graph layout launches; per-launch times are cold-cache and serialised, so the SHARES are what agrees with the live bench, not the absolutes); `profiles/r02_ncu_layer_kernels.csv` = `ncu --set full` of `tools/exp_layer_one.py` per layer shape (DRAM bytes, unit utilisation per kernel); `profiles/r02_layer_times.txt` = the same kernels timed with CUDA events (no profiler); `profiles/r02_bench_n1.json` = `python bench.py`; `profiles/r02_bench_n{2,4,8}.json` = the partitioned runs; `profiles/r02_sass_histogram.txt` = SASS opcodes per kernel. (The launch lists and the ncu table were captured one commit before the gather kernels' row-contiguous output stores, -3 % on those two kernels.)\n")
+md.append("Sources: `profiles/r02_launches_train_steps3_objects64.csv` / `r02_launches_infer_steps3_objects64.csv` = `ncu --metrics gpu__time_duration.sum --clock-control none --csv` of `tools/step_once.py 64 3 [infer]` (3 eager steps of the bench's configs[1] batch, 1 208 829 cells, incl. the one-off graph layout launches; per-launch times are cold-cache and serialised, so the SHARES are what agrees with the live bench, not the absolutes); `profiles/r02_ncu_layer_kernels.csv` = `ncu --set full` of `tools/exp_layer_one.py` per layer shape (DRAM bytes, unit utilisation per kernel); `profiles/r02_layer_times.txt` = the same kernels timed with CUDA events (no profiler); `profiles/r02_bench_n1.json` = `python bench.py`; `profiles/r02_bench_n{2,4,8}.json` = the partitioned runs; `profiles/r02_sass_histogram.txt` = SASS opcodes per kernel.\n")
 md.append("## Live bench (CUDA events, no profiler)\n")
 md.append("* step %.2f ms = %.3e cells/s resident (CUDA graph replay; eager %.2f ms), e2e %.3e cells/s (%.2f ms per step, %d MB uploaded per step), step_hbm_frac %.4f" % (d["ms_per_step"], d["value"], d["ms_per_step_eager"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["h2d_bytes_per_step"] // 10**6, d["step_hbm_frac"]))
 r = d["roofline"]
