@@ -6,7 +6,9 @@ Same constructor (``SurfaceNet(n_node_features, clf)``, ``Updated:191-210``), mo
 ``forward(data_all)`` contract (``Updated:216-251``).  The reference's three inference methods call
 the conv without ``edge_attr`` and raise; they are not provided.
 
-Per layer (edge state materialised as ``[E, F_in]``, as the reference does, ``Updated:236``):
+Per layer (edge state materialised as ``[E, F_in]``, as the reference does, ``Updated:236``; when every layer gets the
+same adjacency - a whole graph as the batch - the state stays in (target, slot) order from layer to layer and the
+scatter to / gather from global edge-id order, 3 passes over ``[E, F]`` per layer and direction, is skipped):
   e'  = lin_e(relu?(e_prev[e_id, :edge_in]))      dgnn_dense_fwd_tc / dgnn_layer_fwd over the edge rows
   agg = mean_k relu?(x_src) (*) e'                 dgnn_gather_phi_fwd
   out = lin_l(agg) + lin_r(x_tgt)                  dgnn_dense_fwd_tc / dgnn_layer_fwd
@@ -149,6 +151,10 @@ def _layer_plan(net, adj, dev, need_backward):
         row_of_edge[flat[ok].long()] = torch.arange(flat.numel(), dtype=torch.int32, device=dev)[ok]
         eo = g._eid_out
         orow = torch.where(eo >= 0, row_of_edge[eo.clamp(min=0).long()], torch.full_like(eo, -1)).contiguous()
+    # chain shortcut (see _forward): when consecutive layers share this plan and every (target, slot) carries an edge, the
+    # edge state stays in incoming order from layer to layer; `ident` is the edge-id table of that order
+    g._upd_all_valid = bool((eid_glob >= 0).all().item())
+    g._upd_ident = torch.arange(eid_glob.numel(), dtype=torch.int32, device=dev).view_as(eid_glob) if g._upd_all_valid else None
     if len(cache) > 16:
         cache.clear()
     cache[key] = ((g, eid_glob, orow), (edge_index, e_id))      # the entry keeps the keyed tensors alive
@@ -165,15 +171,26 @@ def _forward(net, data_all, dev, sv, comm=None):
     e_all = data_all.edge_attr.shape[0]
     e_state = pad_cols(data_all.edge_attr[:, :2].to(dev, dtype=torch.float32), 4)   # layer 0 reads 2 columns
     relu_in = False
+    plans = [_layer_plan(net, data_all.adjs[i], dev, sv is not None) for i in range(len(net.convs))]
+    # Whole-graph batches pass the SAME adjacency to every layer (Updated:216-251 with one edge_index): then layer i + 1
+    # reads, for every (target, slot), exactly the row layer i has just written for it, and the detour through the edge
+    # state in global edge-id order (zero-fill + scatter here, gather there: 3 passes over [E, F] per layer, again in the
+    # backward) is the identity.  `chained[i]`: layer i takes its edge rows straight from layer i - 1.
+    chained = [i > 0 and plans[i][1] is plans[i - 1][1] and plans[i][0]._upd_all_valid for i in range(len(net.convs))]
+    e_prev = None
     for i, conv in enumerate(net.convs):
         edge_index, e_id, size = data_all.adjs[i]
-        g, eid_glob, orow = _layer_plan(net, data_all.adjs[i], dev, sv is not None)
+        g, eid_glob, orow = plans[i]
         n_tgt = size[1]
         fi, fo = pad4(conv.in_channels), conv.out_channels
-        k_in = e_state.shape[1]
-        # rows of the edge state for every (target, slot): global edge id = e_id[local edge id]
-        ea = torch.empty((n_tgt * 4, k_in), dtype=torch.float32, device=dev)
-        call("dgnn_gather_rows", ptr(e_state), ptr(eid_glob), n_tgt * 4, k_in, ptr(ea), _stream())
+        if chained[i]:
+            ea = e_prev
+            k_in = ea.shape[1]
+        else:
+            k_in = e_state.shape[1]
+            # rows of the edge state for every (target, slot): global edge id = e_id[local edge id]
+            ea = torch.empty((n_tgt * 4, k_in), dtype=torch.float32, device=dev)
+            call("dgnn_gather_rows", ptr(e_state), ptr(eid_glob), n_tgt * 4, k_in, ptr(ea), _stream())
         w_e = engine._pad2(conv.lin_e.weight.detach(), fi, k_in).contiguous()
         b_e = engine._pad1(conv.lin_e.bias.detach(), fi).contiguous()
         e_new = _dense(ea, relu_in, w_e, b_e, n_tgt * 4, k_in, fi)            # pre-ReLU e' (Updated:157)
@@ -192,11 +209,14 @@ def _forward(net, data_all, dev, sv, comm=None):
             s.g, s.eid_glob, s.ea, s.phi, s.agg, s.x_in, s.out = g, eid_glob, ea, e_new, agg, x, out
             s.relu_in, s.w_e, s.w_cat, s.fi, s.fo, s.k_in, s.e_all = relu_in, w_e, w_cat, fi, fo, k_in, e_all
             s.orow = orow          # row 4t+k of e' for every out-edge (s,j)
+            s.chained = chained[i]  # this layer's edge rows ARE the previous layer's e' (gradient flows back row by row)
             sv.append(s)
         x = out
-        # new edge state, indexed by global edge id; edges outside this hop stay 0 (Updated:236-238)
-        e_state = torch.zeros((e_all, fi), dtype=torch.float32, device=dev)
-        call("dgnn_scatter_rows", ptr(e_new), ptr(eid_glob), n_tgt * 4, fi, ptr(e_state), _stream())
+        e_prev = e_new
+        if i + 1 < len(net.convs) and not chained[i + 1]:
+            # new edge state, indexed by global edge id; edges outside this hop stay 0 (Updated:236-238)
+            e_state = torch.zeros((e_all, fi), dtype=torch.float32, device=dev)
+            call("dgnn_scatter_rows", ptr(e_new), ptr(eid_glob), n_tgt * 4, fi, ptr(e_state), _stream())
         relu_in = True                                                        # x, e <- relu (applied on load)
     if net._has_head():
         n = data_all.adjs[len(net.convs) - 1][2][1]
@@ -251,6 +271,7 @@ class _UpdFn(torch.autograd.Function):
                 call("dgnn_relu_mask", ptr(d_relu_x), ptr(s.x_in), d_relu_x.numel(), ptr(d_out), st)
                 head_grads = [dw1, db1, dw3, db3]
             de_next = None
+            de_chained = False     # de_next is in the incoming order of the layer below (chain shortcut), not by global edge id
             layer_grads = []
             for i in range(len(net.convs) - 1, -1, -1):
                 s, conv = sv[i], net.convs[i]
@@ -259,7 +280,7 @@ class _UpdFn(torch.autograd.Function):
                                                                    s.x_in, None, s.relu_in, n_tgt, fi, fo)
                 dphi = torch.empty((n_tgt * 4, fi), dtype=torch.float32, device=dev)
                 call("dgnn_upd_edge_bwd", ptr(s.x_in), None, None, int(s.relu_in), ptr(g.nbr), ptr(d_agg), ptr(s.phi),
-                     ptr(de_next), ptr(s.eid_glob), n_tgt, fi, ptr(dphi), st)
+                     ptr(de_next), ptr(g._upd_ident if de_chained else s.eid_glob), n_tgt, fi, ptr(dphi), st)
                 _, d_ea, db_e, dw_e = engine._dense_and_dw(dphi, s.phi, _NOCOEF, _NOAFF, s.w_e, None, None, s.ea, None,
                                                            s.relu_in, n_tgt * 4, s.k_in, fi)
                 ic, ec = conv.in_channels, conv.edge_in_channels
@@ -275,8 +296,12 @@ class _UpdFn(torch.autograd.Function):
                         comm.reverse_add(d_x)
                         d_x = d_x[:sv[i - 1].g.n_tgt]
                     d_out = d_x
-                    de_next = torch.zeros((s.e_all, s.k_in), dtype=torch.float32, device=dev)
-                    call("dgnn_scatter_rows", ptr(d_ea), ptr(s.eid_glob), n_tgt * 4, s.k_in, ptr(de_next), st)
+                    de_chained = s.chained
+                    if s.chained:              # row r of this layer's edge input is row r of the layer below's e'
+                        de_next = d_ea
+                    else:
+                        de_next = torch.zeros((s.e_all, s.k_in), dtype=torch.float32, device=dev)
+                        call("dgnn_scatter_rows", ptr(d_ea), ptr(s.eid_glob), n_tgt * 4, s.k_in, ptr(de_next), st)
             for lg in reversed(layer_grads):
                 grads += lg
             grads += head_grads
